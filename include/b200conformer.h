@@ -1,0 +1,162 @@
+/* b200conformer.h -- C ABI of libb200conformer.so: the sm_100a kernels behind the Conformer-encoder hot path.
+ *
+ * The reference (icadriani/nn_conformer_for_speech_recognition) is pure Python and has no FFI layer
+ * (SURVEY.md R1); its hot path is the set of torch modules listed beside each entry point below.  This header
+ * is the drop-in boundary a maintainer binds with ctypes (INTEGRATION.md shows the stub): plain device
+ * pointers and sizes, no torch types.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work, they never synchronise;
+ *   - return 0 on success, <0 for a rejected argument, >0 = cudaError_t; b2c_last_error() explains (thread-local);
+ *   - activations are token-major: row = b*T + t, features contiguous; bf16 unless stated; statistics fp32.
+ */
+#ifndef B200CONFORMER_H_
+#define B200CONFORMER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2C_VERSION 1
+
+enum { B2C_BF16 = 0, B2C_F32 = 1 };
+enum { B2C_ACT_NONE = 0, B2C_ACT_SILU = 1, B2C_ACT_SILU_BWD = 2 };
+
+const char* b2c_last_error(void);
+int b2c_version(void);
+/* fails (returns <0) unless the current CUDA device is compute capability 10.x -- there is no fallback path */
+int b2c_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * GEMM  D[M,N] = epi(A * B^T), bf16 x bf16 -> fp32 (tcgen05.mma, accumulators in TMEM, operands by TMA).
+ * Replaces torch.nn.Linear / Conv1d(kernel 1) + the elementwise ops around them:
+ *   FFN   torchaudio/models/conformer.py:102-109 (Linear+SiLU, Linear) and the 0.5*x+residual at :186-187,208-209
+ *   MHSA  in/out projections, torch/nn/functional.py:5798,6690 (called from conformer.py:194-200)
+ *   conv module pointwise convs, conformer.py:44-51,66-73
+ * a_mn / b_mn: 0 = the operand is [rows][K] with K contiguous; 1 = it is stored [K][rows] (rows contiguous).
+ *   forward (0,0) with B = weight (out,in);  dX = dY*W is (0,1) with B = W;  dW = dY^T*X is (1,1).
+ * epilogue, in this order:  v = acc (+ bias[n]);  out2 = bf16(v) if out2;  v = act(v);  v *= dropout(seed, m*N+n);
+ *                           v *= alpha;  then  out = bf16(v) | out = v + resid (fp32) | atomicAdd(out, v) (fp32).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct b2c_epilogue {
+  const void* bias;   /* fp32 [N] or NULL */
+  const void* aux;    /* bf16 [M, ld_aux]: pre-activation for B2C_ACT_SILU_BWD, else NULL */
+  const void* resid;  /* fp32 [M, ld_out] added to an fp32 output (may alias out), or NULL */
+  void* out;          /* bf16 or fp32 [M, ld_out] */
+  void* out2;         /* optional bf16 [M, ld_out2] copy of acc+bias (saved pre-activation) */
+  int64_t ld_out, ld_out2, ld_aux;
+  float alpha;
+  float drop_p;       /* 0 = no dropout */
+  uint64_t drop_seed;
+  int act;            /* B2C_ACT_* */
+  int out_dtype;      /* B2C_BF16 | B2C_F32 */
+  int accumulate;     /* 1: fp32 atomicAdd into out (split-K / gradient accumulation) */
+  int reserved;
+} b2c_epilogue;
+
+int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M, int64_t N,
+                  int64_t K, int split_k, int block_n, const b2c_epilogue* ep, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (biased variance, eps) -- torch.nn.LayerNorm at conformer.py:42,103,151,165.
+ * x fp32 [rows,d] -> y (bf16 or fp32); mean/rstd fp32 [rows] optional (saved for backward).
+ * bwd: dx (+)= LN'(dy); dgamma/dbeta fp32 [d] are ACCUMULATED (atomicAdd) -- zero them first.
+ * ------------------------------------------------------------------------------------------------------- */
+int b2c_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype, float* mean,
+                      float* rstd, int64_t rows, int d, float eps, void* stream);
+int b2c_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
+                      const float* rstd, float* dx, int dx_accumulate, float* dgamma, float* dbeta, int64_t rows, int d,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Conv-module chain  GLU -> depthwise conv1d('same', cross-correlation) -> BatchNorm1d -> SiLU
+ * (conformer.py:52-65; frames past `lengths` are NOT zeroed, conformer.py:85-88).
+ *   u   bf16 [B*T, 2d]  pointwise-conv-1 output (first d channels are gated by sigmoid of the last d)
+ *   wdw fp32 [d,k] (= sequential.2.weight[:,0,:]), bdw fp32 [d]
+ * eval : out = SiLU(BN_running(dw(GLU(u))))           one kernel
+ * train: _dw writes y = dw(GLU(u)) (bf16) and accumulates per-channel sum / sum-of-squares (fp64 [2*d], zeroed
+ *        by the caller); _bn_finalize turns them into mean/rstd, updates running stats (momentum, unbiased var);
+ *        _bn_apply writes SiLU(BN_batch(y)).
+ * ------------------------------------------------------------------------------------------------------- */
+int b2c_convmod_eval_fwd(const void* u, const float* wdw, const float* bdw, const float* bn_w, const float* bn_b,
+                         const float* bn_mean, const float* bn_var, float eps, void* out, int B, int T, int d, int k,
+                         void* stream);
+int b2c_convmod_dw_fwd(const void* u, const float* wdw, const float* bdw, void* y, double* stats, int B, int T, int d,
+                       int k, void* stream);
+int b2c_convmod_bn_finalize(const double* stats, int64_t count, float eps, float momentum, float* mean, float* rstd,
+                            float* running_mean, float* running_var, int d, void* stream);
+int b2c_convmod_bn_apply(const void* y, const float* mean, const float* rstd, const float* bn_w, const float* bn_b,
+                         void* out, int64_t rows, int d, void* stream);
+/* ---------------------------------------------------------------------------------------------------------
+ * Multi-head self-attention core, flash style: softmax(Q K^T * scale + key-length mask) V per (batch, head).
+ * Replaces scaled_dot_product_attention as reached from nn.MultiheadAttention (torch/nn/functional.py:6608-6682,
+ * conformer.py:152,194-200).  Keys t >= lengths[b] are masked; padded QUERY rows are still computed.
+ *   qkv  bf16 [B*T, ld]: head h of Q at column h*64, K at k_off + h*64, V at v_off + h*64 (head dim padded to 64)
+ *   out  bf16 [B*T, ld_out], head h at column h*64;   lse fp32 [B,H,T] (log2 domain), may be NULL in eval
+ *   dropout on the probabilities (train only): p_drop / seed, regenerated identically by the backward kernel.
+ * ------------------------------------------------------------------------------------------------------- */
+int b2c_attention_fwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths, void* out,
+                      int64_t ld_out, float* lse, int B, int T, int H, float scale, float drop_p, uint64_t drop_seed,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * ConvSubSampling (/root/reference/lib/convsubsampling.py:16-45): conv_sub_2(conv_sub_1(x)), no activation
+ * between, valid padding.  Executed as the exact composition Conv2d(1->C2, kc x kc, stride s1*s2) with
+ * kc = k1 + (k2-1)*s1: _compose builds Wc (bf16 [C2, KP], KP = kc*kc rounded up to 64)
+ * and bc (fp32 [C2]) from the module's own parameters; _fwd is an implicit GEMM on tcgen05.
+ *   x   fp32 [B, F, T]         (in_size = 1)
+ *   out [B, T', F', C2] token-major (row (b*T'+t')*F'+f', channels contiguous), bf16 (out_f32=0) or fp32 (1);
+ *       the reference module's (B, C2, F', T') return value is the permuted VIEW of the fp32 form.
+ * _compose_bwd maps dWc/dbc (fp32 [C2,KP] / [C2]) back to dW1, db1, dW2, db2 (accumulating); _wgrad accumulates dWc.
+ * ------------------------------------------------------------------------------------------------------- */
+int b2c_convsub_compose(const float* W1, const float* b1, const float* W2, const float* b2, int C1, int C2, int k1,
+                        int s1, int k2, void* Wc, float* Wc_f32, float* bc, int KP, void* stream);
+int b2c_convsub_fwd(const float* x, const void* Wc, const float* bc, void* out, int out_f32, int B, int F, int T,
+                    int C2, int kc, int stride, int KP, void* stream);
+/* dWc fp32 [C2,KP] += dout^T * im2col(x); dout bf16 token-major [B*T', F'*C2]. (dbc = column sums: b2c_colsum_bf16) */
+int b2c_convsub_wgrad(const float* x, const void* dout, float* dWc, int B, int F, int T, int C2, int kc, int stride,
+                      int KP, void* stream);
+int b2c_convsub_compose_bwd(const float* dWc, const float* dbc, const float* W1, const float* b1, const float* W2,
+                            int C1, int C2, int k1, int s1, int k2, int KP, float* dW1, float* db1, float* dW2,
+                            float* db2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * SpecAugment (/root/reference/lib/standard/asrnn.py:91-192): time-warp gather + frequency / time masks in one
+ * pass.  The random draws stay on the host (CPython `random` stream, bit-exact: b2c_mt19937_*); the kernel gets
+ * the drawn parameters.
+ *   x, out fp32 [B,F,T];  tau int32 [B]
+ *   warp_w, warp_w0 int32 [n_warp, B]  (w, w0 of asrnn.py:103-107), composed in call order
+ *   fmask int32 [n_fmask, 2] = (f0, f);  tmask int32 [n_tmask, B, 2] = (t0, t)
+ *   apply_masks 0 = "reference" mode (the reference's masks are no-ops), 1 = "paper" mode
+ * ------------------------------------------------------------------------------------------------------- */
+int b2c_specaug_apply(const float* x, float* out, const int32_t* tau, const int32_t* warp_w, const int32_t* warp_w0,
+                      int n_warp, const int32_t* fmask, int n_fmask, const int32_t* tmask, int n_tmask,
+                      int apply_masks, float mask_value, int B, int F, int T, void* stream);
+
+/* CPython-compatible MT19937 (host): seed(int) via init_by_array, randint via the bit_length rejection loop
+ * (/usr/lib/python3.12/random.py:242-249,318,336).  state_host: 625 uint32 words owned by the caller. */
+void b2c_mt19937_seed_host(uint32_t* state_host, uint64_t seed);
+int64_t b2c_mt19937_randint_host(uint32_t* state_host, int64_t a, int64_t b);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Small memory-bound helpers
+ * ------------------------------------------------------------------------------------------------------- */
+/* multi-tensor fp32 -> bf16 cast; optional zero padding of rows/cols (pads attention heads to 64):
+ *   dst[r_dst(r), c] with r in [0,rows), src row pitch = cols, dst pitch = dst_cols >= cols */
+int b2c_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* dst bf16 [rows, cols] = alpha * dropout(src fp32 [rows, cols]) -- gradient of  x + alpha*drop(y)  wrt y */
+int b2c_scale_cast(const float* src, void* dst, int64_t rows, int64_t cols, float alpha, float drop_p,
+                   uint64_t drop_seed, void* stream);
+/* out fp32 [cols] += column sums of a bf16 [rows, ld] matrix (bias gradients) */
+int b2c_colsum_bf16(const void* a, int64_t ld, int64_t rows, int64_t cols, float* out, void* stream);
+/* pads / unpads per-head columns:  dst[r, h*dst_dh + c] = src[r, h*src_dh + c] (zero fill), nblk = blocks per row */
+int b2c_repack_heads(const void* src, void* dst, int64_t rows, int nblk, int src_dh, int dst_dh, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CONFORMER_H_ */

@@ -1,0 +1,120 @@
+"""ctypes binding of libb200conformer.so (the C ABI declared in include/b200conformer.h).
+
+There is NO fallback: if the shared library is missing, or the current device is not sm_100, every entry point
+raises.  torch is used only for device memory and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200conformer.so")
+
+BF16, F32 = 0, 1
+ACT_NONE, ACT_SILU, ACT_SILU_BWD = 0, 1, 2
+
+
+class B2CError(RuntimeError):
+    pass
+
+
+class Epilogue(Structure):
+    _fields_ = [("bias", c_void_p), ("aux", c_void_p), ("resid", c_void_p), ("out", c_void_p), ("out2", c_void_p),
+                ("ld_out", c_int64), ("ld_out2", c_int64), ("ld_aux", c_int64), ("alpha", c_float), ("drop_p", c_float),
+                ("drop_seed", c_uint64), ("act", c_int), ("out_dtype", c_int), ("accumulate", c_int), ("reserved", c_int)]
+
+
+_P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
+# name -> argtypes ; every function returns int unless listed in _RESTYPES
+SIGNATURES = {
+    "b2c_version": [],
+    "b2c_device_check": [],
+    "b2c_gemm_bf16": [_P, _L, _I, _P, _L, _I, _L, _L, _L, _I, _I, POINTER(Epilogue), _P],
+    "b2c_layernorm_fwd": [_P, _P, _P, _P, _I, _P, _P, _L, _I, _F, _P],
+    "b2c_layernorm_bwd": [_P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],
+    "b2c_convmod_eval_fwd": [_P, _P, _P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _P],
+    "b2c_convmod_dw_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "b2c_convmod_bn_finalize": [_P, _L, _F, _F, _P, _P, _P, _P, _I, _P],
+    "b2c_convmod_bn_apply": [_P, _P, _P, _P, _P, _P, _L, _I, _P],
+    "b2c_attention_fwd": [_P, _L, _L, _L, _P, _P, _L, _P, _I, _I, _I, _F, _F, c_uint64, _P],
+    "b2c_convsub_compose": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
+    "b2c_convsub_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "b2c_convsub_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "b2c_convsub_compose_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "b2c_specaug_apply": [_P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _F, _I, _I, _I, _P],
+    "b2c_cast_f32_bf16": [_P, _P, _L, _P],
+    "b2c_scale_cast": [_P, _P, _L, _L, _F, _F, c_uint64, _P],
+    "b2c_colsum_bf16": [_P, _L, _L, _L, _P, _P],
+    "b2c_repack_heads": [_P, _P, _L, _I, _I, _I, _P],
+}
+HOST_SIGNATURES = {
+    "b2c_last_error": ([], c_char_p),
+    "b2c_mt19937_seed_host": ([POINTER(c_uint32), c_uint64], None),
+    "b2c_mt19937_randint_host": ([POINTER(c_uint32), c_int64, c_int64], c_int64),
+}
+
+_lib = None
+LAUNCHES = 0          # kernels launched through this binding (bench.py reports it as gpu_launches)
+_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 2, "b2c_convsub_compose_bwd": 2, "b2c_version": 0, "b2c_device_check": 0}
+
+
+def load() -> ctypes.CDLL:
+    """Loads the library (once).  Raises B2CError when it has not been built -- there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B2CError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(or `make -C nn_conformer_for_speech_recognition_b200/csrc`). There is no CPU/PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    for name, (args, res) in HOST_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().b2c_last_error().decode()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point on the current torch stream; raise with the library's message on error."""
+    global LAUNCHES
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        kind = ValueError if rc < 0 else B2CError
+        raise kind(f"{name} failed (rc={rc}): {last_error()}")
+    LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
+
+
+_checked = False
+
+
+def require_device() -> None:
+    """Fail loudly unless a CUDA device of compute capability 10.x is current."""
+    global _checked
+    if _checked:
+        return
+    if not torch.cuda.is_available():
+        raise B2CError("nn_conformer_for_speech_recognition_b200 needs a B200 (sm_100a) GPU; CUDA is not available "
+                       "and there is no CPU fallback")
+    call("b2c_device_check")
+    _checked = True
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()

@@ -1,0 +1,244 @@
+// Flash-style multi-head self-attention on tcgen05 / TMEM / TMA (sm_100a), head dim 64 (smaller heads are
+// zero-padded to 64 by the host side).
+//
+// Replaces scaled_dot_product_attention reached from nn.MultiheadAttention (torch/nn/functional.py:6608-6682),
+// called by torchaudio ConformerLayer (conformer.py:152,194-200): softmax(Q K^T / sqrt(dh) + key mask) V where
+// keys t >= lengths[b] are masked and padded QUERY rows are still computed.
+//
+// Forward, one CTA = (128-query tile, head, utterance), 128 threads, thread r <-> query row r <-> TMEM lane r:
+//   TMA   Q tile once, then per 128-key block K_j, V_j                       (128B-swizzled smem)
+//   UMMA  S = Q K_j^T          (M128 N128 K16 x4, both operands K-major)      -> TMEM cols [0,128)
+//   regs  online softmax on the thread's row (tcgen05.ld), P -> smem as bf16 in the K-major SW128 UMMA layout
+//   UMMA  O_j = P V_j          (M128 N64 K16 x8, A K-major, B MN-major = V as loaded) -> TMEM cols [128,192)
+//   regs  o = o*alpha + O_j    (running output stays in registers; no TMEM rescale pass)
+// Key blocks past lengths[b] are skipped entirely.  80 KB smem and 256 TMEM columns per CTA -> 2 CTAs per SM, so
+// one CTA's softmax overlaps the other's MMAs/TMA.
+//
+// Backward = two kernels that recompute S/P from the saved log-sum-exp (no T x T tensor ever reaches HBM):
+//   attn_bwd_dkv : CTA = (key block, head, utterance), loops over query blocks: dV += P^T dO, dK += dS^T Q
+//   attn_bwd_dq  : CTA = (query block, head, utterance), loops over key blocks:   dQ += dS K
+// with dS = P o (dP - delta) * scale, dP = dO V^T, delta = rowsum(dO o O) (attn_delta kernel).
+#include "common.cuh"
+#include "b200conformer.h"
+
+namespace b2c {
+
+constexpr int AT_BQ = 128;   // query rows per tile
+constexpr int AT_BK = 128;   // keys per block
+constexpr int AT_DH = 64;
+constexpr float LOG2E = 1.4426950408889634f;
+
+// byte offset of element (row, col) inside a K-major SWIZZLE_128B bf16 tile made of 64-column blocks of
+// [rows][128 B]; `rows` = rows per block.  16-byte chunk index is XORed with (row & 7).
+__device__ __forceinline__ uint32_t sw128_offset(int row, int col, int rows) {
+  const int blk = col >> 6, cc = col & 63;
+  return static_cast<uint32_t>(blk * rows * 128 + row * 128 + ((((cc >> 3) ^ (row & 7)) << 4) | ((cc & 7) << 1)));
+}
+
+struct AttnParams {
+  const int32_t* lengths;
+  __nv_bfloat16* out;
+  float* lse;
+  int64_t ld_out;
+  int B, T, H;
+  int q_col, k_col, v_col;     // column offsets (elements) of head 0 inside a qkv row
+  float scale_log2;            // scale * log2(e)
+  uint32_t drop_thresh;
+  float inv_keep;
+  uint64_t drop_seed;
+};
+
+__global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sQ = smem;                 // 16 KB  [128 q][64]
+  uint8_t* sK = smem + 16384;         // 16 KB  [128 keys][64]
+  uint8_t* sV = smem + 32768;         // 16 KB  [128 keys][64]
+  uint8_t* sP = smem + 49152;         // 32 KB  2 x [128 q][64 keys]
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + 81920);
+  uint64_t* bar_kv = bar_q + 1;
+  uint64_t* bar_s = bar_q + 2;
+  uint64_t* bar_o = bar_q + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
+  const int len = min(p.lengths[b], p.T);
+  const int nkb = (len + AT_BK - 1) / AT_BK;
+  const int row_base = b * p.T;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 256); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, 16384);
+    tma_load_2d(sQ, &tmQKV, bar_q, p.q_col + h * AT_DH, row_base + q0);
+  }
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
+
+  float o[AT_DH];
+#pragma unroll
+  for (int i = 0; i < AT_DH; ++i) o[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+  const int q_idx = q0 + tid;                           // query position inside the utterance
+  const uint64_t drop_row = (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.T;
+
+  for (int j = 0; j < nkb; ++j) {
+    const uint32_t ph = j & 1;
+    if (tid == 0) {
+      mbar_expect_tx(bar_kv, 32768);
+      tma_load_2d(sK, &tmQKV, bar_kv, p.k_col + h * AT_DH, row_base + j * AT_BK);
+      tma_load_2d(sV, &tmQKV, bar_kv, p.v_col + h * AT_DH, row_base + j * AT_BK);
+      if (j == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < AT_DH / 16; ++k)
+        umma_bf16(tmem_base, umma_desc_sw128(base + k * 32, 16, 1024), umma_desc_sw128(base + 16384 + k * 32, 16, 1024),
+                  idesc_s, k > 0 ? 1u : 0u);
+      tc_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+
+    // ---- online softmax on this thread's row ----
+    const int key0 = j * AT_BK;
+    float m_blk = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < AT_BK; c += 32) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(tm_lane + c, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (key0 + c + i < len) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+    }
+    const float m_new = fmaxf(m_run, m_blk * p.scale_log2);
+    const float alpha = exp2f(m_run - m_new);           // first block: exp2(-inf) = 0
+    float l_blk = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < AT_BK; c += 32) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(tm_lane + c, v);
+      tmem_wait_ld();
+      float pr[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e = (key0 + c + i < len) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new) : 0.f;
+        l_blk += e;
+        pr[i] = e;
+      }
+      if (p.drop_thresh) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          pr[i] *= drop_scale(p.drop_seed, drop_row + key0 + c + i, p.drop_thresh, p.inv_keep);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint4 u = make_uint4(pack_bf16(pr[g * 8], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
+                                   pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
+        *reinterpret_cast<uint4*>(sP + sw128_offset(tid, c + g * 8, 128)) = u;
+      }
+    }
+    l_run = l_run * alpha + l_blk;
+    m_run = m_new;
+#pragma unroll
+    for (int i = 0; i < AT_DH; ++i) o[i] *= alpha;
+
+    fence_proxy_async();          // P (generic-proxy stores) -> visible to the UMMA async proxy
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < AT_BK / 16; ++k)
+        umma_bf16(tmem_base + 128, umma_desc_sw128(base + 49152 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                  umma_desc_sw128(base + 32768 + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+      tc_commit(bar_o);
+    }
+    mbar_wait(bar_o, ph);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < AT_DH; c += 32) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(tm_lane + 128 + c, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(v[i]);
+    }
+    tc_fence_before();
+    __syncthreads();              // sK/sV/sP and both TMEM regions are free for the next block
+  }
+
+  // len == 0 -> l_run == 0 -> 0/0 = NaN, the same value torch's softmax over an all-masked row gives
+  if (q_idx < p.T) {
+    const float inv_l = 1.f / l_run;
+    __nv_bfloat16* dst = p.out + static_cast<int64_t>(row_base + q_idx) * p.ld_out + h * AT_DH;
+#pragma unroll
+    for (int g = 0; g < AT_DH / 8; ++g) {
+      const uint4 u = make_uint4(pack_bf16(o[g * 8] * inv_l, o[g * 8 + 1] * inv_l),
+                                 pack_bf16(o[g * 8 + 2] * inv_l, o[g * 8 + 3] * inv_l),
+                                 pack_bf16(o[g * 8 + 4] * inv_l, o[g * 8 + 5] * inv_l),
+                                 pack_bf16(o[g * 8 + 6] * inv_l, o[g * 8 + 7] * inv_l));
+      *reinterpret_cast<uint4*>(dst + g * 8) = u;
+    }
+    if (p.lse) p.lse[static_cast<int64_t>(b * p.H + h) * p.T + q_idx] = m_run + log2f(l_run);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+constexpr uint32_t ATTN_FWD_SMEM = 81920 + 64 + 1024;
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_attention_fwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
+                                 void* out, int64_t ld_out, float* lse, int B, int T, int H, float scale, float drop_p,
+                                 uint64_t drop_seed, void* stream) {
+  B2C_REQUIRE(qkv && lengths && out, "b2c_attention_fwd: null pointer");
+  B2C_REQUIRE(B > 0 && T > 0 && H > 0, "b2c_attention_fwd: empty problem");
+  B2C_REQUIRE(ld % 8 == 0 && ld_out % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
+              "b2c_attention_fwd: pitches/offsets must be multiples of 8 elements");
+  B2C_REQUIRE(static_cast<int64_t>(B) * T < (1ll << 31), "b2c_attention_fwd: B*T too large");
+  CUtensorMap tm;
+  int rc = get_tensor_map_2d(&tm, qkv, 2, static_cast<uint64_t>(ld), static_cast<uint64_t>(B) * T, ld * 2, 64, 128, true);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    B2C_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_FWD_SMEM));
+    configured = true;
+  }
+  AttnParams p;
+  p.lengths = lengths; p.out = static_cast<__nv_bfloat16*>(out); p.lse = lse; p.ld_out = ld_out;
+  p.B = B; p.T = T; p.H = H;
+  p.q_col = 0; p.k_col = static_cast<int>(k_off); p.v_col = static_cast<int>(v_off);
+  p.scale_log2 = scale * LOG2E;
+  p.drop_thresh = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+  p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.drop_seed = drop_seed;
+  dim3 grid((T + AT_BQ - 1) / AT_BQ, H, B);
+  attn_fwd_kernel<<<grid, 128, ATTN_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}

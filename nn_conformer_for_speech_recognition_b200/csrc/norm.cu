@@ -1,0 +1,318 @@
+// LayerNorm forward / backward and small memory-bound helpers (HBM/L2-bound, warp-shuffle reductions).
+// Replaces torch.nn.LayerNorm at torchaudio/models/conformer.py:42,103,151,165 (5 per layer).
+//
+// One warp per row: a row of d <= 1024 fp32 lives in registers as float4 chunks (chunk index = lane + 32*i),
+// so global accesses are 512-byte coalesced per warp instruction; statistics use the two-pass formula
+// (mean, then centred sum of squares) entirely in registers -- x is read from HBM exactly once.
+// Algorithmic bytes per row: fwd 4d (read) + 2d or 4d (write); bwd 4d (x) + 2d/4d (dy) + 4d (+4d when accumulating).
+#include "common.cuh"
+#include "b200conformer.h"
+
+namespace b2c {
+
+constexpr int LN_MAXV = 8;        // float4 chunks per lane -> d <= 1024
+constexpr int LN_WARPS = 8;
+
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const float* __restrict__ x,
+                                                                      const float* __restrict__ gamma,
+                                                                      const float* __restrict__ beta, void* __restrict__ y,
+                                                                      float* __restrict__ mean_out,
+                                                                      float* __restrict__ rstd_out, int64_t rows, int d,
+                                                                      float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = d >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+  float4 v[LN_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      v[i] = xr[c];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(s) / d;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, e = v[i].w - mean;
+      ss += a * a + b * b + cc * cc + e * e;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / d + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if constexpr (OUT_BF16) {
+        reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(y) + row * d)[c] =
+            make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      } else {
+        reinterpret_cast<float4*>(static_cast<float*>(y) + row * d)[c] = o;
+      }
+    }
+  }
+}
+
+// dx = rstd * (g - mean_d(g) - xhat * mean_d(g*xhat)),  g = dy*gamma ; dgamma += dy*xhat ; dbeta += dy
+template <bool DY_BF16>
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const void* __restrict__ dy,
+                                                                      const float* __restrict__ x,
+                                                                      const float* __restrict__ gamma,
+                                                                      const float* __restrict__ mean_in,
+                                                                      const float* __restrict__ rstd_in,
+                                                                      float* __restrict__ dx, int accumulate,
+                                                                      float* __restrict__ dgamma,
+                                                                      float* __restrict__ dbeta, int64_t rows, int d,
+                                                                      int rows_per_warp) {
+  extern __shared__ float red[];           // [2][d] per-block partial dgamma / dbeta
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = d >> 2;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float4 dg[LN_MAXV], db[LN_MAXV];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp) * rows_per_warp;
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const int64_t row = row0 + rr;
+    if (row >= rows) break;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+    float4 xh[LN_MAXV], g[LN_MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        const float4 xv = xr[c];
+        float4 dyv;
+        if constexpr (DY_BF16) {
+          const uint2 u = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(dy) + row * d)[c];
+          const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+          dyv = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+          dyv = reinterpret_cast<const float4*>(static_cast<const float*>(dy) + row * d)[c];
+        }
+        const float4 gm = __ldg(g4 + c);
+        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        g[i] = make_float4(dyv.x * gm.x, dyv.y * gm.y, dyv.z * gm.z, dyv.w * gm.w);
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+        dg[i].x += dyv.x * xh[i].x; dg[i].y += dyv.y * xh[i].y; dg[i].z += dyv.z * xh[i].z; dg[i].w += dyv.w * xh[i].w;
+        db[i].x += dyv.x; db[i].y += dyv.y; db[i].z += dyv.z; db[i].w += dyv.w;
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+    float4* dxr = reinterpret_cast<float4*>(dx + row * d);
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        float4 o;
+        o.x = rstd * (g[i].x - s1 - xh[i].x * s2);
+        o.y = rstd * (g[i].y - s1 - xh[i].y * s2);
+        o.z = rstd * (g[i].z - s1 - xh[i].z * s2);
+        o.w = rstd * (g[i].w - s1 - xh[i].w * s2);
+        if (accumulate) {
+          const float4 p = dxr[c];
+          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        dxr[c] = o;
+      }
+    }
+  }
+  // block-level reduction of the parameter gradients, then one atomic per channel per block
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      atomicAdd(&red[4 * c + 0], dg[i].x); atomicAdd(&red[4 * c + 1], dg[i].y);
+      atomicAdd(&red[4 * c + 2], dg[i].z); atomicAdd(&red[4 * c + 3], dg[i].w);
+      atomicAdd(&red[d + 4 * c + 0], db[i].x); atomicAdd(&red[d + 4 * c + 1], db[i].y);
+      atomicAdd(&red[d + 4 * c + 2], db[i].z); atomicAdd(&red[d + 4 * c + 3], db[i].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(dgamma + i, red[i]);
+    atomicAdd(dbeta + i, red[d + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- helpers
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i);
+    const float4 b = *reinterpret_cast<const float4*>(src + i + 4);
+    *reinterpret_cast<uint4*>(dst + i) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  } else {
+    for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+  }
+}
+
+__global__ void scale_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n,
+                                  float alpha, uint32_t thresh, float inv_keep, uint64_t seed) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;                       // n % 4 == 0 enforced by the host
+  float4 a = *reinterpret_cast<const float4*>(src + i);
+  float f[4] = {a.x * alpha, a.y * alpha, a.z * alpha, a.w * alpha};
+  if (thresh) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f[j] *= drop_scale(seed, static_cast<uint64_t>(i + j), thresh, inv_keep);
+  }
+  *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+}
+
+// column sums of a bf16 matrix: block = 32 x 8 threads, each thread owns 2 adjacent columns over a row slab
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ a, int64_t ld, int64_t rows,
+                                                         int64_t cols, float* __restrict__ out, int rows_per_block) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t col = static_cast<int64_t>(blockIdx.x) * 64 + tx * 2;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  if (col < cols) {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(a + r * ld + col));
+      s0 += v.x; s1 += v.y;
+    }
+  }
+  red[ty][tx * 2] = s0;
+  red[ty][tx * 2 + 1] = s1;
+  __syncthreads();
+  if (ty == 0) {
+    for (int j = 1; j < 8; ++j) { s0 += red[j][tx * 2]; s1 += red[j][tx * 2 + 1]; }
+    if (col < cols) { atomicAdd(out + col, s0); atomicAdd(out + col + 1, s1); }
+  }
+}
+
+__global__ void repack_heads_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows,
+                                    int nblk, int src_dh, int dst_dh) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t per_row = static_cast<int64_t>(nblk) * dst_dh;
+  if (i >= rows * per_row) return;
+  const int64_t r = i / per_row;
+  const int rem = static_cast<int>(i % per_row);
+  const int h = rem / dst_dh, c = rem % dst_dh;
+  dst[i] = c < src_dh ? src[r * nblk * src_dh + h * src_dh + c] : __float2bfloat16(0.f);
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
+                                 float* mean, float* rstd, int64_t rows, int d, float eps, void* stream) {
+  B2C_REQUIRE(x && gamma && beta && y, "b2c_layernorm_fwd: null pointer");
+  B2C_REQUIRE(d % 4 == 0 && d > 0 && d <= 128 * LN_MAXV, "b2c_layernorm_fwd: d=%d must be a multiple of 4, <= 1024", d);
+  if (rows <= 0) return 0;
+  const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (y_dtype == B2C_BF16)
+    layernorm_fwd_kernel<true><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
+  else
+    layernorm_fwd_kernel<false><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2c_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
+                                 const float* rstd, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
+                                 int64_t rows, int d, void* stream) {
+  B2C_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "b2c_layernorm_bwd: null pointer");
+  B2C_REQUIRE(d % 4 == 0 && d > 0 && d <= 128 * LN_MAXV, "b2c_layernorm_bwd: d=%d must be a multiple of 4, <= 1024", d);
+  if (rows <= 0) return 0;
+  // ~4 blocks per SM; each warp walks a contiguous run of rows so parameter-gradient atomics stay rare
+  const int64_t target_warps = static_cast<int64_t>(num_sms()) * 4 * LN_WARPS;
+  int rows_per_warp = static_cast<int>((rows + target_warps - 1) / target_warps);
+  if (rows_per_warp < 1) rows_per_warp = 1;
+  const int64_t warps = (rows + rows_per_warp - 1) / rows_per_warp;
+  const unsigned grid = static_cast<unsigned>((warps + LN_WARPS - 1) / LN_WARPS);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = 2 * d * sizeof(float);
+  if (dy_dtype == B2C_BF16)
+    layernorm_bwd_kernel<true><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma,
+                                                                dbeta, rows, d, rows_per_warp);
+  else
+    layernorm_bwd_kernel<false><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma,
+                                                                 dbeta, rows, d, rows_per_warp);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2c_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  B2C_REQUIRE(src && dst, "b2c_cast_f32_bf16: null pointer");
+  if (n <= 0) return 0;
+  B2C_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+              "b2c_cast_f32_bf16: pointers must be 16-byte aligned");
+  const int64_t threads = (n + 7) / 8;
+  cast_f32_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2c_scale_cast(const float* src, void* dst, int64_t rows, int64_t cols, float alpha, float drop_p,
+                              uint64_t drop_seed, void* stream) {
+  B2C_REQUIRE(src && dst, "b2c_scale_cast: null pointer");
+  const int64_t n = rows * cols;
+  if (n <= 0) return 0;
+  B2C_REQUIRE(n % 4 == 0, "b2c_scale_cast: element count must be a multiple of 4");
+  const uint32_t thresh = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int64_t threads = n / 4;
+  scale_cast_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n, alpha, thresh, inv_keep, drop_seed);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2c_colsum_bf16(const void* a, int64_t ld, int64_t rows, int64_t cols, float* out, void* stream) {
+  B2C_REQUIRE(a && out, "b2c_colsum_bf16: null pointer");
+  B2C_REQUIRE(cols % 2 == 0 && ld % 2 == 0, "b2c_colsum_bf16: cols and ld must be even");
+  if (rows <= 0 || cols <= 0) return 0;
+  const unsigned gx = static_cast<unsigned>((cols + 63) / 64);
+  int64_t want_y = (static_cast<int64_t>(num_sms()) * 4 + gx - 1) / gx;
+  int rows_per_block = static_cast<int>((rows + want_y - 1) / want_y);
+  rows_per_block = ((rows_per_block + 7) / 8) * 8;
+  const unsigned gy = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
+  colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), ld, rows, cols, out, rows_per_block);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2c_repack_heads(const void* src, void* dst, int64_t rows, int nblk, int src_dh, int dst_dh,
+                                void* stream) {
+  B2C_REQUIRE(src && dst && nblk > 0 && src_dh > 0 && dst_dh > 0, "b2c_repack_heads: bad argument");
+  const int64_t n = rows * nblk * dst_dh;
+  if (n <= 0) return 0;
+  repack_heads_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), rows, nblk, src_dh, dst_dh);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,214 @@
+"""Thin tensor-level wrappers over the C ABI (one call = one kernel launch on the current torch stream).
+
+Nothing here computes with torch ops: tensors are only allocated (torch.empty / zeros) and their device pointers
+handed to libb200conformer.so.  Shapes follow include/b200conformer.h.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_SILU, ACT_SILU_BWD, BF16, F32, Epilogue, call, ptr, stream_ptr
+
+__all__ = ["gemm", "layernorm_fwd", "layernorm_bwd", "convmod_eval", "convmod_dw_fwd", "convmod_bn_finalize",
+           "convmod_bn_apply", "attention_fwd", "convsub_compose", "convsub_fwd", "convsub_wgrad",
+           "convsub_compose_bwd", "specaug_apply", "cast_bf16", "scale_cast", "colsum", "repack_heads",
+           "ACT_NONE", "ACT_SILU", "ACT_SILU_BWD"]
+
+
+def _check(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
+         bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, aux: Optional[torch.Tensor] = None,
+         resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
+         out_dtype: torch.dtype = torch.bfloat16, alpha: float = 1.0, drop_p: float = 0.0, drop_seed: int = 0,
+         accumulate: bool = False, split_k: int = 1, block_n: int = 0) -> torch.Tensor:
+    """D[M,N] = epilogue(A * B^T) -- see b2c_gemm_bf16.  a/b are 2-D bf16 tensors whose last dim is contiguous;
+    with a_mn/b_mn the tensor is the [K, rows] storage."""
+    _lib.require_device()
+    _check(a, torch.bfloat16, "a")
+    _check(b, torch.bfloat16, "b")
+    if a.stride(-1) != 1 or b.stride(-1) != 1:
+        raise ValueError("gemm operands must have a contiguous last dimension")
+    if out is None:
+        out = (torch.zeros if accumulate else torch.empty)((M, N), device=a.device, dtype=out_dtype)
+    ep = Epilogue()
+    ep.bias = ptr(bias)
+    ep.aux = ptr(aux)
+    ep.resid = ptr(resid)
+    ep.out = ptr(out)
+    ep.out2 = ptr(out2)
+    ep.ld_out = out.stride(0)
+    ep.ld_out2 = out2.stride(0) if out2 is not None else 0
+    ep.ld_aux = aux.stride(0) if aux is not None else 0
+    ep.alpha = alpha
+    ep.drop_p = drop_p
+    ep.drop_seed = drop_seed
+    ep.act = act
+    ep.out_dtype = BF16 if out.dtype == torch.bfloat16 else F32
+    ep.accumulate = int(accumulate)
+    call("b2c_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), M, N, K, split_k, block_n,
+         ctypes.byref(ep), stream_ptr())
+    return out
+
+
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, out_dtype=torch.bfloat16,
+                  save_stats: bool = False, eps: float = 1e-5, out: Optional[torch.Tensor] = None):
+    _lib.require_device()
+    _check(x, torch.float32, "x")
+    d = x.shape[-1]
+    rows = x.numel() // d
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    call("b2c_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(out), BF16 if out.dtype == torch.bfloat16 else F32,
+         ptr(mean), ptr(rstd), rows, d, eps, stream_ptr())
+    return (out, mean, rstd) if save_stats else out
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, accumulate: bool, dgamma, dbeta):
+    d = x.shape[-1]
+    rows = x.numel() // d
+    call("b2c_layernorm_bwd", ptr(dy), BF16 if dy.dtype == torch.bfloat16 else F32, ptr(x), ptr(gamma), ptr(mean),
+         ptr(rstd), ptr(dx), int(accumulate), ptr(dgamma), ptr(dbeta), rows, d, stream_ptr())
+    return dx
+
+
+def convmod_eval(u, wdw, bdw, bn_w, bn_b, bn_mean, bn_var, B: int, T: int, eps: float = 1e-5):
+    _lib.require_device()
+    _check(u, torch.bfloat16, "u")
+    d, k = wdw.shape[0], wdw.shape[-1]
+    out = torch.empty((B * T, d), device=u.device, dtype=torch.bfloat16)
+    call("b2c_convmod_eval_fwd", ptr(u), ptr(wdw), ptr(bdw), ptr(bn_w), ptr(bn_b), ptr(bn_mean), ptr(bn_var), eps,
+         ptr(out), B, T, d, k, stream_ptr())
+    return out
+
+
+def convmod_dw_fwd(u, wdw, bdw, B: int, T: int):
+    d, k = wdw.shape[0], wdw.shape[-1]
+    y = torch.empty((B * T, d), device=u.device, dtype=torch.bfloat16)
+    stats = torch.zeros(2 * d, device=u.device, dtype=torch.float64)
+    call("b2c_convmod_dw_fwd", ptr(u), ptr(wdw), ptr(bdw), ptr(y), ptr(stats), B, T, d, k, stream_ptr())
+    return y, stats
+
+
+def convmod_bn_finalize(stats, count: int, running_mean, running_var, eps: float = 1e-5, momentum: float = 0.1):
+    d = stats.numel() // 2
+    mean = torch.empty(d, device=stats.device, dtype=torch.float32)
+    rstd = torch.empty(d, device=stats.device, dtype=torch.float32)
+    call("b2c_convmod_bn_finalize", ptr(stats), count, eps, momentum, ptr(mean), ptr(rstd), ptr(running_mean),
+         ptr(running_var), d, stream_ptr())
+    return mean, rstd
+
+
+def convmod_bn_apply(y, mean, rstd, bn_w, bn_b):
+    out = torch.empty_like(y)
+    call("b2c_convmod_bn_apply", ptr(y), ptr(mean), ptr(rstd), ptr(bn_w), ptr(bn_b), ptr(out), y.shape[0], y.shape[1],
+         stream_ptr())
+    return out
+
+
+def attention_fwd(qkv: torch.Tensor, lengths_i32: torch.Tensor, B: int, T: int, H: int, scale: float, *,
+                  save_lse: bool = False, drop_p: float = 0.0, drop_seed: int = 0):
+    """qkv bf16 [B*T, 3*H*64] (heads padded to 64) -> out bf16 [B*T, H*64]."""
+    _lib.require_device()
+    _check(qkv, torch.bfloat16, "qkv")
+    _check(lengths_i32, torch.int32, "lengths")
+    out = torch.empty((B * T, H * 64), device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32) if save_lse else None
+    call("b2c_attention_fwd", ptr(qkv), qkv.stride(0), H * 64, 2 * H * 64, ptr(lengths_i32), ptr(out), out.stride(0),
+         ptr(lse), B, T, H, scale, drop_p, drop_seed, stream_ptr())
+    return (out, lse) if save_lse else out
+
+
+def convsub_compose(W1, b1, W2, b2, s1: int, KP: int, want_f32: bool = False):
+    _lib.require_device()
+    C1, _, k1, _ = W1.shape
+    C2, _, k2, _ = W2.shape
+    Wc = torch.empty((C2, KP), device=W1.device, dtype=torch.bfloat16)
+    Wc32 = torch.empty((C2, KP), device=W1.device, dtype=torch.float32) if want_f32 else None
+    bc = torch.empty(C2, device=W1.device, dtype=torch.float32)
+    call("b2c_convsub_compose", ptr(W1), ptr(b1), ptr(W2), ptr(b2), C1, C2, k1, s1, k2, ptr(Wc), ptr(Wc32), ptr(bc), KP,
+         stream_ptr())
+    return (Wc, bc, Wc32) if want_f32 else (Wc, bc)
+
+
+def convsub_fwd(x, Wc, bc, kc: int, stride: int, out_dtype=torch.bfloat16):
+    """x fp32 [B,F,T] -> [B, T', F', C2] token-major."""
+    _lib.require_device()
+    _check(x, torch.float32, "x")
+    B, F, T = x.shape
+    C2, KP = Wc.shape
+    Fo, To = (F - kc) // stride + 1, (T - kc) // stride + 1
+    out = torch.empty((B, To, Fo, C2), device=x.device, dtype=out_dtype)
+    call("b2c_convsub_fwd", ptr(x), ptr(Wc), ptr(bc), ptr(out), int(out_dtype == torch.float32), B, F, T, C2, kc, stride,
+         KP, stream_ptr())
+    return out
+
+
+def convsub_wgrad(x, dout, dWc, kc: int, stride: int):
+    B, F, T = x.shape
+    C2, KP = dWc.shape
+    call("b2c_convsub_wgrad", ptr(x), ptr(dout), ptr(dWc), B, F, T, C2, kc, stride, KP, stream_ptr())
+    return dWc
+
+
+def convsub_compose_bwd(dWc, dbc, W1, b1, W2, s1: int, dW1, db1, dW2, db2):
+    C1, _, k1, _ = W1.shape
+    C2, _, k2, _ = W2.shape
+    call("b2c_convsub_compose_bwd", ptr(dWc), ptr(dbc), ptr(W1), ptr(b1), ptr(W2), C1, C2, k1, s1, k2, dWc.shape[1],
+         ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), stream_ptr())
+
+
+def specaug_apply(x, tau_i32, warp_w, warp_w0, fmask, tmask, apply_masks: bool, mask_value: float):
+    """x fp32 [B,F,T]; parameter tensors are int32 device tensors (or None when the count is 0)."""
+    _lib.require_device()
+    _check(x, torch.float32, "x")
+    B, F, T = x.shape
+    out = torch.empty_like(x)
+    n_warp = 0 if warp_w is None else warp_w.shape[0]
+    n_f = 0 if fmask is None else fmask.shape[0]
+    n_t = 0 if tmask is None else tmask.shape[0]
+    call("b2c_specaug_apply", ptr(x), ptr(out), ptr(tau_i32), ptr(warp_w), ptr(warp_w0), n_warp, ptr(fmask), n_f,
+         ptr(tmask), n_t, int(apply_masks), float(mask_value), B, F, T, stream_ptr())
+    return out
+
+
+def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None):
+    _lib.require_device()
+    _check(src, torch.float32, "src")
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    call("b2c_cast_f32_bf16", ptr(src), ptr(dst), src.numel(), stream_ptr())
+    return dst
+
+
+def scale_cast(src, alpha: float, drop_p: float = 0.0, drop_seed: int = 0):
+    rows, cols = src.shape
+    dst = torch.empty((rows, cols), device=src.device, dtype=torch.bfloat16)
+    call("b2c_scale_cast", ptr(src), ptr(dst), rows, cols, alpha, drop_p, drop_seed, stream_ptr())
+    return dst
+
+
+def colsum(a, out):
+    rows, cols = a.shape
+    call("b2c_colsum_bf16", ptr(a), a.stride(0), rows, cols, ptr(out), stream_ptr())
+    return out
+
+
+def repack_heads(src, nblk: int, src_dh: int, dst_dh: int):
+    rows = src.shape[0]
+    dst = torch.empty((rows, nblk * dst_dh), device=src.device, dtype=torch.bfloat16)
+    call("b2c_repack_heads", ptr(src), ptr(dst), rows, nblk, src_dh, dst_dh, stream_ptr())
+    return dst

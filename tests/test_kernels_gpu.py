@@ -1,0 +1,270 @@
+"""Per-kernel numerics on a real B200, through the C ABI (ctypes), against plain PyTorch fp32 references.
+
+Tolerances: operands are bf16 (8 mantissa bits, eps 2^-8 = 3.9e-3), accumulation fp32.  A bf16-stored result
+is therefore compared with  |got - ref| <= 1e-2 * max(|ref|) + small abs  (about 2.5 ulp of the largest value);
+fp32-stored results with a tighter bound.  Integer / index work (SpecAugment) is compared bit-exactly.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from nn_conformer_for_speech_recognition_b200 import ops as _ops
+    return _ops
+
+
+def _close(got, ref, rel=1e-2, abs_=1e-3, name=""):
+    got, ref = got.float(), ref.float()
+    tol = rel * ref.abs().max().item() + abs_
+    err = (got - ref).abs().max().item()
+    assert math.isfinite(err) and err <= tol, f"{name}: max err {err:.3e} > tol {tol:.3e}"
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (256, 256, 256, 128), (300, 144, 144, 64),
+                                      (1000, 576, 144, 128), (777, 1024, 256, 256), (129, 64, 1024, 64),
+                                      (513, 768, 320, 0)])
+def test_gemm_forward_kk(ops, M, N, K, bn):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().T + bias
+    out = ops.gemm(a, w, M=M, N=N, K=K, bias=bias, block_n=bn)
+    _close(out, ref, name="gemm kk bias")
+    # SiLU epilogue + saved pre-activation
+    out2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    h = ops.gemm(a, w, M=M, N=N, K=K, bias=bias, act=ops.ACT_SILU, out2=out2, block_n=bn)
+    _close(out2, ref, name="gemm pre-act")
+    _close(h, torch.nn.functional.silu(ref), name="gemm silu")
+    # fp32 residual epilogue, in place: x = x + 0.5*(a w^T + b)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    want = x + 0.5 * ref
+    ops.gemm(a, w, M=M, N=N, K=K, bias=bias, resid=x, out=x, alpha=0.5, block_n=bn)
+    _close(x, want, rel=5e-3, name="gemm resid")
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (300, 144, 576), (1000, 256, 1024)])
+def test_gemm_dgrad_k_mn(ops, M, N, K):
+    """dX[M,N] = dY[M,K] * W[K,N]  (W stored (out=K, in=N): B is MN-major)."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    dy = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(K, N, device="cuda", generator=g) / math.sqrt(K))
+    ref = dy.float() @ w.float()
+    out = ops.gemm(dy, w, M=M, N=N, K=K, b_mn=True)
+    _close(out, ref, name="gemm dgrad")
+    # fused SiLU backward: out = (dy W) * silu'(u)
+    u = _bf(torch.randn(M, N, device="cuda", generator=g))
+    s = torch.sigmoid(u.float())
+    out = ops.gemm(dy, w, M=M, N=N, K=K, b_mn=True, act=ops.ACT_SILU_BWD, aux=u)
+    _close(out, ref * (s * (1 + u.float() * (1 - s))), name="gemm silu bwd")
+
+
+@pytest.mark.parametrize("M,N,K,split", [(256, 256, 512, 1), (144, 576, 1000, 4), (1024, 256, 3000, 16),
+                                         (256, 1024, 23872, 37)])
+def test_gemm_wgrad_mn_mn(ops, M, N, K, split):
+    """dW[M,N] = dY[K,M]^T * X[K,N], reduction over tokens K, fp32 atomics across split-K."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    dy = _bf(torch.randn(K, M, device="cuda", generator=g))
+    x = _bf(torch.randn(K, N, device="cuda", generator=g))
+    ref = dy.float().T @ x.float()
+    out = ops.gemm(dy, x, M=M, N=N, K=K, a_mn=True, b_mn=True, out_dtype=torch.float32, accumulate=True, split_k=split)
+    _close(out, ref, rel=2e-3, name="gemm wgrad")
+
+
+def test_gemm_dropout_is_regenerable(ops):
+    M, N, K = 256, 256, 64
+    a = _bf(torch.randn(M, K, device="cuda"))
+    w = _bf(torch.randn(N, K, device="cuda"))
+    o1 = ops.gemm(a, w, M=M, N=N, K=K, drop_p=0.5, drop_seed=123)
+    o2 = ops.gemm(a, w, M=M, N=N, K=K, drop_p=0.5, drop_seed=123)
+    o0 = ops.gemm(a, w, M=M, N=N, K=K)
+    assert torch.equal(o1, o2)
+    kept = o1 != 0
+    frac = kept.float().mean().item()
+    assert 0.45 < frac < 0.55
+    _close(o1[kept], 2 * o0.float()[kept], name="dropout scale")
+    # scale_cast regenerates the same mask for the backward pass
+    ones = torch.ones(M, N, device="cuda")
+    m = ops.scale_cast(ones, 1.0, 0.5, 123)
+    assert torch.equal(m != 0, kept | (o0 == 0))
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    a = _bf(torch.randn(128, 64, device="cuda"))
+    with pytest.raises(ValueError):
+        ops.gemm(a, a, M=128, N=100, K=64)          # N not a multiple of 8
+    with pytest.raises(ValueError):
+        ops.gemm(a.float(), a, M=128, N=128, K=64)  # wrong dtype
+    with pytest.raises(ValueError):
+        ops.gemm(a.cpu(), a, M=128, N=128, K=64)    # CPU tensor: no fallback
+
+
+# ----------------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows,d", [(1, 144), (37, 256), (1000, 512), (23872, 256), (65, 1024), (9, 16)])
+def test_layernorm_fwd_bwd(ops, rows, d):
+    g = torch.Generator(device="cuda").manual_seed(rows + d)
+    x = (torch.randn(rows, d, device="cuda", generator=g) * 2 + 0.5).requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(d, device="cuda", generator=g)).requires_grad_(True)
+    beta = (0.1 * torch.randn(d, device="cuda", generator=g)).requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(x, (d,), gamma, beta, 1e-5)
+    y32, mean, rstd = ops.layernorm_fwd(x.detach(), gamma.detach(), beta.detach(), out_dtype=torch.float32, save_stats=True)
+    _close(y32, ref, rel=1e-5, abs_=1e-5, name="ln fwd f32")
+    y16 = ops.layernorm_fwd(x.detach(), gamma.detach(), beta.detach())
+    _close(y16, ref, name="ln fwd bf16")
+    dy = torch.randn(rows, d, device="cuda", generator=g)
+    ref.backward(dy)
+    for dyk in (dy, _bf(dy)):
+        dx0 = torch.randn(rows, d, device="cuda", generator=g)
+        dx = dx0.clone()
+        dg = torch.zeros(d, device="cuda")
+        db = torch.zeros(d, device="cuda")
+        ops.layernorm_bwd(dyk, x.detach(), gamma.detach(), mean, rstd, dx, True, dg, db)
+        rel = 1e-4 if dyk.dtype == torch.float32 else 1e-2
+        _close(dx - dx0, x.grad, rel=rel, abs_=1e-4, name="ln dx")
+        _close(dg, gamma.grad, rel=rel, abs_=1e-3, name="ln dgamma")
+        _close(db, beta.grad, rel=rel, abs_=1e-3, name="ln dbeta")
+
+
+# ----------------------------------------------------------------------------------------------- conv module chain
+def _convmod_ref(u, wdw, bdw, bn_w, bn_b, mean, var, B, T, d, k):
+    u = u.float().view(B, T, 2 * d)
+    g = u[..., :d] * torch.sigmoid(u[..., d:])
+    y = torch.nn.functional.conv1d(g.transpose(1, 2), wdw.view(d, 1, k), bdw, padding=(k - 1) // 2, groups=d)
+    z = (y - mean[None, :, None]) / torch.sqrt(var[None, :, None] + 1e-5) * bn_w[None, :, None] + bn_b[None, :, None]
+    return y.transpose(1, 2).reshape(B * T, d), torch.nn.functional.silu(z).transpose(1, 2).reshape(B * T, d)
+
+
+@pytest.mark.parametrize("B,T,d,k", [(2, 50, 16, 7), (3, 373, 144, 31), (2, 129, 256, 31), (1, 128, 512, 33),
+                                     (4, 1, 64, 3), (2, 300, 72, 5)])
+def test_convmod_eval_and_train(ops, B, T, d, k):
+    g = torch.Generator(device="cuda").manual_seed(B * T + d)
+    u = _bf(torch.randn(B * T, 2 * d, device="cuda", generator=g))
+    wdw = torch.randn(d, k, device="cuda", generator=g) / math.sqrt(k)
+    bdw = 0.1 * torch.randn(d, device="cuda", generator=g)
+    bn_w = 1 + 0.1 * torch.randn(d, device="cuda", generator=g)
+    bn_b = 0.1 * torch.randn(d, device="cuda", generator=g)
+    rmean = 0.1 * torch.randn(d, device="cuda", generator=g)
+    rvar = 0.5 + torch.rand(d, device="cuda", generator=g)
+    y_ref, c_ref = _convmod_ref(u, wdw, bdw, bn_w, bn_b, rmean, rvar, B, T, d, k)
+    out = ops.convmod_eval(u, wdw, bdw, bn_w, bn_b, rmean, rvar, B, T)
+    _close(out, c_ref, name="convmod eval")
+    # train mode: batch statistics over all B*T positions, running stats updated with momentum 0.1
+    y, stats = ops.convmod_dw_fwd(u, wdw, bdw, B, T)
+    _close(y, y_ref, name="convmod dw")
+    rm, rv = rmean.clone(), rvar.clone()
+    mean, rstd = ops.convmod_bn_finalize(stats, B * T, rm, rv)
+    mu_ref = y_ref.mean(0)
+    var_ref = y_ref.var(0, unbiased=False)
+    _close(mean, mu_ref, rel=1e-4, abs_=1e-5, name="bn mean")
+    _close(rstd, 1 / torch.sqrt(var_ref + 1e-5), rel=1e-3, name="bn rstd")
+    n = B * T
+    _close(rm, 0.9 * rmean + 0.1 * mu_ref, rel=1e-4, abs_=1e-5, name="running mean")
+    _close(rv, 0.9 * rvar + 0.1 * var_ref * n / max(n - 1, 1), rel=1e-3, name="running var")
+    c = ops.convmod_bn_apply(y, mean, rstd, bn_w, bn_b)
+    z = (y.float() - mu_ref) / torch.sqrt(var_ref + 1e-5) * bn_w + bn_b
+    _close(c, torch.nn.functional.silu(z), name="bn apply")
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def _attn_ref(qkv, lengths, B, T, H):
+    q, k, v = (qkv.float().view(B, T, 3, H, 64)[:, :, i].transpose(1, 2) for i in range(3))
+    s = q @ k.transpose(-1, -2) / 8.0
+    mask = torch.arange(T, device=qkv.device)[None, :] >= lengths[:, None]
+    s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, -1)
+    return (p @ v).transpose(1, 2).reshape(B * T, H * 64), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,T,H,lens", [(1, 128, 1, [128]), (2, 100, 2, [100, 37]), (3, 373, 4, [373, 200, 1]),
+                                        (2, 748, 2, [748, 513]), (2, 130, 1, [129, 130])])
+def test_attention_fwd(ops, B, T, H, lens):
+    g = torch.Generator(device="cuda").manual_seed(T)
+    qkv = _bf(torch.randn(B * T, 3 * H * 64, device="cuda", generator=g))
+    lengths = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    ref, lse_ref = _attn_ref(qkv, lengths, B, T, H)
+    out, lse = ops.attention_fwd(qkv, lengths, B, T, H, 1 / 8.0, save_lse=True)
+    _close(out, ref, rel=2e-2, name="attention out")
+    _close(lse * math.log(2.0), lse_ref, rel=1e-3, abs_=1e-2, name="attention lse")
+
+
+def test_attention_zero_length_row_is_nan_like_torch(ops):
+    qkv = _bf(torch.randn(2 * 64, 3 * 64, device="cuda"))
+    lengths = torch.tensor([64, 0], device="cuda", dtype=torch.int32)
+    out = ops.attention_fwd(qkv, lengths, 2, 64, 1, 0.125)
+    assert torch.isfinite(out[:64]).all() and torch.isnan(out[64:].float()).all()
+
+
+# ----------------------------------------------------------------------------------------------- ConvSubSampling
+@pytest.mark.parametrize("B,F,T,C1,C2", [(2, 20, 30, 8, 16), (2, 80, 61, 24, 16), (3, 80, 300, 64, 128),
+                                         (2, 40, 40, 512, 128)])
+def test_convsub_compose_and_forward(ops, B, F, T, C1, C2):
+    g = torch.Generator(device="cuda").manual_seed(C1)
+    W1 = torch.randn(C1, 1, 7, 7, device="cuda", generator=g) / 7
+    b1 = 0.1 * torch.randn(C1, device="cuda", generator=g)
+    W2 = torch.randn(C2, C1, 3, 3, device="cuda", generator=g) / math.sqrt(9 * C1)
+    b2 = 0.1 * torch.randn(C2, device="cuda", generator=g)
+    x = torch.rand(B, 1, F, T, device="cuda", generator=g)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.conv2d(x, W1, b1, stride=2), W2, b2, stride=2)   # (B,C2,F',T')
+    Wc, bc, Wc32 = ops.convsub_compose(W1, b1, W2, b2, 2, 128, want_f32=True)
+    # composition identity in fp32
+    refc = torch.nn.functional.conv2d(x, Wc32[:, :121].view(C2, 1, 11, 11), bc, stride=4)
+    _close(refc, ref, rel=1e-4, abs_=1e-4, name="composition")
+    out32 = ops.convsub_fwd(x[:, 0].contiguous(), Wc, bc, 11, 4, out_dtype=torch.float32)   # [B,T',F',C2]
+    _close(out32.permute(0, 3, 2, 1), ref, name="convsub fwd f32")
+    out16 = ops.convsub_fwd(x[:, 0].contiguous(), Wc, bc, 11, 4)
+    _close(out16.permute(0, 3, 2, 1), ref, name="convsub fwd bf16")
+
+
+def test_convsub_wgrad_and_compose_bwd(ops):
+    B, F, T, C1, C2 = 2, 80, 200, 32, 128
+    g = torch.Generator(device="cuda").manual_seed(3)
+    W1 = (torch.randn(C1, 1, 7, 7, device="cuda", generator=g) / 7).requires_grad_(True)
+    b1 = (0.1 * torch.randn(C1, device="cuda", generator=g)).requires_grad_(True)
+    W2 = (torch.randn(C2, C1, 3, 3, device="cuda", generator=g) / math.sqrt(9 * C1)).requires_grad_(True)
+    b2 = (0.1 * torch.randn(C2, device="cuda", generator=g)).requires_grad_(True)
+    x = torch.rand(B, 1, F, T, device="cuda", generator=g)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.conv2d(x, W1, b1, stride=2), W2, b2, stride=2)
+    dref = torch.randn_like(ref)
+    dref = _bf(dref).float()
+    ref.backward(dref)
+    dout = _bf(dref.permute(0, 3, 2, 1).contiguous())            # token-major [B,T',F',C2]
+    Fo, To = ref.shape[2], ref.shape[3]
+    dWc = torch.zeros(C2, 128, device="cuda")
+    ops.convsub_wgrad(x[:, 0].contiguous(), dout.view(B * To, Fo * C2), dWc, 11, 4)
+    dbc = torch.zeros(C2, device="cuda")
+    ops.colsum(dout.view(-1, C2), dbc)
+    _close(dbc, b2.grad, rel=2e-3, name="dbc")
+    dW1, db1 = torch.zeros_like(W1), torch.zeros_like(b1)
+    dW2, db2 = torch.zeros_like(W2), torch.zeros_like(b2)
+    ops.convsub_compose_bwd(dWc, dbc, W1.detach(), b1.detach(), W2.detach(), 2, dW1, db1, dW2, db2)
+    _close(dW1, W1.grad, name="dW1")
+    _close(db1, b1.grad, rel=2e-3, name="db1")
+    _close(dW2, W2.grad, name="dW2")
+    _close(db2, b2.grad, rel=2e-3, name="db2")
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def test_cast_colsum_repack(ops):
+    x = torch.randn(1001, 40, device="cuda")
+    assert torch.equal(ops.cast_bf16(x), x.to(torch.bfloat16))
+    a = _bf(torch.randn(5000, 144, device="cuda"))
+    out = torch.zeros(144, device="cuda")
+    ops.colsum(a, out)
+    _close(out, a.float().sum(0), rel=1e-4, abs_=1e-2, name="colsum")
+    src = _bf(torch.randn(10, 3 * 4 * 36, device="cuda"))
+    dst = ops.repack_heads(src, 12, 36, 64)
+    want = torch.zeros(10, 12, 64, device="cuda", dtype=torch.bfloat16)
+    want[:, :, :36] = src.view(10, 12, 36)
+    assert torch.equal(dst, want.view(10, 768))
+    back = ops.repack_heads(dst, 12, 64, 36)
+    assert torch.equal(back, src)
