@@ -91,6 +91,18 @@ int b2c_convmod_bn_finalize(const double* stats, int64_t count, float eps, float
                             float* running_mean, float* running_var, int d, void* stream);
 int b2c_convmod_bn_apply(const void* y, const float* mean, const float* rstd, const float* bn_w, const float* bn_b,
                          void* out, int64_t rows, int d, void* stream);
+/* backward of the chain.  dc = grad wrt the chain output (bf16 [rows,d]); y = saved depthwise output; mean/rstd = the
+ * statistics the forward normalised with (batch stats in train mode, running stats -> rstd = 1/sqrt(var+eps) in eval).
+ *  _bn_bwd_reduce: fp64 sums [2*d] (zeroed by the caller): S1 = sum dz, S2 = sum dz*yhat, dz = dc*SiLU'(z)
+ *  _dw_bwd       : dy = BN'(dz) on the fly (bn_train selects the batch-stat formula), du bf16 [rows,2d] through the
+ *                  depthwise conv and GLU; dwdw [d,k], dbdw, dbn_w, dbn_b fp32 are ACCUMULATED with atomics. */
+int b2c_convmod_bn_bwd_reduce(const void* dc, const void* y, const float* mean, const float* rstd, const float* bn_w,
+                              const float* bn_b, double* sums, int64_t rows, int d, void* stream);
+int b2c_convmod_dw_bwd(const void* dc, const void* y, const void* u, const float* mean, const float* rstd,
+                       const float* bn_w, const float* bn_b, const double* sums, int bn_train, const float* wdw,
+                       void* du, float* dwdw, float* dbdw, float* dbn_w, float* dbn_b, int B, int T, int d, int k,
+                       void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Multi-head self-attention core, flash style: softmax(Q K^T * scale + key-length mask) V per (batch, head).
  * Replaces scaled_dot_product_attention as reached from nn.MultiheadAttention (torch/nn/functional.py:6608-6682,
@@ -102,6 +114,12 @@ int b2c_convmod_bn_apply(const void* y, const float* mean, const float* rstd, co
 int b2c_attention_fwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths, void* out,
                       int64_t ld_out, float* lse, int B, int T, int H, float scale, float drop_p, uint64_t drop_seed,
                       void* stream);
+
+/* backward: dqkv bf16 [B*T, ld] laid out like qkv (every row < B*T and all three head slabs are written);
+ * delta fp32 [B,H,T] workspace.  Recomputes P from lse; dropout mask regenerated from (drop_p, drop_seed). */
+int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
+                      const void* out, const void* dout, int64_t ld_out, const float* lse, float* delta, void* dqkv,
+                      int B, int T, int H, float scale, float drop_p, uint64_t drop_seed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * ConvSubSampling (/root/reference/lib/convsubsampling.py:16-45): conv_sub_2(conv_sub_1(x)), no activation
@@ -148,6 +166,9 @@ int64_t b2c_mt19937_randint_host(uint32_t* state_host, int64_t a, int64_t b);
 /* multi-tensor fp32 -> bf16 cast; optional zero padding of rows/cols (pads attention heads to 64):
  *   dst[r_dst(r), c] with r in [0,rows), src row pitch = cols, dst pitch = dst_cols >= cols */
 int b2c_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* one launch for a whole parameter set: table_dev = device array of {const float* src; bf16* dst; int64 n} (24 B each,
+ * sources/destinations 16-byte aligned); max_n = largest n (sizes the grid) */
+int b2c_multi_cast_f32_bf16(const void* table_dev, int n_tensors, int64_t max_n, void* stream);
 /* dst bf16 [rows, cols] = alpha * dropout(src fp32 [rows, cols]) -- gradient of  x + alpha*drop(y)  wrt y */
 int b2c_scale_cast(const float* src, void* dst, int64_t rows, int64_t cols, float alpha, float drop_p,
                    uint64_t drop_seed, void* stream);

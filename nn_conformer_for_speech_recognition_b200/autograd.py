@@ -1,0 +1,182 @@
+"""Autograd glue for the Conformer stack: ONE torch.autograd.Function spans all layers, so forward and backward
+are straight sequences of kernel launches (capturable in a CUDA graph) and torch's autograd engine sees a single
+node.  Gradient math mirrors what autograd derives for torchaudio's modules (conformer.py:18-212); every
+matrix product is the tcgen05 GEMM in one of its three operand-major modes:
+
+    forward   Y  = X W^T            (K-major, K-major)
+    dgrad     dX = dY W             (K-major, MN-major)  -- W used as stored, no transpose copy
+    wgrad     dW = dY^T X           (MN-major, MN-major) -- split over tokens, fp32 atomics into the grad arena
+"""
+from __future__ import annotations
+
+import math
+from typing import List
+
+import torch
+
+from . import ops
+from .conformer import _LAYER_PARAMS, HEAD_PAD, Conformer, _get, run_layers
+
+
+def conformer_apply(model: Conformer, inp: torch.Tensor, lengths_i32: torch.Tensor) -> torch.Tensor:
+    B, T, d = inp.shape
+    params = [_get(layer, n) for layer in model.conformer_layers for n in _LAYER_PARAMS]
+    need_grad = torch.is_grad_enabled() and (inp.requires_grad or any(p.requires_grad for p in params))
+    drop_p = model.dropout_p if model.training else 0.0
+    if not need_grad:
+        x = inp.detach().reshape(B * T, d).to(torch.float32).clone(memory_format=torch.contiguous_format)
+        y = run_layers(model, x, lengths_i32, B, T, None, model.training, drop_p, model.next_seed())
+        return y.view(B, T, d)
+    return _ConformerFn.apply(inp, lengths_i32, model, *params)
+
+
+def _split_k(tokens: int, out_tiles: int, sms: int = 148) -> int:
+    """split factor for a weight-gradient GEMM: enough CTAs to fill the chip, at least 4 K-blocks each."""
+    kb = (tokens + 63) // 64
+    want = max(1, (2 * sms + out_tiles - 1) // out_tiles)
+    return max(1, min(want, kb // 4 if kb >= 4 else 1))
+
+
+class _ConformerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, lengths_i32, model, *params):
+        B, T, d = inp.shape
+        x = inp.detach().reshape(B * T, d).to(torch.float32).clone(memory_format=torch.contiguous_format)
+        state: List[dict] = []
+        drop_p = model.dropout_p if model.training else 0.0
+        seed = model.next_seed()
+        # gradients are wanted: always run the two-pass conv-module chain so `y` exists for the backward pass
+        y = run_layers(model, x, lengths_i32, B, T, state, model.training, drop_p, seed, force_two_pass=True)
+        ctx.model, ctx.state, ctx.lengths = model, state, lengths_i32
+        ctx.dims = (B, T, d)
+        ctx.drop_p, ctx.seed = drop_p, seed
+        ctx.in_dtype = inp.dtype
+        return y.view(B, T, d)
+
+    @staticmethod
+    def backward(ctx, dy):
+        model: Conformer = ctx.model
+        B, T, d = ctx.dims
+        M = B * T
+        f, H, k = model.ffn_dim, model.num_heads, model.kernel_size
+        Hd = H * HEAD_PAD
+        dh = model.head_dim
+        scale = 1.0 / math.sqrt(dh)
+        drop_p, seed = ctx.drop_p, ctx.seed
+        weights = model._cache.get()
+        dev = dy.device
+        dx = dy.reshape(M, d).to(torch.float32).contiguous()
+        if dx.data_ptr() == dy.data_ptr():
+            dx = dx.clone()
+
+        # one zeroed fp32 arena holds every parameter gradient of the stack (atomics accumulate into it)
+        padded = dh != HEAD_PAD
+        sizes = []
+        for layer in model.conformer_layers:
+            for n in _LAYER_PARAMS:
+                p = _get(layer, n)
+                if padded and n == "self_attn.in_proj_weight":
+                    sizes.append(3 * Hd * d)
+                elif padded and n == "self_attn.in_proj_bias":
+                    sizes.append(3 * Hd)
+                elif padded and n == "self_attn.out_proj.weight":
+                    sizes.append(d * Hd)
+                else:
+                    sizes.append(p.numel())
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + ((s + 3) // 4) * 4)         # keep every slice 16-byte aligned
+        arena = torch.zeros(offs[-1], device=dev, dtype=torch.float32)
+        np_ = len(_LAYER_PARAMS)
+
+        def G(li, name):
+            i = li * np_ + _LAYER_PARAMS.index(name)
+            return arena[offs[i]:offs[i] + sizes[i]]
+
+        def wgrad(dyb, act, Mo, No, out):
+            """out[Mo,No] += dyb[tokens,Mo]^T act[tokens,No]"""
+            tiles = ((Mo + 127) // 128) * ((No + 127) // 128)
+            ops.gemm(dyb, act, M=Mo, N=No, K=M, a_mn=True, b_mn=True, out=out.view(Mo, No), accumulate=True,
+                     split_k=_split_k(M, tiles))
+
+        for li in reversed(range(model.num_layers)):
+            layer = model.conformer_layers[li]
+            st = ctx.state[li]
+            w = weights[li]
+            sd = (seed + li * 16) if drop_p > 0 else 0
+            P = lambda name: _get(layer, name)                                   # noqa: E731
+
+            # ---- 5. final LayerNorm: the stream passes through it (no skip connection)
+            s5 = st["final"]
+            dx_new = torch.empty_like(dx)
+            ops.layernorm_bwd(dx, s5["x"], P("final_layer_norm.weight"), s5["mean"], s5["rstd"], dx_new, False,
+                              G(li, "final_layer_norm.weight"), G(li, "final_layer_norm.bias"))
+            dx = dx_new
+
+            def ffn_bwd(pre, site):
+                s = st[pre]
+                dyb = ops.scale_cast(dx, 0.5, drop_p, sd + site + 1)                       # d(0.5*drop(.))
+                ops.colsum(dyb, G(li, pre + ".sequential.4.bias"))
+                wgrad(dyb, s["h"], d, f, G(li, pre + ".sequential.4.weight"))
+                du = ops.gemm(dyb, w[pre + ".sequential.4.weight"], M=M, N=f, K=d, b_mn=True, act=ops.ACT_SILU_BWD,
+                              aux=s["u"], drop_p=drop_p, drop_seed=sd + site)
+                ops.colsum(du, G(li, pre + ".sequential.1.bias"))
+                wgrad(du, s["a"], f, d, G(li, pre + ".sequential.1.weight"))
+                da = ops.gemm(du, w[pre + ".sequential.1.weight"], M=M, N=d, K=f, b_mn=True)
+                ops.layernorm_bwd(da, s["x"], P(pre + ".sequential.0.weight"), s["mean"], s["rstd"], dx, True,
+                                  G(li, pre + ".sequential.0.weight"), G(li, pre + ".sequential.0.bias"))
+
+            # ---- 4. FFN2
+            ffn_bwd("ffn2", 12)
+
+            # ---- 3. conv module
+            s = st["conv"]
+            bn = layer.conv_module.sequential[3]
+            dyb = ops.scale_cast(dx, 1.0, drop_p, sd + 8)
+            ops.colsum(dyb, G(li, "conv_module.sequential.5.bias"))
+            wgrad(dyb, s["c"], d, d, G(li, "conv_module.sequential.5.weight"))
+            dc = ops.gemm(dyb, w["conv_module.sequential.5.weight"], M=M, N=d, K=d, b_mn=True)
+            sums = ops.convmod_bn_bwd_reduce(dc, s["y"], s["bmean"], s["brstd"], bn.weight, bn.bias)
+            du = ops.convmod_dw_bwd(dc, s["y"], s["u"], s["bmean"], s["brstd"], bn.weight, bn.bias, sums, s["bn_train"],
+                                    P("conv_module.sequential.2.weight").view(d, k),
+                                    G(li, "conv_module.sequential.2.weight"), G(li, "conv_module.sequential.2.bias"),
+                                    G(li, "conv_module.sequential.3.weight"), G(li, "conv_module.sequential.3.bias"), B, T)
+            ops.colsum(du, G(li, "conv_module.sequential.0.bias"))
+            wgrad(du, s["a"], 2 * d, d, G(li, "conv_module.sequential.0.weight"))
+            da = ops.gemm(du, w["conv_module.sequential.0.weight"], M=M, N=d, K=2 * d, b_mn=True)
+            ops.layernorm_bwd(da, s["x"], P("conv_module.layer_norm.weight"), s["mean"], s["rstd"], dx, True,
+                              G(li, "conv_module.layer_norm.weight"), G(li, "conv_module.layer_norm.bias"))
+
+            # ---- 2. attention
+            s = st["attn"]
+            dyb = ops.scale_cast(dx, 1.0, drop_p, sd + 5)
+            ops.colsum(dyb, G(li, "self_attn.out_proj.bias"))
+            wgrad(dyb, s["att"], d, Hd, G(li, "self_attn.out_proj.weight"))
+            datt = ops.gemm(dyb, w["self_attn.out_proj.weight"], M=M, N=Hd, K=d, b_mn=True)
+            dqkv = ops.attention_bwd(s["qkv"], ctx.lengths, s["att"], datt, s["lse"], B, T, H, scale, drop_p, sd + 4)
+            ops.colsum(dqkv, G(li, "self_attn.in_proj_bias"))
+            wgrad(dqkv, s["a"], 3 * Hd, d, G(li, "self_attn.in_proj_weight"))
+            da = ops.gemm(dqkv, w["self_attn.in_proj_weight"], M=M, N=d, K=3 * Hd, b_mn=True)
+            ops.layernorm_bwd(da, s["x"], P("self_attn_layer_norm.weight"), s["mean"], s["rstd"], dx, True,
+                              G(li, "self_attn_layer_norm.weight"), G(li, "self_attn_layer_norm.bias"))
+
+            # ---- 1. FFN1
+            ffn_bwd("ffn1", 0)
+            ctx.state[li] = None                  # free this layer's saved activations
+
+        grads = []
+        for li, layer in enumerate(model.conformer_layers):
+            for n in _LAYER_PARAMS:
+                p = _get(layer, n)
+                g = G(li, n)
+                if padded and n == "self_attn.in_proj_weight":
+                    g = g.view(3, H, HEAD_PAD, d)[:, :, :dh].reshape(3 * d, d)
+                elif padded and n == "self_attn.in_proj_bias":
+                    g = g.view(3, H, HEAD_PAD)[:, :, :dh].reshape(3 * d)
+                elif padded and n == "self_attn.out_proj.weight":
+                    g = g.view(d, H, HEAD_PAD)[:, :, :dh].reshape(d, d)
+                else:
+                    g = g.view(p.shape)
+                grads.append(g if p.requires_grad else None)
+        dinp = dx.view(B, T, d).to(ctx.in_dtype) if ctx.needs_input_grad[0] else None
+        return (dinp, None, None, *grads)

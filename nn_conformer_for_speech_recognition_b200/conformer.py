@@ -1,0 +1,363 @@
+"""Drop-in for `torchaudio.models.Conformer`, the Conformer stack the reference constructs at
+`/root/reference/lib/standard/asrnn.py:29` and calls at `asrnn.py:214`.
+
+Same constructor signature, same `forward(input (B,T,D), lengths (B,)) -> (output (B,T,D), lengths)`, same
+attribute tree and therefore the same `state_dict` keys/shapes -- a reference checkpoint
+loads here and vice versa, and `Runner.load_model`'s `'conformer' in key` filter (`runner.py:74`) keeps working.
+The torch.nn submodules below are PARAMETER HOLDERS ONLY (they also make `torch.manual_seed(s); Conformer(...)`
+reproduce torchaudio's initialisation bit for bit); their `forward` is never called.  All arithmetic runs in the
+hand-written sm_100a kernels of libb200conformer.so (see ops.py / include/b200conformer.h):
+
+    per layer, on a token-major fp32 residual stream x [B*T, d]         (torchaudio conformer.py:176-212)
+      x += 0.5 * W4 SiLU(W1 LN(x))             LN kernel, GEMM(+bias+SiLU), GEMM(+bias, *0.5, +residual)
+      x += Wo Attn(Wqkv LN(x))                 LN, GEMM, flash attention (key-length mask), GEMM(+residual)
+      x += Wpw2 SiLU(BN(DW(GLU(Wpw1 LN(x)))))  LN, GEMM, fused GLU/depthwise/BN/SiLU chain, GEMM(+residual)
+      x += 0.5 * FFN2(x);  x = LN(x)
+
+bf16 operands, fp32 accumulation, fp32 residual stream / LayerNorm / softmax / BatchNorm statistics.
+There is no CPU or eager-PyTorch fallback: without the built library or off sm_100 the forward raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+
+HEAD_PAD = 64          # the attention kernel's head dimension
+
+
+class _FeedForwardModule(nn.Module):
+    """Parameter holder mirroring torchaudio `_FeedForwardModule` (conformer.py:91-119)."""
+
+    def __init__(self, input_dim: int, hidden_dim: int, dropout: float = 0.0) -> None:
+        super().__init__()
+        self.sequential = nn.Sequential(
+            nn.LayerNorm(input_dim),
+            nn.Linear(input_dim, hidden_dim, bias=True),
+            nn.SiLU(),
+            nn.Dropout(dropout),
+            nn.Linear(hidden_dim, input_dim, bias=True),
+            nn.Dropout(dropout),
+        )
+
+
+class _ConvolutionModule(nn.Module):
+    """Parameter holder mirroring torchaudio `_ConvolutionModule` (conformer.py:18-88)."""
+
+    def __init__(self, input_dim: int, num_channels: int, depthwise_kernel_size: int, dropout: float = 0.0,
+                 bias: bool = False, use_group_norm: bool = False) -> None:
+        super().__init__()
+        if (depthwise_kernel_size - 1) % 2 != 0:
+            raise ValueError("depthwise_kernel_size must be odd to achieve 'SAME' padding.")
+        if use_group_norm:
+            raise NotImplementedError("use_group_norm=True is not on the reference's path (asrnn.py:29 uses the "
+                                      "BatchNorm default); only BatchNorm1d is implemented")
+        self.layer_norm = nn.LayerNorm(input_dim)
+        self.sequential = nn.Sequential(
+            nn.Conv1d(input_dim, 2 * num_channels, 1, stride=1, padding=0, bias=bias),
+            nn.GLU(dim=1),
+            nn.Conv1d(num_channels, num_channels, depthwise_kernel_size, stride=1,
+                      padding=(depthwise_kernel_size - 1) // 2, groups=num_channels, bias=bias),
+            nn.BatchNorm1d(num_channels),
+            nn.SiLU(),
+            nn.Conv1d(num_channels, input_dim, kernel_size=1, stride=1, padding=0, bias=bias),
+            nn.Dropout(dropout),
+        )
+
+
+class ConformerLayer(nn.Module):
+    """Parameter holder mirroring torchaudio `ConformerLayer` (conformer.py:122-212)."""
+
+    def __init__(self, input_dim: int, ffn_dim: int, num_attention_heads: int, depthwise_conv_kernel_size: int,
+                 dropout: float = 0.0, use_group_norm: bool = False, convolution_first: bool = False) -> None:
+        super().__init__()
+        if convolution_first:
+            raise NotImplementedError("convolution_first=True is not on the reference's path (asrnn.py:29)")
+        self.ffn1 = _FeedForwardModule(input_dim, ffn_dim, dropout=dropout)
+        self.self_attn_layer_norm = nn.LayerNorm(input_dim)
+        self.self_attn = nn.MultiheadAttention(input_dim, num_attention_heads, dropout=dropout)
+        self.self_attn_dropout = nn.Dropout(dropout)
+        self.conv_module = _ConvolutionModule(input_dim=input_dim, num_channels=input_dim,
+                                              depthwise_kernel_size=depthwise_conv_kernel_size, dropout=dropout,
+                                              bias=True, use_group_norm=use_group_norm)
+        self.ffn2 = _FeedForwardModule(input_dim, ffn_dim, dropout=dropout)
+        self.final_layer_norm = nn.LayerNorm(input_dim)
+        self.convolution_first = convolution_first
+
+
+# order of the per-layer parameters handed to the autograd function (and of the gradients it returns)
+_LAYER_PARAMS = [
+    "ffn1.sequential.0.weight", "ffn1.sequential.0.bias", "ffn1.sequential.1.weight", "ffn1.sequential.1.bias",
+    "ffn1.sequential.4.weight", "ffn1.sequential.4.bias",
+    "self_attn_layer_norm.weight", "self_attn_layer_norm.bias", "self_attn.in_proj_weight", "self_attn.in_proj_bias",
+    "self_attn.out_proj.weight", "self_attn.out_proj.bias",
+    "conv_module.layer_norm.weight", "conv_module.layer_norm.bias", "conv_module.sequential.0.weight",
+    "conv_module.sequential.0.bias", "conv_module.sequential.2.weight", "conv_module.sequential.2.bias",
+    "conv_module.sequential.3.weight", "conv_module.sequential.3.bias", "conv_module.sequential.5.weight",
+    "conv_module.sequential.5.bias",
+    "ffn2.sequential.0.weight", "ffn2.sequential.0.bias", "ffn2.sequential.1.weight", "ffn2.sequential.1.bias",
+    "ffn2.sequential.4.weight", "ffn2.sequential.4.bias",
+    "final_layer_norm.weight", "final_layer_norm.bias",
+]
+# GEMM weights that need a bf16 copy (everything else is consumed as fp32 straight from the Parameter)
+_BF16_WEIGHTS = ["ffn1.sequential.1.weight", "ffn1.sequential.4.weight", "self_attn.in_proj_weight",
+                 "self_attn.out_proj.weight", "conv_module.sequential.0.weight", "conv_module.sequential.5.weight",
+                 "ffn2.sequential.1.weight", "ffn2.sequential.4.weight"]
+
+
+def _get(module: nn.Module, dotted: str) -> torch.Tensor:
+    obj = module
+    for part in dotted.split("."):
+        obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
+    return obj
+
+
+class _WeightCache:
+    """bf16 copies of the GEMM weights (one multi-tensor cast launch), refreshed when a Parameter changes."""
+
+    def __init__(self, owner: "Conformer"):
+        self.owner = owner
+        self.key = None
+        self.bf16: List[dict] = []
+        self.table = None
+        self.max_n = 0
+
+    def _signature(self):
+        sig = []
+        for layer in self.owner.conformer_layers:
+            for name in _BF16_WEIGHTS + ["self_attn.in_proj_bias"]:
+                p = _get(layer, name)
+                sig.append((p.data_ptr(), p._version))
+        return tuple(sig)
+
+    def get(self) -> List[dict]:
+        sig = self._signature()
+        if sig == self.key:
+            return self.bf16
+        o = self.owner
+        dev = next(o.parameters()).device
+        if o.head_dim != HEAD_PAD:
+            self._build_padded(dev)
+        else:
+            rebuild = self.table is None or [s[0] for s in sig] != [s[0] for s in (self.key or ())]
+            if rebuild:
+                self.bf16, entries = [], []
+                for layer in o.conformer_layers:
+                    d = {}
+                    for name in _BF16_WEIGHTS:
+                        p = _get(layer, name)
+                        t = torch.empty(p.shape[:2] if p.dim() == 3 else p.shape, device=dev, dtype=torch.bfloat16)
+                        d[name] = t
+                        entries.append((p.data_ptr(), t.data_ptr(), p.numel()))
+                    d["in_bias"] = _get(layer, "self_attn.in_proj_bias")
+                    self.bf16.append(d)
+                flat = torch.tensor([v for e in entries for v in e], dtype=torch.int64)
+                self.table = flat.to(dev)
+                self.ntab = len(entries)
+                self.max_n = max(e[2] for e in entries)
+            _lib.call("b2c_multi_cast_f32_bf16", self.table.data_ptr(), self.ntab, self.max_n, _lib.stream_ptr())
+        self.key = sig
+        return self.bf16
+
+    def _build_padded(self, dev):
+        """head_dim < 64 (Conformer-S: 36): zero-pad every head to 64 in the in/out projections so the attention
+        kernel sees head dim 64.  Weight preparation only (runs when parameters change), done with torch indexing."""
+        o = self.owner
+        H, dh, d = o.num_heads, o.head_dim, o.input_dim
+        self.bf16 = []
+        for layer in o.conformer_layers:
+            out = {}
+            for name in _BF16_WEIGHTS:
+                p = _get(layer, name).detach()
+                if name == "self_attn.in_proj_weight":
+                    w = torch.zeros(3, H, HEAD_PAD, d, device=dev, dtype=torch.float32)
+                    w[:, :, :dh] = p.view(3, H, dh, d)
+                    p = w.view(3 * H * HEAD_PAD, d)
+                elif name == "self_attn.out_proj.weight":
+                    w = torch.zeros(d, H, HEAD_PAD, device=dev, dtype=torch.float32)
+                    w[:, :, :dh] = p.view(d, H, dh)
+                    p = w.view(d, H * HEAD_PAD)
+                elif p.dim() == 3:
+                    p = p[:, :, 0]
+                out[name] = ops.cast_bf16(p.contiguous())
+            b = torch.zeros(3, H, HEAD_PAD, device=dev, dtype=torch.float32)
+            b[:, :, :dh] = _get(layer, "self_attn.in_proj_bias").detach().view(3, H, dh)
+            out["in_bias"] = b.view(-1)
+            self.bf16.append(out)
+
+
+class Conformer(nn.Module):
+    r"""Conformer stack with torchaudio's interface (torchaudio/models/conformer.py:215-293).
+
+    Args mirror `torchaudio.models.Conformer`: input_dim, num_heads, ffn_dim, num_layers,
+    depthwise_conv_kernel_size, dropout=0.0, use_group_norm=False, convolution_first=False.
+    The reference calls it positionally: `Conformer(512, 8, 512, 1, 33, 0.5)` (asrnn.py:29).
+    """
+
+    def __init__(self, input_dim: int, num_heads: int, ffn_dim: int, num_layers: int,
+                 depthwise_conv_kernel_size: int, dropout: float = 0.0, use_group_norm: bool = False,
+                 convolution_first: bool = False):
+        super().__init__()
+        if input_dim % num_heads != 0:
+            raise AssertionError("embed_dim must be divisible by num_heads")
+        self.conformer_layers = nn.ModuleList([
+            ConformerLayer(input_dim, ffn_dim, num_heads, depthwise_conv_kernel_size, dropout=dropout,
+                           use_group_norm=use_group_norm, convolution_first=convolution_first)
+            for _ in range(num_layers)
+        ])
+        self.input_dim, self.num_heads, self.ffn_dim = input_dim, num_heads, ffn_dim
+        self.num_layers, self.kernel_size, self.dropout_p = num_layers, depthwise_conv_kernel_size, float(dropout)
+        self.head_dim = input_dim // num_heads
+        if self.head_dim > HEAD_PAD:
+            raise NotImplementedError(f"head_dim {self.head_dim} > {HEAD_PAD} is not supported by the attention kernel "
+                                      "(reference default, Conformer-S/M/L all have head_dim <= 64)")
+        if input_dim % 8 != 0 or ffn_dim % 8 != 0 or input_dim > 1024:
+            raise NotImplementedError("input_dim and ffn_dim must be multiples of 8, input_dim <= 1024")
+        self._cache = _WeightCache(self)
+        self._seed_counter = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, input: torch.Tensor, lengths: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        r"""input (B, T, input_dim); lengths (B,) valid frames per utterance. Returns (output (B,T,input_dim), lengths)."""
+        _lib.require_device()
+        if input.dim() != 3 or input.shape[-1] != self.input_dim:
+            raise ValueError(f"expected input of shape (B, T, {self.input_dim}), got {tuple(input.shape)}")
+        if not input.is_cuda:
+            raise _lib.B2CError("Conformer.forward needs CUDA tensors; there is no CPU fallback")
+        B, T, _ = input.shape
+        if lengths.shape[0] != B:
+            raise ValueError("lengths must have one entry per utterance")
+        lengths_i32 = lengths.to(device=input.device, dtype=torch.int32)
+        from .autograd import conformer_apply          # local import: autograd.py imports this module
+        y = conformer_apply(self, input, lengths_i32)
+        return y, lengths
+
+    # ------------------------------------------------------------------------------------------------
+    def next_seed(self) -> int:
+        """Dropout seeds: torch's CPU generator picks the stream (so torch.manual_seed controls it), the counter
+        keeps successive forward passes distinct."""
+        self._seed_counter += 1
+        base = int(torch.initial_seed()) & 0xFFFFFFFF
+        return (base << 20) ^ (self._seed_counter * 0x9E3779B1)
+
+    def extra_repr(self) -> str:
+        return (f"input_dim={self.input_dim}, num_heads={self.num_heads}, ffn_dim={self.ffn_dim}, "
+                f"num_layers={self.num_layers}, kernel={self.kernel_size}, dropout={self.dropout_p} [sm_100a kernels]")
+
+
+# ----------------------------------------------------------------------------------------------------
+# the layer pipeline (shared by eval forward and the autograd function's forward)
+# ----------------------------------------------------------------------------------------------------
+def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: int, T: int, train_state: Optional[list],
+               bn_train: bool, drop_p: float, seed: int, force_two_pass: bool = False) -> torch.Tensor:
+    """x: fp32 [B*T, d] residual stream (overwritten in eval mode). `train_state` (a list) receives what the
+    backward pass needs; None = inference (buffers are reused across layers, nothing is kept)."""
+    d, f, H, k = model.input_dim, model.ffn_dim, model.num_heads, model.kernel_size
+    M = B * T
+    Hd = H * HEAD_PAD
+    scale = 1.0 / math.sqrt(model.head_dim)
+    weights = model._cache.get()
+    dev = x.device
+    save = train_state is not None
+    bf = torch.bfloat16
+    if not save:       # inference workspaces, reused by every layer (stay L2-resident between kernels)
+        a_buf = torch.empty((M, d), device=dev, dtype=bf)
+        h_buf = torch.empty((M, f), device=dev, dtype=bf)
+        qkv_buf = torch.empty((M, 3 * Hd), device=dev, dtype=bf)
+        u_buf = torch.empty((M, 2 * d), device=dev, dtype=bf)
+
+    for li, layer in enumerate(model.conformer_layers):
+        w = weights[li]
+        P = lambda name: _get(layer, name)                                      # noqa: E731
+        sd = (seed + li * 16) if drop_p > 0 else 0
+        st = {} if save else None
+
+        def ffn(x_in, pre, site):
+            ln_w, ln_b = P(pre + ".sequential.0.weight"), P(pre + ".sequential.0.bias")
+            if save:
+                a, mean, rstd = ops.layernorm_fwd(x_in, ln_w, ln_b, save_stats=True)
+                u = torch.empty((M, f), device=dev, dtype=bf)
+                h = ops.gemm(a, w[pre + ".sequential.1.weight"], M=M, N=f, K=d, bias=P(pre + ".sequential.1.bias"),
+                             act=ops.ACT_SILU, out2=u, drop_p=drop_p, drop_seed=sd + site)
+                x_out = ops.gemm(h, w[pre + ".sequential.4.weight"], M=M, N=d, K=f, bias=P(pre + ".sequential.4.bias"),
+                                 resid=x_in, out_dtype=torch.float32, alpha=0.5, drop_p=drop_p, drop_seed=sd + site + 1)
+                st[pre] = dict(x=x_in, a=a, mean=mean, rstd=rstd, u=u, h=h)
+                return x_out
+            ops.layernorm_fwd(x_in, ln_w, ln_b, out=a_buf)
+            ops.gemm(a_buf, w[pre + ".sequential.1.weight"], M=M, N=f, K=d, bias=P(pre + ".sequential.1.bias"),
+                     act=ops.ACT_SILU, out=h_buf)
+            ops.gemm(h_buf, w[pre + ".sequential.4.weight"], M=M, N=d, K=f, bias=P(pre + ".sequential.4.bias"),
+                     resid=x_in, out=x_in, alpha=0.5)
+            return x_in
+
+        # ---- 1. x += 0.5 * FFN1(x)                                                   conformer.py:185-187
+        x = ffn(x, "ffn1", 0)
+
+        # ---- 2. x += out_proj(Attn(in_proj(LN(x))))                                  conformer.py:192-202
+        ln_w, ln_b = P("self_attn_layer_norm.weight"), P("self_attn_layer_norm.bias")
+        if save:
+            a, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, save_stats=True)
+            qkv = ops.gemm(a, w["self_attn.in_proj_weight"], M=M, N=3 * Hd, K=d, bias=w["in_bias"])
+            att, lse = ops.attention_fwd(qkv, lengths_i32, B, T, H, scale, save_lse=True, drop_p=drop_p, drop_seed=sd + 4)
+            x_out = ops.gemm(att, w["self_attn.out_proj.weight"], M=M, N=d, K=Hd, bias=P("self_attn.out_proj.bias"),
+                             resid=x, out_dtype=torch.float32, drop_p=drop_p, drop_seed=sd + 5)
+            st["attn"] = dict(x=x, a=a, mean=mean, rstd=rstd, qkv=qkv, att=att, lse=lse)
+            x = x_out
+        else:
+            ops.layernorm_fwd(x, ln_w, ln_b, out=a_buf)
+            ops.gemm(a_buf, w["self_attn.in_proj_weight"], M=M, N=3 * Hd, K=d, bias=w["in_bias"], out=qkv_buf)
+            att = ops.attention_fwd(qkv_buf, lengths_i32, B, T, H, scale)
+            ops.gemm(att, w["self_attn.out_proj.weight"], M=M, N=d, K=Hd, bias=P("self_attn.out_proj.bias"),
+                     resid=x, out=x)
+
+        # ---- 3. x += conv_module(x)                                                  conformer.py:168-174,77-88
+        bn = layer.conv_module.sequential[3]
+        ln_w, ln_b = P("conv_module.layer_norm.weight"), P("conv_module.layer_norm.bias")
+        wdw = P("conv_module.sequential.2.weight").view(d, k)
+        bdw = P("conv_module.sequential.2.bias")
+        if save:
+            a, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, save_stats=True)
+            u = ops.gemm(a, w["conv_module.sequential.0.weight"], M=M, N=2 * d, K=d, bias=P("conv_module.sequential.0.bias"))
+        else:
+            ops.layernorm_fwd(x, ln_w, ln_b, out=a_buf)
+            u = ops.gemm(a_buf, w["conv_module.sequential.0.weight"], M=M, N=2 * d, K=d,
+                         bias=P("conv_module.sequential.0.bias"), out=u_buf)
+        if bn_train:
+            y, stats = ops.convmod_dw_fwd(u, wdw, bdw, B, T)
+            bmean, brstd = ops.convmod_bn_finalize(stats, M, bn.running_mean, bn.running_var, bn.eps,
+                                                   bn.momentum if bn.momentum is not None else 0.1)
+            bn.num_batches_tracked += 1
+            c = ops.convmod_bn_apply(y, bmean, brstd, bn.weight, bn.bias)
+        elif force_two_pass:     # eval-mode BatchNorm under autograd: keep y, normalise with the running statistics
+            y, _ = ops.convmod_dw_fwd(u, wdw, bdw, B, T)
+            bmean, brstd = bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)
+            c = ops.convmod_bn_apply(y, bmean, brstd, bn.weight, bn.bias)
+        else:
+            c = ops.convmod_eval(u, wdw, bdw, bn.weight, bn.bias, bn.running_mean, bn.running_var, B, T, bn.eps)
+            y = bmean = brstd = None
+        if save:
+            x_out = ops.gemm(c, w["conv_module.sequential.5.weight"], M=M, N=d, K=d, bias=P("conv_module.sequential.5.bias"),
+                             resid=x, out_dtype=torch.float32, drop_p=drop_p, drop_seed=sd + 8)
+            st["conv"] = dict(x=x, a=a, mean=mean, rstd=rstd, u=u, y=y, bmean=bmean, brstd=brstd, c=c, bn_train=bn_train)
+            x = x_out
+        else:
+            ops.gemm(c, w["conv_module.sequential.5.weight"], M=M, N=d, K=d, bias=P("conv_module.sequential.5.bias"),
+                     resid=x, out=x)
+
+        # ---- 4. x += 0.5 * FFN2(x)                                                   conformer.py:206-209
+        x = ffn(x, "ffn2", 12)
+
+        # ---- 5. x = LN(x)                                                            conformer.py:211
+        ln_w, ln_b = P("final_layer_norm.weight"), P("final_layer_norm.bias")
+        if save:
+            x_out, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, out_dtype=torch.float32, save_stats=True)
+            st["final"] = dict(x=x, mean=mean, rstd=rstd)
+            train_state.append(st)
+            x = x_out
+        else:
+            x = ops.layernorm_fwd(x, ln_w, ln_b, out_dtype=torch.float32)
+    return x

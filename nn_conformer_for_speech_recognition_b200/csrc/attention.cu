@@ -208,6 +208,313 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 }
 
 constexpr uint32_t ATTN_FWD_SMEM = 81920 + 64 + 1024;
+// ================================================================================================
+// backward
+// ================================================================================================
+struct AttnBwdParams {
+  const int32_t* lengths;
+  const float* lse;        // [B,H,T] log2-domain log-sum-exp saved by the forward pass
+  const float* delta;      // [B,H,T] rowsum(dO o O)
+  __nv_bfloat16* dqkv;     // [B*T, ld] laid out like qkv
+  int64_t ld;
+  int B, T, H;
+  int q_col, k_col, v_col;
+  float scale, scale_log2;
+  uint32_t drop_thresh;
+  float inv_keep;
+  uint64_t drop_seed;
+};
+
+// delta[b,h,t] = sum_c dO[row, h*64+c] * O[row, h*64+c]
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
+                                                        const __nv_bfloat16* __restrict__ dout, int64_t ld_out,
+                                                        float* __restrict__ delta, int B, int T, int H) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;     // (row, h)
+  if (idx >= static_cast<int64_t>(B) * T * H) return;
+  const int h = static_cast<int>(idx % H);
+  const int64_t row = idx / H;
+  const uint4* po = reinterpret_cast<const uint4*>(o + row * ld_out + h * AT_DH);
+  const uint4* pd = reinterpret_cast<const uint4*>(dout + row * ld_out + h * AT_DH);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < AT_DH / 8; ++i) {
+    const uint4 a = po[i], b = pd[i];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = unpack_bf16(aw[j]), y = unpack_bf16(bw[j]);
+      acc = fmaf(x.x, y.x, acc);
+      acc = fmaf(x.y, y.y, acc);
+    }
+  }
+  const int b_ = static_cast<int>(row / T), t = static_cast<int>(row % T);
+  delta[(static_cast<int64_t>(b_) * H + h) * T + t] = acc;
+}
+
+// Thread r (query row q_idx) turns its S row and dP row (TMEM) into P (optionally dropped, for dV) and
+// dS = P o (dP*drop - delta) * scale, both written as bf16 [q][key] K-major SW128 tiles (2 x [128][64]).
+// sP may be nullptr (dQ kernel needs only dS).
+__device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint32_t tm_s, uint32_t tm_dp, uint8_t* sP,
+                                                   uint8_t* sdS, int tid, int q_idx, int key0, int len, float lse_r,
+                                                   float delta_r, uint64_t drop_row) {
+  const bool q_ok = q_idx < p.T;
+#pragma unroll 1
+  for (int c = 0; c < AT_BK; c += 32) {
+    uint32_t vs[32], vd[32];
+    __syncwarp();
+    tmem_ld32(tm_s + c, vs);
+    tmem_ld32(tm_dp + c, vd);
+    tmem_wait_ld();
+    float pr[32], ds[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const bool ok = q_ok && (key0 + c + i < len);
+      const float pv = ok ? exp2f(__uint_as_float(vs[i]) * p.scale_log2 - lse_r) : 0.f;
+      float dsc = 1.f;
+      if (p.drop_thresh) dsc = drop_scale(p.drop_seed, drop_row + key0 + c + i, p.drop_thresh, p.inv_keep);
+      pr[i] = pv * dsc;
+      ds[i] = pv * (__uint_as_float(vd[i]) * dsc - delta_r) * p.scale;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t off = sw128_offset(tid, c + g * 8, 128);
+      if (sP)
+        *reinterpret_cast<uint4*>(sP + off) =
+            make_uint4(pack_bf16(pr[g * 8], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
+                       pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
+      *reinterpret_cast<uint4*>(sdS + off) =
+          make_uint4(pack_bf16(ds[g * 8], ds[g * 8 + 1]), pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]),
+                     pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]), pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]));
+    }
+  }
+}
+
+// write a 128 x 64 fp32 TMEM tile (this thread's row) as bf16 to dst (nullptr = skip)
+__device__ __forceinline__ void attn_store_row(uint32_t tm, __nv_bfloat16* dst) {
+#pragma unroll
+  for (int c = 0; c < AT_DH; c += 32) {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld32(tm + c, v);
+    tmem_wait_ld();
+    if (dst) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(dst + c + g * 8) =
+            make_uint4(pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
+                       pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
+                       pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
+                       pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+    }
+  }
+}
+
+// dK, dV for one 128-key block: loops over all query blocks of the utterance.
+__global__ void __launch_bounds__(128, 1) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                               const __grid_constant__ CUtensorMap tmDO,
+                                                               const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  constexpr uint32_t OFF_K = 0, OFF_V = 16384, OFF_Q = 32768, OFF_DO = 49152, OFF_P = 65536, OFF_DS = 98304,
+                     OFF_BAR = 131072;
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* bar_q = bar_kv + 1;
+  uint64_t* bar_s = bar_kv + 2;
+  uint64_t* bar_acc = bar_kv + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 4);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int len = min(p.lengths[b], p.T);
+  const int key0 = j * AT_BK, row_base = b * p.T;
+  const int key_idx = key0 + tid;
+  __nv_bfloat16* dk_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.k_col + h * AT_DH : nullptr;
+  __nv_bfloat16* dv_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.v_col + h * AT_DH : nullptr;
+  if (key0 >= len) {                       // every key of this block is masked: P = 0 -> dK = dV = 0
+    if (dk_dst) {
+#pragma unroll
+      for (int g = 0; g < AT_DH / 8; ++g) {
+        reinterpret_cast<uint4*>(dk_dst)[g] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(dv_dst)[g] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    return;
+  }
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO);
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 512); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320;
+  if (tid == 0) {
+    mbar_expect_tx(bar_kv, 32768);
+    tma_load_2d(smem + OFF_K, &tmQKV, bar_kv, p.k_col + h * AT_DH, row_base + key0);
+    tma_load_2d(smem + OFF_V, &tmQKV, bar_kv, p.v_col + h * AT_DH, row_base + key0);
+  }
+  constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_mm = umma_idesc_bf16(128, 64, true, true);
+  const int nqb = (p.T + AT_BQ - 1) / AT_BQ;
+  for (int i = 0; i < nqb; ++i) {
+    const uint32_t ph = i & 1;
+    const int q_idx = i * AT_BQ + tid;
+    if (tid == 0) {
+      mbar_expect_tx(bar_q, 32768);
+      tma_load_2d(smem + OFF_Q, &tmQKV, bar_q, p.q_col + h * AT_DH, row_base + i * AT_BQ);
+      tma_load_2d(smem + OFF_DO, &tmDO, bar_q, h * AT_DH, row_base + i * AT_BQ);
+      if (i == 0) mbar_wait(bar_kv, 0);
+      mbar_wait(bar_q, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)          // S = Q K^T
+        umma_bf16(tmem_base + TM_S, umma_desc_sw128(base + OFF_Q + k * 32, 16, 1024),
+                  umma_desc_sw128(base + OFF_K + k * 32, 16, 1024), idesc_kk, k > 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)          // dP = dO V^T
+        umma_bf16(tmem_base + TM_DP, umma_desc_sw128(base + OFF_DO + k * 32, 16, 1024),
+                  umma_desc_sw128(base + OFF_V + k * 32, 16, 1024), idesc_kk, k > 0);
+      tc_commit(bar_s);
+    }
+    const int64_t stat = static_cast<int64_t>(b * p.H + h) * p.T + min(q_idx, p.T - 1);
+    const float lse_r = p.lse[stat], delta_r = p.delta[stat];
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    attn_bwd_tile_math(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P, smem + OFF_DS, tid, q_idx, key0, len, lse_r,
+                       delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.T);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)          // dV += P^T dO   (reduction over the 128 queries)
+        umma_bf16(tmem_base + TM_DV, umma_desc_sw128(base + OFF_P + k * 2048, 16384, 1024),
+                  umma_desc_sw128(base + OFF_DO + k * 2048, 8192, 1024), idesc_mm, (i | k) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)          // dK += dS^T Q
+        umma_bf16(tmem_base + TM_DK, umma_desc_sw128(base + OFF_DS + k * 2048, 16384, 1024),
+                  umma_desc_sw128(base + OFF_Q + k * 2048, 8192, 1024), idesc_mm, (i | k) ? 1u : 0u);
+      tc_commit(bar_acc);
+      mbar_wait(bar_acc, ph);              // Q/dO/P/dS tiles are reused by the next query block
+    }
+    __syncthreads();
+  }
+  tc_fence_after();
+  attn_store_row(tm_lane + TM_DV, dv_dst);
+  attn_store_row(tm_lane + TM_DK, dk_dst);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dQ for one 128-query block: loops over the key blocks below lengths[b].
+__global__ void __launch_bounds__(128, 1) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                              const __grid_constant__ CUtensorMap tmDO,
+                                                              const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  constexpr uint32_t OFF_K = 0, OFF_V = 16384, OFF_Q = 32768, OFF_DO = 49152, OFF_DS = 65536, OFF_BAR = 98304;
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* bar_q = bar_kv + 1;
+  uint64_t* bar_s = bar_kv + 2;
+  uint64_t* bar_acc = bar_kv + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 4);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int len = min(p.lengths[b], p.T);
+  const int nkb = (len + AT_BK - 1) / AT_BK;
+  const int row_base = b * p.T;
+  const int q_idx = i * AT_BQ + tid;
+  __nv_bfloat16* dq_dst = q_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + q_idx) * p.ld + p.q_col + h * AT_DH : nullptr;
+  if (nkb == 0) {                          // zero-length utterance: the forward output was NaN; define dQ = 0
+    if (dq_dst)
+#pragma unroll
+      for (int g = 0; g < AT_DH / 8; ++g) reinterpret_cast<uint4*>(dq_dst)[g] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO);
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 512); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256;
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, 32768);
+    tma_load_2d(smem + OFF_Q, &tmQKV, bar_q, p.q_col + h * AT_DH, row_base + i * AT_BQ);
+    tma_load_2d(smem + OFF_DO, &tmDO, bar_q, h * AT_DH, row_base + i * AT_BQ);
+  }
+  constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_km = umma_idesc_bf16(128, 64, false, true);
+  const int64_t stat = static_cast<int64_t>(b * p.H + h) * p.T + min(q_idx, p.T - 1);
+  const float lse_r = p.lse[stat], delta_r = p.delta[stat];
+  for (int j = 0; j < nkb; ++j) {
+    const uint32_t ph = j & 1;
+    const int key0 = j * AT_BK;
+    if (tid == 0) {
+      mbar_expect_tx(bar_kv, 32768);
+      tma_load_2d(smem + OFF_K, &tmQKV, bar_kv, p.k_col + h * AT_DH, row_base + key0);
+      tma_load_2d(smem + OFF_V, &tmQKV, bar_kv, p.v_col + h * AT_DH, row_base + key0);
+      if (j == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_base + TM_S, umma_desc_sw128(base + OFF_Q + k * 32, 16, 1024),
+                  umma_desc_sw128(base + OFF_K + k * 32, 16, 1024), idesc_kk, k > 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_base + TM_DP, umma_desc_sw128(base + OFF_DO + k * 32, 16, 1024),
+                  umma_desc_sw128(base + OFF_V + k * 32, 16, 1024), idesc_kk, k > 0);
+      tc_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    attn_bwd_tile_math(p, tm_lane + TM_S, tm_lane + TM_DP, nullptr, smem + OFF_DS, tid, q_idx, key0, len, lse_r,
+                       delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.T);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)          // dQ += dS K   (reduction over the 128 keys; K tile read MN-major)
+        umma_bf16(tmem_base + TM_DQ, umma_desc_sw128(base + OFF_DS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                  umma_desc_sw128(base + OFF_K + k * 2048, 8192, 1024), idesc_km, (j | k) ? 1u : 0u);
+      tc_commit(bar_acc);
+      mbar_wait(bar_acc, ph);
+    }
+    __syncthreads();
+  }
+  tc_fence_after();
+  attn_store_row(tm_lane + TM_DQ, dq_dst);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+constexpr uint32_t ATTN_DKV_SMEM = 131072 + 64 + 1024;
+constexpr uint32_t ATTN_DQ_SMEM = 98304 + 64 + 1024;
+
 
 }  // namespace b2c
 
@@ -239,6 +546,42 @@ extern "C" int b2c_attention_fwd(const void* qkv, int64_t ld, int64_t k_off, int
   p.drop_seed = drop_seed;
   dim3 grid((T + AT_BQ - 1) / AT_BQ, H, B);
   attn_fwd_kernel<<<grid, 128, ATTN_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
+                                 const void* out, const void* dout, int64_t ld_out, const float* lse, float* delta,
+                                 void* dqkv, int B, int T, int H, float scale, float drop_p, uint64_t drop_seed,
+                                 void* stream) {
+  B2C_REQUIRE(qkv && lengths && out && dout && lse && delta && dqkv, "b2c_attention_bwd: null pointer");
+  B2C_REQUIRE(B > 0 && T > 0 && H > 0, "b2c_attention_bwd: empty problem");
+  B2C_REQUIRE(ld % 8 == 0 && ld_out % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
+              "b2c_attention_bwd: pitches/offsets must be multiples of 8 elements");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap tq, td;
+  if (int rc = get_tensor_map_2d(&tq, qkv, 2, static_cast<uint64_t>(ld), static_cast<uint64_t>(B) * T, ld * 2, 64, 128, true)) return rc;
+  if (int rc = get_tensor_map_2d(&td, dout, 2, static_cast<uint64_t>(H) * AT_DH, static_cast<uint64_t>(B) * T, ld_out * 2, 64, 128, true)) return rc;
+  static bool configured = false;
+  if (!configured) {
+    B2C_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_DKV_SMEM));
+    B2C_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_DQ_SMEM));
+    configured = true;
+  }
+  const int64_t n = static_cast<int64_t>(B) * T * H;
+  attn_delta_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), ld_out, delta, B, T, H);
+  AttnBwdParams p;
+  p.lengths = lengths; p.lse = lse; p.delta = delta; p.dqkv = static_cast<__nv_bfloat16*>(dqkv); p.ld = ld;
+  p.B = B; p.T = T; p.H = H;
+  p.q_col = 0; p.k_col = static_cast<int>(k_off); p.v_col = static_cast<int>(v_off);
+  p.scale = scale; p.scale_log2 = scale * LOG2E;
+  p.drop_thresh = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+  p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.drop_seed = drop_seed;
+  dim3 grid((T + AT_BQ - 1) / AT_BQ, H, B);
+  attn_bwd_dkv_kernel<<<grid, 128, ATTN_DKV_SMEM, st>>>(tq, td, p);
+  attn_bwd_dq_kernel<<<grid, 128, ATTN_DQ_SMEM, st>>>(tq, td, p);
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

@@ -163,6 +163,173 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
   reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+
+// ================================================================================================
+// backward of the chain
+//   dz = dc * SiLU'(z),  z = yhat*gamma + beta,  yhat = (y - mean) * rstd
+//   train BN: dy = gamma*rstd * (dz - mean_N(dz) - yhat * mean_N(dz*yhat))     eval BN: dy = gamma*rstd*dz
+//   dg[t] = sum_j w[j] * dy[t + h - j]      dw[j] = sum_t dy[t] * g[t + j - h]      dbdw = sum_t dy[t]
+//   GLU: da = dg * sigmoid(b),  db = dg * a * sigmoid(b) * (1 - sigmoid(b))
+// ================================================================================================
+
+// pass 1: S1 = sum dz, S2 = sum dz*yhat per channel (fp64 atomics, once per CTA per channel) = dbeta, dgamma
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dc,
+                                                           const __nv_bfloat16* __restrict__ y,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                                                           double* __restrict__ sums, int64_t rows, int d,
+                                                           int rows_per_block) {
+  __shared__ float red[2][8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 64 + tx * 2;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+  if (ch < d) {
+    const float m0 = mean[ch], m1 = mean[ch + 1], q0 = rstd[ch], q1 = rstd[ch + 1];
+    const float g0 = bn_w[ch], g1 = bn_w[ch + 1], b0 = bn_b[ch], b1 = bn_b[ch + 1];
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const float2 dcv = unpack_bf16(*reinterpret_cast<const uint32_t*>(dc + r * d + ch));
+      const float2 yv = unpack_bf16(*reinterpret_cast<const uint32_t*>(y + r * d + ch));
+      const float yh0 = (yv.x - m0) * q0, yh1 = (yv.y - m1) * q1;
+      const float dz0 = dcv.x * silu_grad_f(yh0 * g0 + b0), dz1 = dcv.y * silu_grad_f(yh1 * g1 + b1);
+      s1a += dz0; s1b += dz1; s2a += dz0 * yh0; s2b += dz1 * yh1;
+    }
+  }
+  red[0][ty][tx * 2] = s1a; red[0][ty][tx * 2 + 1] = s1b;
+  red[1][ty][tx * 2] = s2a; red[1][ty][tx * 2 + 1] = s2b;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[which][w][c];
+    if (blockIdx.x * 64 + c < d) atomicAdd(sums + static_cast<int64_t>(which) * d + blockIdx.x * 64 + c, static_cast<double>(sum));
+  }
+}
+
+// pass 2: dy on the fly -> du (through depthwise conv + GLU), dwdw, dbdw (fp32 atomics), dbn_w/dbn_b (from sums)
+template <bool BN_TRAIN>
+__global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* __restrict__ dc,
+                                                          const __nv_bfloat16* __restrict__ y,
+                                                          const __nv_bfloat16* __restrict__ u,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                                                          const double* __restrict__ sums, double inv_count,
+                                                          const float* __restrict__ wdw, __nv_bfloat16* __restrict__ du,
+                                                          float* __restrict__ dwdw, float* __restrict__ dbdw,
+                                                          float* __restrict__ dbn_w, float* __restrict__ dbn_b, int T,
+                                                          int d, int k) {
+  extern __shared__ float2 sbuf[];
+  const int nrow = CM_TT + k - 1;
+  float2* sG = sbuf;                                 // GLU(u)  [nrow][32]
+  float2* sDY = sbuf + nrow * 32;                    // dy      [nrow][32]
+  float* sW = reinterpret_cast<float*>(sbuf + 2 * nrow * 32);   // dw partials [64][CM_MAXK] + dbdw [64]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t0 = blockIdx.x * CM_TT, c0 = blockIdx.y * CM_CH, b = blockIdx.z;
+  const int half = (k - 1) / 2;
+  const int ch = c0 + lane * 2;
+  const bool ch_ok = ch < d;
+  for (int i = threadIdx.x; i < CM_CH * (CM_MAXK + 1); i += blockDim.x) sW[i] = 0.f;
+
+  stage_glu(u, sG, b, T, d, c0, t0 - half, nrow);
+  {
+    float m0 = 0, m1 = 0, q0 = 0, q1 = 0, g0 = 0, g1 = 0, b0 = 0, b1 = 0, a10 = 0, a11 = 0, a20 = 0, a21 = 0;
+    if (ch_ok) {
+      m0 = mean[ch]; m1 = mean[ch + 1]; q0 = rstd[ch]; q1 = rstd[ch + 1];
+      g0 = bn_w[ch]; g1 = bn_w[ch + 1]; b0 = bn_b[ch]; b1 = bn_b[ch + 1];
+      if (BN_TRAIN) {
+        a10 = static_cast<float>(sums[ch] * inv_count); a11 = static_cast<float>(sums[ch + 1] * inv_count);
+        a20 = static_cast<float>(sums[d + ch] * inv_count); a21 = static_cast<float>(sums[d + ch + 1] * inv_count);
+      }
+      if (blockIdx.x == 0 && blockIdx.z == 0 && warp == 0) {     // parameter grads of BN = the two sums
+        atomicAdd(dbn_b + ch, static_cast<float>(sums[ch])); atomicAdd(dbn_b + ch + 1, static_cast<float>(sums[ch + 1]));
+        atomicAdd(dbn_w + ch, static_cast<float>(sums[d + ch])); atomicAdd(dbn_w + ch + 1, static_cast<float>(sums[d + ch + 1]));
+      }
+    }
+    for (int r = warp; r < nrow; r += 8) {
+      const int t = t0 - half + r;
+      float2 dyv = make_float2(0.f, 0.f);
+      if (t >= 0 && t < T && ch_ok) {
+        const int64_t row = static_cast<int64_t>(b) * T + t;
+        const float2 dcv = unpack_bf16(*reinterpret_cast<const uint32_t*>(dc + row * d + ch));
+        const float2 yv = unpack_bf16(*reinterpret_cast<const uint32_t*>(y + row * d + ch));
+        const float yh0 = (yv.x - m0) * q0, yh1 = (yv.y - m1) * q1;
+        const float dz0 = dcv.x * silu_grad_f(yh0 * g0 + b0), dz1 = dcv.y * silu_grad_f(yh1 * g1 + b1);
+        dyv.x = g0 * q0 * (BN_TRAIN ? (dz0 - a10 - yh0 * a20) : dz0);
+        dyv.y = g1 * q1 * (BN_TRAIN ? (dz1 - a11 - yh1 * a21) : dz1);
+      }
+      sDY[r * 32 + lane] = dyv;
+    }
+  }
+  float w0[CM_MAXK], w1[CM_MAXK];                     // REVERSED taps: wr[j'] = w[k-1-j']
+#pragma unroll
+  for (int j = 0; j < CM_MAXK; ++j) {
+    w0[j] = (j < k && ch_ok) ? __ldg(wdw + static_cast<int64_t>(ch) * k + (k - 1 - j)) : 0.f;
+    w1[j] = (j < k && ch_ok) ? __ldg(wdw + static_cast<int64_t>(ch + 1) * k + (k - 1 - j)) : 0.f;
+  }
+  __syncthreads();
+
+  float acc0[CM_MAXK], acc1[CM_MAXK];                 // dw partials of this lane's two channels
+#pragma unroll
+  for (int j = 0; j < CM_MAXK; ++j) acc0[j] = acc1[j] = 0.f;
+  float dbs0 = 0.f, dbs1 = 0.f;
+#pragma unroll 1
+  for (int grp = 0; grp < (CM_TT / 8) / CM_G; ++grp) {
+    const int tl = warp * (CM_TT / 8) + grp * CM_G;
+    float a0[CM_G], a1[CM_G];                         // dg for 8 frames
+    float2 dyc[CM_G];                                 // dy at the 8 centre frames
+#pragma unroll
+    for (int i = 0; i < CM_G; ++i) { a0[i] = 0.f; a1[i] = 0.f; dyc[i] = sDY[(tl + half + i) * 32 + lane]; }
+#pragma unroll
+    for (int r = 0; r < CM_G + CM_MAXK - 1; ++r) {
+      if (r < CM_G + k - 1) {
+        const float2 dyr = sDY[(tl + r) * 32 + lane];
+        const float2 gr = sG[(tl + r) * 32 + lane];
+#pragma unroll
+        for (int i = 0; i < CM_G; ++i) {
+          const int j = r - i;
+          if (j >= 0 && j < CM_MAXK) {
+            a0[i] = fmaf(dyr.x, w0[j], a0[i]); a1[i] = fmaf(dyr.y, w1[j], a1[i]);       // dg
+            acc0[j] = fmaf(dyc[i].x, gr.x, acc0[j]); acc1[j] = fmaf(dyc[i].y, gr.y, acc1[j]);   // dw[j] += dy[t]*g[t+j-h]
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CM_G; ++i) {
+      dbs0 += dyc[i].x; dbs1 += dyc[i].y;
+      const int t = t0 + tl + i;
+      if (t < T && ch_ok) {
+        const int64_t row = static_cast<int64_t>(b) * T + t;
+        const float2 av = unpack_bf16(*reinterpret_cast<const uint32_t*>(u + row * 2 * d + ch));
+        const float2 bv = unpack_bf16(*reinterpret_cast<const uint32_t*>(u + row * 2 * d + d + ch));
+        const float s0 = sigmoid_f(bv.x), s1 = sigmoid_f(bv.y);
+        *reinterpret_cast<uint32_t*>(du + row * 2 * d + ch) = pack_bf16(a0[i] * s0, a1[i] * s1);
+        *reinterpret_cast<uint32_t*>(du + row * 2 * d + d + ch) =
+            pack_bf16(a0[i] * av.x * s0 * (1.f - s0), a1[i] * av.y * s1 * (1.f - s1));
+      }
+    }
+  }
+  // CTA-level reduction of dw / dbdw over the 8 warps (shared-memory atomics), then one global atomic each
+#pragma unroll
+  for (int j = 0; j < CM_MAXK; ++j) {
+    if (j < k) {
+      atomicAdd(&sW[(lane * 2) * (CM_MAXK + 1) + j], acc0[j]);
+      atomicAdd(&sW[(lane * 2 + 1) * (CM_MAXK + 1) + j], acc1[j]);
+    }
+  }
+  atomicAdd(&sW[(lane * 2) * (CM_MAXK + 1) + CM_MAXK], dbs0);
+  atomicAdd(&sW[(lane * 2 + 1) * (CM_MAXK + 1) + CM_MAXK], dbs1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < CM_CH * (CM_MAXK + 1); i += blockDim.x) {
+    const int c = i / (CM_MAXK + 1), j = i % (CM_MAXK + 1);
+    if (c0 + c >= d) continue;
+    if (j == CM_MAXK) atomicAdd(dbdw + c0 + c, sW[i]);
+    else if (j < k) atomicAdd(dwdw + static_cast<int64_t>(c0 + c) * k + j, sW[i]);
+  }
+}
+
 static int check_convmod(int B, int T, int d, int k, const char* who) {
   B2C_REQUIRE(B > 0 && T > 0 && d > 0, "%s: empty problem", who);
   B2C_REQUIRE(d % 8 == 0, "%s: d=%d must be a multiple of 8", who, d);
@@ -219,6 +386,51 @@ extern "C" int b2c_convmod_bn_apply(const void* y, const float* mean, const floa
   if (n8 <= 0) return 0;
   bn_apply_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(y), mean, rstd, bn_w, bn_b, static_cast<__nv_bfloat16*>(out), n8, d);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2c_convmod_bn_bwd_reduce(const void* dc, const void* y, const float* mean, const float* rstd,
+                                         const float* bn_w, const float* bn_b, double* sums, int64_t rows, int d,
+                                         void* stream) {
+  B2C_REQUIRE(dc && y && mean && rstd && bn_w && bn_b && sums, "b2c_convmod_bn_bwd_reduce: null pointer");
+  B2C_REQUIRE(d % 8 == 0, "b2c_convmod_bn_bwd_reduce: d must be a multiple of 8");
+  if (rows <= 0) return 0;
+  const unsigned gx = static_cast<unsigned>((d + 63) / 64);
+  int64_t want_y = (static_cast<int64_t>(num_sms()) * 4 + gx - 1) / gx;
+  int rows_per_block = static_cast<int>((rows + want_y - 1) / want_y);
+  rows_per_block = ((rows_per_block + 7) / 8) * 8;
+  const unsigned gy = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
+  bn_bwd_reduce_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dc), static_cast<const __nv_bfloat16*>(y), mean, rstd, bn_w, bn_b, sums, rows, d,
+      rows_per_block);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2c_convmod_dw_bwd(const void* dc, const void* y, const void* u, const float* mean, const float* rstd,
+                                  const float* bn_w, const float* bn_b, const double* sums, int bn_train,
+                                  const float* wdw, void* du, float* dwdw, float* dbdw, float* dbn_w, float* dbn_b,
+                                  int B, int T, int d, int k, void* stream) {
+  B2C_REQUIRE(dc && y && u && mean && rstd && bn_w && bn_b && sums && wdw && du && dwdw && dbdw && dbn_w && dbn_b,
+              "b2c_convmod_dw_bwd: null pointer");
+  if (int rc = check_convmod(B, T, d, k, "b2c_convmod_dw_bwd")) return rc;
+  dim3 grid((T + CM_TT - 1) / CM_TT, (d + CM_CH - 1) / CM_CH, B);
+  const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) * 2 + CM_CH * (CM_MAXK + 1) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    B2C_CUDA(cudaFuncSetAttribute(convmod_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  const double inv_count = 1.0 / (static_cast<double>(B) * T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto args = [&](auto kern) {
+    kern<<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(dc), static_cast<const __nv_bfloat16*>(y),
+                                  static_cast<const __nv_bfloat16*>(u), mean, rstd, bn_w, bn_b, sums, inv_count, wdw,
+                                  static_cast<__nv_bfloat16*>(du), dwdw, dbdw, dbn_w, dbn_b, T, d, k);
+  };
+  if (bn_train) args(convmod_bwd_kernel<true>); else args(convmod_bwd_kernel<false>);
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

@@ -173,6 +173,23 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   }
 }
 
+// table entries: {src fp32*, dst bf16*, n}; blockIdx.y = tensor, grid-stride over 8-element chunks
+struct CastEntry { const float* src; __nv_bfloat16* dst; int64_t n; };
+__global__ void multi_cast_kernel(const CastEntry* __restrict__ table) {
+  const CastEntry e = table[blockIdx.y];
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
+  for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < e.n; i += stride) {
+    if (i + 8 <= e.n) {
+      const float4 a = *reinterpret_cast<const float4*>(e.src + i);
+      const float4 b = *reinterpret_cast<const float4*>(e.src + i + 4);
+      *reinterpret_cast<uint4*>(e.dst + i) =
+          make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+    } else {
+      for (int64_t j = i; j < e.n; ++j) e.dst[j] = __float2bfloat16(e.src[j]);
+    }
+  }
+}
+
 __global__ void scale_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n,
                                   float alpha, uint32_t thresh, float inv_keep, uint64_t seed) {
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
@@ -272,6 +289,17 @@ extern "C" int b2c_cast_f32_bf16(const float* src, void* dst, int64_t n, void* s
   const int64_t threads = (n + 7) / 8;
   cast_f32_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<__nv_bfloat16*>(dst), n);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2c_multi_cast_f32_bf16(const void* table_dev, int n_tensors, int64_t max_n, void* stream) {
+  B2C_REQUIRE(table_dev && n_tensors > 0, "b2c_multi_cast_f32_bf16: bad argument");
+  int64_t gx = (max_n / 8 + 255) / 256;
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  multi_cast_kernel<<<dim3(static_cast<unsigned>(gx), n_tensors), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const CastEntry*>(table_dev));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

@@ -212,3 +212,28 @@ def repack_heads(src, nblk: int, src_dh: int, dst_dh: int):
     dst = torch.empty((rows, nblk * dst_dh), device=src.device, dtype=torch.bfloat16)
     call("b2c_repack_heads", ptr(src), ptr(dst), rows, nblk, src_dh, dst_dh, stream_ptr())
     return dst
+
+
+def convmod_bn_bwd_reduce(dc, y, mean, rstd, bn_w, bn_b):
+    rows, d = y.shape
+    sums = torch.zeros(2 * d, device=y.device, dtype=torch.float64)
+    call("b2c_convmod_bn_bwd_reduce", ptr(dc), ptr(y), ptr(mean), ptr(rstd), ptr(bn_w), ptr(bn_b), ptr(sums), rows, d,
+         stream_ptr())
+    return sums
+
+
+def convmod_dw_bwd(dc, y, u, mean, rstd, bn_w, bn_b, sums, bn_train: bool, wdw, dwdw, dbdw, dbn_w, dbn_b, B: int, T: int):
+    d, k = wdw.shape[0], wdw.shape[-1]
+    du = torch.empty((B * T, 2 * d), device=u.device, dtype=torch.bfloat16)
+    call("b2c_convmod_dw_bwd", ptr(dc), ptr(y), ptr(u), ptr(mean), ptr(rstd), ptr(bn_w), ptr(bn_b), ptr(sums),
+         int(bn_train), ptr(wdw), ptr(du), ptr(dwdw), ptr(dbdw), ptr(dbn_w), ptr(dbn_b), B, T, d, k, stream_ptr())
+    return du
+
+
+def attention_bwd(qkv, lengths_i32, att, datt, lse, B: int, T: int, H: int, scale: float, drop_p: float = 0.0,
+                  drop_seed: int = 0):
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32)
+    call("b2c_attention_bwd", ptr(qkv), qkv.stride(0), H * 64, 2 * H * 64, ptr(lengths_i32), ptr(att), ptr(datt),
+         att.stride(0), ptr(lse), ptr(delta), ptr(dqkv), B, T, H, scale, drop_p, drop_seed, stream_ptr())
+    return dqkv

@@ -1,0 +1,121 @@
+"""Drop-in for `ASRNN.SpecAugment / time_warping / frequency_masking / time_masking`
+(/root/reference/lib/standard/asrnn.py:91-192).
+
+The random draws are made on the host with the interpreter's GLOBAL `random` module, in exactly the order the
+reference makes them -- so `random.seed(s)` before the call gives the same parameters and
+leaves the stream in the same state as the reference would.  The data path is one sm_100a kernel
+(csrc/specaug.cu): warp gather + masks, no host round trip of the spectrogram.
+
+mode="reference" (default): bit-exact with the code as it runs -- the two mask assignments at asrnn.py:141,165 hit
+    temporaries, so the frequency/time masks are drawn but never applied.
+mode="paper": same draws, masks applied as the docstrings / main.ipynb cell 24 describe.
+Functions take `self` (anything with an `.hp`) so they can be bound onto an ASRNN instance (see patch.py).
+"""
+from __future__ import annotations
+
+import random
+from math import floor
+
+import torch
+
+from . import _lib, ops
+
+MODE = "reference"      # module-level default; patch_asrnn(model, specaug_mode=...) overrides per model
+
+
+def _mode(self):
+    return getattr(self, "_b2c_specaug_mode", MODE)
+
+
+def _tau_list(tau):
+    if isinstance(tau, torch.Tensor):
+        return [int(v) for v in tau.tolist()]
+    return [int(v) for v in tau]
+
+
+def _i32(values, device):
+    return torch.tensor(values, dtype=torch.int32).to(device, non_blocking=True)
+
+
+def _draw_warp(hp, B, tau):
+    W = hp.warping_param_W
+    ws, w0s = [], []
+    for u in range(B):
+        w = random.randint(-W, W)                                             # asrnn.py:103
+        w0 = W if tau[u] < 2 * W else random.randint(W, tau[u] - W - 1)       # asrnn.py:104-107 (ValueError if tau==2W)
+        if tau[u] > 0 and w0 == 0:
+            raise ZeroDivisionError("division by zero")                       # (w0+w)/w0 at asrnn.py:110
+        ws.append(w)
+        w0s.append(w0)
+    return ws, w0s
+
+
+def _draw_fmask(hp, v):
+    f = random.randint(0, hp.frequency_mask_param_F)                          # asrnn.py:138
+    f0 = random.randint(0, v - hp.frequency_mask_param_F)                     # asrnn.py:139
+    return f0, f
+
+
+def _draw_tmask(hp, B, tau):
+    out = []
+    for u in range(B):
+        T_ = floor(hp.ps * tau[u]) if (u < len(tau) and hp.adaptive_size) else hp.time_mask_param_T
+        t = random.randint(0, T_)                                             # asrnn.py:162
+        t0 = random.randint(0, max(tau[u] - T_, tau[u]))                      # asrnn.py:163
+        out.append((t0, t))
+    return out
+
+
+def _launch(x3, tau, warps, fmasks, tmasks, apply_masks, mask_value):
+    dev = x3.device
+    B = x3.shape[0]
+    tau_t = _i32(tau + [0] * (B - len(tau)), dev)
+    ww = _i32([w[0] for w in warps], dev) if warps else None
+    w0 = _i32([w[1] for w in warps], dev) if warps else None
+    fm = _i32(fmasks, dev) if fmasks else None
+    tm = _i32(tmasks, dev) if tmasks else None
+    return ops.specaug_apply(x3.to(torch.float32).contiguous(), tau_t, ww, w0, fm, tm, apply_masks, float(mask_value))
+
+
+def time_warping(self, x, tau):
+    """asrnn.py:91-125: x (B,F,T) -> (B,F,T) fp32 on the input's device."""
+    tau = _tau_list(tau)
+    return _launch(x, tau, [_draw_warp(self.hp, x.shape[0], tau)], [], [], False, 0.0)
+
+
+def frequency_masking(self, x):
+    """asrnn.py:127-144: draws (f, f0); masks rows only in "paper" mode."""
+    f0, f = _draw_fmask(self.hp, x.shape[1])
+    if _mode(self) == "reference":
+        return x.clone()
+    return _launch(x, [x.shape[2]] * x.shape[0], [], [(f0, f)], [], True, self.hp.mask_value)
+
+
+def time_masking(self, x, tau):
+    """asrnn.py:146-168."""
+    tau = _tau_list(tau)
+    tm = _draw_tmask(self.hp, x.shape[0], tau)
+    if _mode(self) == "reference":
+        return x.clone()
+    return _launch(x, tau, [], [], [tm], True, self.hp.mask_value)
+
+
+def SpecAugment(self, x, tau):
+    """asrnn.py:170-192: (B,1,F,T) -> (B,1,F,T); all passes fused into one kernel launch."""
+    _lib.require_device()
+    hp = self.hp
+    x = x.squeeze()
+    if len(list(x.shape)) < 3:
+        x = x.unsqueeze(0)
+    if x.dim() != 3:
+        raise ValueError(f"SpecAugment expects (B,1,F,T) with F,T > 1; got squeezed shape {tuple(x.shape)}")
+    B, F, _ = x.shape
+    tau = _tau_list(tau)
+    warps = [_draw_warp(hp, B, tau) for _ in range(hp.warping_ntimes)]                     # asrnn.py:183-184
+    fmasks = [_draw_fmask(hp, F) for _ in range(hp.frequency_mask_ntimes)]                 # asrnn.py:185-186
+    Mt = hp.time_multiplicity
+    if hp.adaptive_multiplicity:
+        Mt = min(Mt, floor(hp.pm))                                                          # asrnn.py:188-189
+    tmasks = [_draw_tmask(hp, B, tau) for _ in range(Mt)]                                   # asrnn.py:190-191
+    out = _launch(x, tau, warps, fmasks, tmasks, _mode(self) == "paper", hp.mask_value)
+    return out.unsqueeze(1)
