@@ -95,14 +95,39 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name: str, *args) -> None:
-    """Invoke an int-returning entry point on the current torch stream; raise with the library's message on error."""
+_profile = None       # list of (name, start_event, end_event, flops, bytes) while an instrumented step runs
+
+
+def call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0) -> None:
+    """Invoke an int-returning entry point on the current torch stream; raise with the library's message on error.
+    flops / nbytes = ALGORITHMIC work of the launch (used only by bench.py's instrumented step)."""
     global LAUNCHES
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(load(), name)(*args)
     if rc != 0:
         kind = ValueError if rc < 0 else B2CError
         raise kind(f"{name} failed (rc={rc}): {last_error()}")
+    if _profile is not None:
+        e1.record()
+        _profile.append((name, e0, e1, flops, nbytes))
     LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
+
+
+def profile_begin():
+    """Start recording a CUDA-event pair around every launch (on the launching stream)."""
+    global _profile
+    _profile = []
+    return _profile
+
+
+def profile_end(prof):
+    """-> [(entry point, milliseconds, flops, bytes)]"""
+    global _profile
+    _profile = None
+    torch.cuda.synchronize()
+    return [(n, a.elapsed_time(b), fl, nb) for n, a, b, fl, nb in prof]
 
 
 _checked = False

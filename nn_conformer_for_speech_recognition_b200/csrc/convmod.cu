@@ -102,6 +102,10 @@ __global__ void __launch_bounds__(256) convmod_fwd_kernel(const __nv_bfloat16* _
       if (t < T && ch_ok) {
         float y0 = a0[i], y1 = a1[i];
         if (MODE == 1) {
+          // statistics of the STORED (bf16-rounded) tensor: BatchNorm and its backward then see exactly the y they
+          // normalise, so sum(yhat) = 0 and the analytically-zero gradients (depthwise bias) stay ~0
+          const float2 yr = unpack_bf16(pack_bf16(y0, y1));
+          y0 = yr.x; y1 = yr.y;
           s_sum0 += y0; s_sum1 += y1; s_sq0 += y0 * y0; s_sq1 += y1 * y1;
         } else {
           y0 = silu_f(y0 * sc0 + sh0);

@@ -56,7 +56,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_mn: bool
     ep.out_dtype = BF16 if out.dtype == torch.bfloat16 else F32
     ep.accumulate = int(accumulate)
     call("b2c_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), M, N, K, split_k, block_n,
-         ctypes.byref(ep), stream_ptr())
+         ctypes.byref(ep), stream_ptr(), flops=2.0 * M * N * K)
     return out
 
 
@@ -91,7 +91,7 @@ def convmod_eval(u, wdw, bdw, bn_w, bn_b, bn_mean, bn_var, B: int, T: int, eps: 
     d, k = wdw.shape[0], wdw.shape[-1]
     out = torch.empty((B * T, d), device=u.device, dtype=torch.bfloat16)
     call("b2c_convmod_eval_fwd", ptr(u), ptr(wdw), ptr(bdw), ptr(bn_w), ptr(bn_b), ptr(bn_mean), ptr(bn_var), eps,
-         ptr(out), B, T, d, k, stream_ptr())
+         ptr(out), B, T, d, k, stream_ptr(), nbytes=3.0 * B * T * d * 2)
     return out
 
 
@@ -99,7 +99,8 @@ def convmod_dw_fwd(u, wdw, bdw, B: int, T: int):
     d, k = wdw.shape[0], wdw.shape[-1]
     y = torch.empty((B * T, d), device=u.device, dtype=torch.bfloat16)
     stats = torch.zeros(2 * d, device=u.device, dtype=torch.float64)
-    call("b2c_convmod_dw_fwd", ptr(u), ptr(wdw), ptr(bdw), ptr(y), ptr(stats), B, T, d, k, stream_ptr())
+    call("b2c_convmod_dw_fwd", ptr(u), ptr(wdw), ptr(bdw), ptr(y), ptr(stats), B, T, d, k, stream_ptr(),
+         nbytes=3.0 * B * T * d * 2)
     return y, stats
 
 
@@ -128,7 +129,7 @@ def attention_fwd(qkv: torch.Tensor, lengths_i32: torch.Tensor, B: int, T: int, 
     out = torch.empty((B * T, H * 64), device=qkv.device, dtype=torch.bfloat16)
     lse = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32) if save_lse else None
     call("b2c_attention_fwd", ptr(qkv), qkv.stride(0), H * 64, 2 * H * 64, ptr(lengths_i32), ptr(out), out.stride(0),
-         ptr(lse), B, T, H, scale, drop_p, drop_seed, stream_ptr())
+         ptr(lse), B, T, H, scale, drop_p, drop_seed, stream_ptr(), flops=4.0 * B * H * T * T * 64)
     return (out, lse) if save_lse else out
 
 
@@ -235,5 +236,6 @@ def attention_bwd(qkv, lengths_i32, att, datt, lse, B: int, T: int, H: int, scal
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32)
     call("b2c_attention_bwd", ptr(qkv), qkv.stride(0), H * 64, 2 * H * 64, ptr(lengths_i32), ptr(att), ptr(datt),
-         att.stride(0), ptr(lse), ptr(delta), ptr(dqkv), B, T, H, scale, drop_p, drop_seed, stream_ptr())
+         att.stride(0), ptr(lse), ptr(delta), ptr(dqkv), B, T, H, scale, drop_p, drop_seed, stream_ptr(),
+         flops=14.0 * B * H * T * T * 64)
     return dqkv
