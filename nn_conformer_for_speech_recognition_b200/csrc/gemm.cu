@@ -11,13 +11,19 @@
 //
 // Replaces, on the reference path: cuBLASLt GEMMs behind torch.nn.Linear / Conv1d(k=1) in
 // torchaudio/models/conformer.py:44-51,66-73,102-109 and the in/out projections of nn.MultiheadAttention
-// (torch/nn/functional.py:5798,6690), with the bias / SiLU / 0.5*residual elementwise kernels fused as epilogue.
+// (torch/nn/functional.py:5798,6690), with the bias / SiLU / 0.5*residual / dropout elementwise kernels fused as epilogue.
 //
-// Structure: one 128 x BN output tile per CTA, 192 threads:
-//   warp 0    TMA producer (one elected lane)  -> 128B-swizzled smem ring, mbarrier full/empty
-//   warp 1    TMEM allocator + MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16
-//   warps 2-5 epilogue: tcgen05.ld 32x32b (thread = accumulator row) -> bias/act/residual/dropout -> global
-// 2-3 CTAs are co-resident per SM (TMEM BN columns each), so one CTA's epilogue overlaps another's main loop.
+// Structure: PERSISTENT kernel, one CTA per SM, 320 threads, static round-robin over 128 x BN output tiles
+// (n fastest, so CTAs running side by side share the same A rows in L2):
+//   warp 0     TMA producer (one elected lane) -> 128B-swizzled smem ring (mbarrier full/empty), runs ahead across tiles
+//   warp 1     TMEM allocator + MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16,
+//              accumulators DOUBLE-BUFFERED in TMEM (2 x BN columns): tile i+1's main loop overlaps tile i's epilogue
+//   warps 2-9  epilogue (8 warps; warp w owns TMEM lanes 32*(w%4).. and one half of the BN columns):
+//              tcgen05.ld (thread = row) -> release the TMEM buffer -> XOR-swizzled smem transpose (per warp, no CTA
+//              barrier) -> coalesced domain (lanes along columns): bias / SiLU / SiLU' / dropout / residual and
+//              128-byte coalesced global loads & stores (or red.global.add.v4.f32 for split-K / gradient accumulation)
+// The problems here are skinny (K = 144..2304) so a tile's main loop is only 3-16 k-blocks: the epilogue, not the MMA,
+// is the critical resource -- hence 8 epilogue warps, MUFU.TANH-based SiLU and the overlap through TMEM.
 #include "common.cuh"
 #include "b200conformer.h"
 
@@ -25,40 +31,54 @@ namespace b2c {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
+constexpr int GEMM_THREADS = 320;
+constexpr int EPI_WARPS = 8;
 
 struct GemmParams {
   int64_t M, N, K;
-  int kblocks_per_split;
+  int kblocks_per_split, total_kb;
+  int m_tiles, n_tiles, splits, total_tiles;
   b2c_epilogue ep;
 };
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 3 : 4;
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int CW = (BN / 2 < 64) ? BN / 2 : 64;                 // columns per epilogue chunk
+  static constexpr int CHUNKS = (BN / 2) / CW;                           // chunks per epilogue warp per tile
+  static constexpr uint32_t STG_WARP_BYTES = 32 * CW * 4;                // fp32 transpose buffer per warp
+  static constexpr uint32_t STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr uint32_t BAR_OFF = STG_OFF + EPI_WARPS * STG_WARP_BYTES;
+  static constexpr uint32_t SMEM = BAR_OFF + 256 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid via one MUFU.TANH: 0.5*tanh(0.5 z) + 0.5 (abs error ~1e-3 of an output that is rounded to bf16 anyway)
+__device__ __forceinline__ float sigmoid_fast(float z) { return fmaf(0.5f, tanh_approx(0.5f * z), 0.5f); }
+
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB,
-                                                           const GemmParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                       const __grid_constant__ CUtensorMap tmB,
+                                                                       const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* accum_bar = empty_bar + Cfg::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;     // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained (8 epilogue warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_blk = blockIdx.x, n_blk = blockIdx.y;
-  const int total_kb = static_cast<int>((p.K + BK - 1) / BK);
-  const int kb0 = blockIdx.z * p.kblocks_per_split;
-  const int kb1 = min(total_kb, kb0 + p.kblocks_per_split);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -67,150 +87,193 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], EPI_WARPS);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ================================ TMA producer ================================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
-        uint8_t* sB = sA + Cfg::A_BYTES;
-        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        if constexpr (!A_MN) {
-          tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m_blk * BM);
-        } else {
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;
+        const int m_blk = (tile / p.n_tiles) % p.m_tiles;
+        const int split = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(p.total_kb, kb0 + p.kblocks_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          if constexpr (!A_MN) {
+            tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m_blk * BM);
+          } else {
 #pragma unroll
-          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sA + c * 8192, &tmA, &full_bar[s], m_blk * BM + c * 64, kb * BK);
-        }
-        if constexpr (!B_MN) {
-          tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n_blk * BN);
-        } else {
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sA + c * 8192, &tmA, &full_bar[s], m_blk * BM + c * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n_blk * BN);
+          } else {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sB + c * 8192, &tmB, &full_bar[s], n_blk * BN + c * 64, kb * BK);
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sB + c * 8192, &tmB, &full_bar[s], n_blk * BN + c * 64, kb * BK);
+          }
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
         }
-        if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
+    // ================================ MMA issuer ================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int split = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(p.total_kb, kb0 + p.kblocks_per_split);
+        const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+        mbar_wait(&tempty_bar[as], aph ^ 1u);          // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t a_addr = base + s * Cfg::STAGE_BYTES;
-        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+        const uint32_t tm_acc = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = base + s * Cfg::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = A_MN ? umma_desc_sw128(a_addr + k * 2048, 8192, 1024)
-                                   : umma_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? umma_desc_sw128(b_addr + k * 2048, 8192, 1024)
-                                   : umma_desc_sw128(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                     : umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                     : umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(tm_acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);                    // smem slot free once these MMAs retire
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
         }
-        tc_commit(&empty_bar[s]);
-        if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+        tc_commit(&tfull_bar[as]);                     // accumulator complete -> epilogue
       }
-      tc_commit(accum_bar);
     }
   } else {
-    // ------------------------------ epilogue: thread <-> accumulator row ------------------------------
+    // ================================ epilogue (8 warps) ================================
     const b2c_epilogue& ep = p.ep;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const int q = warp & 3;
-    const int64_t row = static_cast<int64_t>(m_blk) * BM + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    const float* bias = blockIdx.z == 0 ? static_cast<const float*>(ep.bias) : nullptr;   // once per split-K
+    constexpr int CW = Cfg::CW;
+    constexpr int LPR = CW / 4;                        // lanes per row in the coalesced domain (float4 each)
+    constexpr int RPI = 32 / LPR;                      // rows per warp instruction
+    const int ew = warp - 2;
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                          // which half of the BN columns
+    float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF + ew * Cfg::STG_WARP_BYTES);
     const uint32_t drop_thresh = ep.drop_p > 0.f ? static_cast<uint32_t>(ep.drop_p * 4294967296.0) : 0u;
     const float inv_keep = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
+    const int c_lane = lane % LPR;                     // float4 chunk (column group) this lane owns after the transpose
+    const int r_lane = lane / LPR;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int n_blk = tile % p.n_tiles;
+      const int m_blk = (tile / p.n_tiles) % p.m_tiles;
+      const int split = tile / (p.n_tiles * p.m_tiles);
+      const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const float* bias = split == 0 ? static_cast<const float*>(ep.bias) : nullptr;   // once per split-K
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      __syncwarp();                            // tcgen05.ld is .sync.aligned: reconverge after masked stores
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
-      tmem_wait_ld();
-      const int64_t col0 = static_cast<int64_t>(n_blk) * BN + c;
-      if (!row_ok || col0 >= p.N) continue;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {            // 4 groups of 8 columns
-        const int64_t col = col0 + g * 8;
-        if (col >= p.N) break;
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-        if (bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
-          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-          f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+      for (int ch = 0; ch < Cfg::CHUNKS; ++ch) {
+        const int col_t = half * (BN / 2) + ch * CW;   // first column of this chunk inside the tile
+        uint32_t v[CW];
+        __syncwarp();
+        const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16) + col_t;
+        tmem_ld32(taddr, v);
+        if constexpr (CW == 64) tmem_ld32(taddr + 32, v + 32);
+        tmem_wait_ld();
+        if (ch == Cfg::CHUNKS - 1) {                   // all of this warp's TMEM reads for the tile are done
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
-        if (ep.out2) {                         // pre-activation copy (saved for the backward pass)
-          uint4 u = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out2) + row * ep.ld_out2 + col) = u;
-        }
-        if (ep.act == B2C_ACT_SILU) {
+        // transpose through smem: row = lane, 16-byte chunk c stored at (c ^ (lane & 7))
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
-        } else if (ep.act == B2C_ACT_SILU_BWD) {   // f = dL/dh ; aux = pre-activation u ; out = f * silu'(u)
-          const uint4 a = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(ep.aux) + row * ep.ld_aux + col);
-          const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-          const float u[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+        for (int c = 0; c < LPR; ++c)
+          *reinterpret_cast<uint4*>(stg + lane * CW + ((c ^ (lane & 7)) << 2)) =
+              make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        __syncwarp();
+        const int64_t col = static_cast<int64_t>(n_blk) * BN + col_t + c_lane * 4;
+        const bool col_ok = col < p.N;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+#pragma unroll 4
+        for (int i = 0; i < 32 / RPI; ++i) {
+          const int r = i * RPI + r_lane;
+          const int64_t row = static_cast<int64_t>(m_blk) * BM + q * 32 + r;
+          if (row >= p.M || !col_ok) continue;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + r * CW + ((c_lane ^ (r & 7)) << 2));
+          float f[4] = {a4.x + bv.x, a4.y + bv.y, a4.z + bv.z, a4.w + bv.w};
+          if (ep.out2)                                 // pre-activation copy (saved for the backward pass)
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(ep.out2) + row * ep.ld_out2 + col) =
+                make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+          if (ep.act == B2C_ACT_SILU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] *= silu_grad_f(u[j]);
-        }
-        if (drop_thresh) {
+            for (int j = 0; j < 4; ++j) f[j] *= sigmoid_fast(f[j]);
+          } else if (ep.act == B2C_ACT_SILU_BWD) {     // f = dL/dh ; aux = pre-activation u ; out = f * silu'(u)
+            const uint2 a = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(ep.aux) + row * ep.ld_aux + col);
+            const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y);
+            const float u[4] = {a0.x, a0.y, a1.x, a1.y};
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            f[j] *= drop_scale(ep.drop_seed, static_cast<uint64_t>(row) * p.N + col + j, drop_thresh, inv_keep);
-        }
-        if (ep.alpha != 1.f) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] *= ep.alpha;
-        }
-        if (ep.out_dtype == B2C_BF16) {
-          uint4 u = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + row * ep.ld_out + col) = u;
-        } else {
-          float* o = static_cast<float*>(ep.out) + row * ep.ld_out + col;
-          if (ep.accumulate) {                 // split-K / gradient accumulation: fp32 reductions in L2
-#pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(o + j, f[j]);
-          } else {
-            if (ep.resid) {
-              const float* r = static_cast<const float*>(ep.resid) + row * ep.ld_out + col;
-              const float4 r0 = *reinterpret_cast<const float4*>(r);
-              const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
-              f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-              f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+            for (int j = 0; j < 4; ++j) {
+              const float sg = sigmoid_fast(u[j]);
+              f[j] *= sg * fmaf(u[j], 1.f - sg, 1.f);
             }
-            *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          }
+          if (drop_thresh) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              f[j] *= drop_scale(ep.drop_seed, static_cast<uint64_t>(row) * p.N + col + j, drop_thresh, inv_keep);
+          }
+          if (ep.alpha != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] *= ep.alpha;
+          }
+          if (ep.out_dtype == B2C_BF16) {
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(ep.out) + row * ep.ld_out + col) =
+                make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+          } else {
+            float* o = static_cast<float*>(ep.out) + row * ep.ld_out + col;
+            if (ep.accumulate) {                       // split-K / gradient accumulation: fp32 reductions in L2
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3])
+                           : "memory");
+            } else {
+              if (ep.resid) {
+                const float4 r4 = *reinterpret_cast<const float4*>(static_cast<const float*>(ep.resid) + row * ep.ld_out + col);
+                f[0] += r4.x; f[1] += r4.y; f[2] += r4.z; f[3] += r4.w;
+              }
+              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+            }
           }
         }
       }
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
   static bool configured = false;
@@ -218,8 +281,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
-  dim3 grid(static_cast<unsigned>((p.M + BM - 1) / BM), static_cast<unsigned>((p.N + BN - 1) / BN), splits);
-  kern<<<grid, 192, Cfg::SMEM, st>>>(ta, tb, p);
+  p.n_tiles = static_cast<int>((p.N + BN - 1) / BN);
+  p.total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -235,7 +300,8 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
               (long long)K);
   B2C_REQUIRE(N % 8 == 0, "b2c_gemm_bf16: N=%lld must be a multiple of 8", (long long)N);
   B2C_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "b2c_gemm_bf16: leading dims must be multiples of 8 elements (16 B)");
-  B2C_REQUIRE(ep->ld_out % 4 == 0, "b2c_gemm_bf16: ld_out must be a multiple of 4");
+  B2C_REQUIRE(ep->ld_out % 4 == 0 && ep->ld_out2 % 4 == 0 && ep->ld_aux % 4 == 0,
+              "b2c_gemm_bf16: output / aux pitches must be multiples of 4 elements");
   B2C_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(ep->out) & 15) == 0,
               "b2c_gemm_bf16: pointers must be 16-byte aligned");
@@ -250,8 +316,10 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   B2C_REQUIRE(splits == 1 || ep->accumulate, "b2c_gemm_bf16: split_k > 1 needs accumulate=1 (fp32 atomics)");
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
+  p.total_kb = total_kb;
   p.kblocks_per_split = (total_kb + splits - 1) / splits;
-  splits = (total_kb + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  p.splits = (total_kb + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  p.m_tiles = static_cast<int>((M + BM - 1) / BM);
   p.ep = *ep;
   CUtensorMap ta, tb;
   int rc;
@@ -262,12 +330,12 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   else       rc = get_tensor_map_2d(&tb, B, 2, N, K, ldb * 2, 64, BK, true);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define B2C_DISPATCH(BN_)                                                                 \
-  if (bn == BN_) {                                                                        \
-    if (!a_mn && !b_mn) return launch_gemm<BN_, false, false>(ta, tb, p, splits, st);     \
-    if (!a_mn && b_mn) return launch_gemm<BN_, false, true>(ta, tb, p, splits, st);       \
-    if (a_mn && b_mn) return launch_gemm<BN_, true, true>(ta, tb, p, splits, st);         \
-    return launch_gemm<BN_, true, false>(ta, tb, p, splits, st);                          \
+#define B2C_DISPATCH(BN_)                                                         \
+  if (bn == BN_) {                                                                \
+    if (!a_mn && !b_mn) return launch_gemm<BN_, false, false>(ta, tb, p, st);     \
+    if (!a_mn && b_mn) return launch_gemm<BN_, false, true>(ta, tb, p, st);       \
+    if (a_mn && b_mn) return launch_gemm<BN_, true, true>(ta, tb, p, st);         \
+    return launch_gemm<BN_, true, false>(ta, tb, p, st);                          \
   }
   B2C_DISPATCH(64)
   B2C_DISPATCH(128)
