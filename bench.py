@@ -228,7 +228,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="utterances per GPU")
     ap.add_argument("--seconds", type=float, default=15.0)
     ap.add_argument("--ref-batch", type=int, default=2, help="utterances per step of the CPU reference arm")
-    ap.add_argument("--optimizer", default="hf", choices=["fused", "hf"])
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "hf"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-instrument", action="store_true")
     args = ap.parse_args()

@@ -161,6 +161,18 @@ void b2c_mt19937_seed_host(uint32_t* state_host, uint64_t seed);
 int64_t b2c_mt19937_randint_host(uint32_t* state_host, int64_t a, int64_t b);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Fused multi-tensor Adafactor step -- transformers.Adafactor(lr, beta1, scale_parameter=False, relative_step=False)
+ * as the reference constructs it (/root/reference/lib/standard/runner.py:36,146).  Four launches for the whole
+ * parameter set.  tensors_dev: device array of 96-byte records
+ *   { float* p; const float* g; float* exp_avg; float* row_or_sq; float* col; float* rowsum_ws; float* colsum_ws;
+ *     float* rmean_ws; float* sumsq_ws; int32 P, R, C, factored; int64 n }      (tensor viewed as [P][R][C])
+ * chunks_dev: device array of { int32 tensor, row0, nrows, pad } covering every flattened row once.  The workspace
+ * fields must be zero on entry.  step >= 1 is the update count (beta2_t = 1 - step^decay_rate).
+ * ------------------------------------------------------------------------------------------------------- */
+int b2c_adafactor_step(const void* tensors_dev, int n_tensors, const void* chunks_dev, int n_chunks, int64_t step,
+                       float lr, float beta1, float eps1, float clip, float decay_rate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Small memory-bound helpers
  * ------------------------------------------------------------------------------------------------------- */
 /* multi-tensor fp32 -> bf16 cast; optional zero padding of rows/cols (pads attention heads to 64):

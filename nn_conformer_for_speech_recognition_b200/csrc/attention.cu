@@ -43,9 +43,8 @@ struct AttnParams {
   int B, T, H;
   int q_col, k_col, v_col;     // column offsets (elements) of head 0 inside a qkv row
   float scale_log2;            // scale * log2(e)
-  uint32_t drop_thresh;
-  float inv_keep;
-  uint64_t drop_seed;
+  int Tpad;                    // even row pitch of the dropout index space
+  DropCfg drop;
 };
 
 __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
@@ -93,7 +92,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   for (int i = 0; i < AT_DH; ++i) o[i] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
   const int q_idx = q0 + tid;                           // query position inside the utterance
-  const uint64_t drop_row = (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.T;
+  const uint64_t drop_row = (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad;
 
   for (int j = 0; j < nkb; ++j) {
     const uint32_t ph = j & 1;
@@ -142,10 +141,13 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
         l_blk += e;
         pr[i] = e;
       }
-      if (p.drop_thresh) {
+      if (p.drop.thresh16) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          pr[i] *= drop_scale(p.drop_seed, drop_row + key0 + c + i, p.drop_thresh, p.inv_keep);
+        for (int i = 0; i < 32; i += 2) {
+          float s0, s1;
+          drop_scale2(p.drop, drop_row + key0 + c + i, s0, s1);
+          pr[i] *= s0; pr[i + 1] *= s1;
+        }
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -220,9 +222,8 @@ struct AttnBwdParams {
   int B, T, H;
   int q_col, k_col, v_col;
   float scale, scale_log2;
-  uint32_t drop_thresh;
-  float inv_keep;
-  uint64_t drop_seed;
+  int Tpad;
+  DropCfg drop;
 };
 
 // delta[b,h,t] = sum_c dO[row, h*64+c] * O[row, h*64+c]
@@ -267,13 +268,16 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
     tmem_wait_ld();
     float pr[32], ds[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const bool ok = q_ok && (key0 + c + i < len);
-      const float pv = ok ? exp2f(__uint_as_float(vs[i]) * p.scale_log2 - lse_r) : 0.f;
-      float dsc = 1.f;
-      if (p.drop_thresh) dsc = drop_scale(p.drop_seed, drop_row + key0 + c + i, p.drop_thresh, p.inv_keep);
-      pr[i] = pv * dsc;
-      ds[i] = pv * (__uint_as_float(vd[i]) * dsc - delta_r) * p.scale;
+    for (int i = 0; i < 32; i += 2) {
+      float dsc[2] = {1.f, 1.f};
+      if (p.drop.thresh16) drop_scale2(p.drop, drop_row + key0 + c + i, dsc[0], dsc[1]);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = q_ok && (key0 + c + i + e < len);
+        const float pv = ok ? exp2f(__uint_as_float(vs[i + e]) * p.scale_log2 - lse_r) : 0.f;
+        pr[i + e] = pv * dsc[e];
+        ds[i + e] = pv * (__uint_as_float(vd[i + e]) * dsc[e] - delta_r) * p.scale;
+      }
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dkv_kernel(const __grid_const
     mbar_wait(bar_s, ph);
     tc_fence_after();
     attn_bwd_tile_math(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P, smem + OFF_DS, tid, q_idx, key0, len, lse_r,
-                       delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.T);
+                       delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dq_kernel(const __grid_consta
     mbar_wait(bar_s, ph);
     tc_fence_after();
     attn_bwd_tile_math(p, tm_lane + TM_S, tm_lane + TM_DP, nullptr, smem + OFF_DS, tid, q_idx, key0, len, lse_r,
-                       delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.T);
+                       delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -541,9 +545,8 @@ extern "C" int b2c_attention_fwd(const void* qkv, int64_t ld, int64_t k_off, int
   p.B = B; p.T = T; p.H = H;
   p.q_col = 0; p.k_col = static_cast<int>(k_off); p.v_col = static_cast<int>(v_off);
   p.scale_log2 = scale * LOG2E;
-  p.drop_thresh = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
-  p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  p.drop_seed = drop_seed;
+  p.Tpad = (T + 1) & ~1;
+  p.drop = make_drop(drop_p, drop_seed);
   dim3 grid((T + AT_BQ - 1) / AT_BQ, H, B);
   attn_fwd_kernel<<<grid, 128, ATTN_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
   B2C_CUDA(cudaGetLastError());
@@ -576,9 +579,8 @@ extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int
   p.B = B; p.T = T; p.H = H;
   p.q_col = 0; p.k_col = static_cast<int>(k_off); p.v_col = static_cast<int>(v_off);
   p.scale = scale; p.scale_log2 = scale * LOG2E;
-  p.drop_thresh = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
-  p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  p.drop_seed = drop_seed;
+  p.Tpad = (T + 1) & ~1;
+  p.drop = make_drop(drop_p, drop_seed);
   dim3 grid((T + AT_BQ - 1) / AT_BQ, H, B);
   attn_bwd_dkv_kernel<<<grid, 128, ATTN_DKV_SMEM, st>>>(tq, td, p);
   attn_bwd_dq_kernel<<<grid, 128, ATTN_DQ_SMEM, st>>>(tq, td, p);

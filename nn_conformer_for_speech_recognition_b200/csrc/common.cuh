@@ -56,18 +56,43 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Counter-based dropout: keep-decision for element `idx` of the tensor tagged by `seed`.
-// splitmix64 finaliser; forward and backward regenerate identical masks from (seed, idx).
-__host__ __device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
+// Counter-based dropout.  One 32-bit hash serves the element PAIR (idx, idx+1), idx even: 16 bits per decision,
+// keep when the 16-bit lane >= thresh16 = round(p * 65536).  Forward and backward regenerate identical masks from
+// (seed, idx); index spaces are laid out with even row pitches so pairs never straddle rows.
+// Mixing: per-tensor affine map of the pair index (odd multiplier and offset derived from the seed) followed by the
+// "lowbias32" avalanche (2 multiplies, 3 xor-shifts) -- ~4 integer ops per element instead of a 64-bit splitmix.
+__host__ __device__ __forceinline__ uint32_t drop_hash32(uint64_t seed, uint64_t pair_idx) {
+  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  uint32_t x = static_cast<uint32_t>(pair_idx) * (k1 | 1u) + k0 + static_cast<uint32_t>(pair_idx >> 32) * 0x85EBCA6Bu;
+  x ^= x >> 16; x *= 0x21F0AAADu;
+  x ^= x >> 15; x *= 0x735A2D97u;
+  x ^= x >> 15;
+  return x;
+}
+struct DropCfg {
+  uint64_t seed;       // well-mixed 64-bit key (host side runs the user seed through splitmix64)
+  uint32_t thresh16;   // 0 = dropout off
+  float inv_keep;
+};
+__host__ __device__ __forceinline__ uint64_t drop_mix_seed(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return static_cast<uint32_t>(z >> 32);
+  return z ^ (z >> 31);
 }
-// threshold = p * 2^32 ; keep when hash >= threshold
-__host__ __device__ __forceinline__ float drop_scale(uint64_t seed, uint64_t idx, uint32_t thresh, float inv_keep) {
-  return drop_hash(seed, idx) >= thresh ? inv_keep : 0.f;
+inline DropCfg make_drop(float p, uint64_t seed) {
+  DropCfg d;
+  d.seed = drop_mix_seed(seed);
+  d.thresh16 = p > 0.f ? static_cast<uint32_t>(p * 65536.0 + 0.5) : 0u;
+  if (d.thresh16 > 65535u) d.thresh16 = 65535u;
+  d.inv_keep = p > 0.f ? 65536.f / static_cast<float>(65536u - d.thresh16) : 1.f;
+  return d;
+}
+// scales for elements idx (even) and idx+1
+__device__ __forceinline__ void drop_scale2(const DropCfg& d, uint64_t idx_even, float& s0, float& s1) {
+  const uint32_t h = drop_hash32(d.seed, idx_even >> 1);
+  s0 = (h & 0xFFFFu) >= d.thresh16 ? d.inv_keep : 0.f;
+  s1 = (h >> 16) >= d.thresh16 ? d.inv_keep : 0.f;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

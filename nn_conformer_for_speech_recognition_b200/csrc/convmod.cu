@@ -266,52 +266,72 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
       sDY[r * 32 + lane] = dyv;
     }
   }
-  float w0[CM_MAXK], w1[CM_MAXK];                     // REVERSED taps: wr[j'] = w[k-1-j']
-#pragma unroll
-  for (int j = 0; j < CM_MAXK; ++j) {
-    w0[j] = (j < k && ch_ok) ? __ldg(wdw + static_cast<int64_t>(ch) * k + (k - 1 - j)) : 0.f;
-    w1[j] = (j < k && ch_ok) ? __ldg(wdw + static_cast<int64_t>(ch + 1) * k + (k - 1 - j)) : 0.f;
-  }
   __syncthreads();
 
-  float acc0[CM_MAXK], acc1[CM_MAXK];                 // dw partials of this lane's two channels
+  // ---- phase 1: dg = correlate(dy, reversed taps) for this warp's 16 frames, then du through the GLU ----
+  {
+    float w0[CM_MAXK], w1[CM_MAXK];                   // REVERSED taps: wr[j'] = w[k-1-j']
+#pragma unroll
+    for (int j = 0; j < CM_MAXK; ++j) {
+      w0[j] = (j < k && ch_ok) ? __ldg(wdw + static_cast<int64_t>(ch) * k + (k - 1 - j)) : 0.f;
+      w1[j] = (j < k && ch_ok) ? __ldg(wdw + static_cast<int64_t>(ch + 1) * k + (k - 1 - j)) : 0.f;
+    }
+#pragma unroll 1
+    for (int grp = 0; grp < (CM_TT / 8) / CM_G; ++grp) {
+      const int tl = warp * (CM_TT / 8) + grp * CM_G;
+      float a0[CM_G], a1[CM_G];
+#pragma unroll
+      for (int i = 0; i < CM_G; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
+#pragma unroll
+      for (int r = 0; r < CM_G + CM_MAXK - 1; ++r) {
+        if (r < CM_G + k - 1) {
+          const float2 dyr = sDY[(tl + r) * 32 + lane];
+#pragma unroll
+          for (int i = 0; i < CM_G; ++i) {
+            const int j = r - i;
+            if (j >= 0 && j < CM_MAXK) { a0[i] = fmaf(dyr.x, w0[j], a0[i]); a1[i] = fmaf(dyr.y, w1[j], a1[i]); }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < CM_G; ++i) {
+        const int t = t0 + tl + i;
+        if (t < T && ch_ok) {
+          const int64_t row = static_cast<int64_t>(b) * T + t;
+          const float2 av = unpack_bf16(*reinterpret_cast<const uint32_t*>(u + row * 2 * d + ch));
+          const float2 bv = unpack_bf16(*reinterpret_cast<const uint32_t*>(u + row * 2 * d + d + ch));
+          const float s0 = sigmoid_f(bv.x), s1 = sigmoid_f(bv.y);
+          *reinterpret_cast<uint32_t*>(du + row * 2 * d + ch) = pack_bf16(a0[i] * s0, a1[i] * s1);
+          *reinterpret_cast<uint32_t*>(du + row * 2 * d + d + ch) =
+              pack_bf16(a0[i] * av.x * s0 * (1.f - s0), a1[i] * av.y * s1 * (1.f - s1));
+        }
+      }
+    }
+  }
+
+  // ---- phase 2: dw[j] += dy[t] * g[t + j - h] over this warp's frames (taps are dead: registers are reused) ----
+  float acc0[CM_MAXK], acc1[CM_MAXK];
 #pragma unroll
   for (int j = 0; j < CM_MAXK; ++j) acc0[j] = acc1[j] = 0.f;
   float dbs0 = 0.f, dbs1 = 0.f;
 #pragma unroll 1
   for (int grp = 0; grp < (CM_TT / 8) / CM_G; ++grp) {
     const int tl = warp * (CM_TT / 8) + grp * CM_G;
-    float a0[CM_G], a1[CM_G];                         // dg for 8 frames
     float2 dyc[CM_G];                                 // dy at the 8 centre frames
 #pragma unroll
-    for (int i = 0; i < CM_G; ++i) { a0[i] = 0.f; a1[i] = 0.f; dyc[i] = sDY[(tl + half + i) * 32 + lane]; }
+    for (int i = 0; i < CM_G; ++i) {
+      dyc[i] = sDY[(tl + half + i) * 32 + lane];
+      dbs0 += dyc[i].x; dbs1 += dyc[i].y;
+    }
 #pragma unroll
     for (int r = 0; r < CM_G + CM_MAXK - 1; ++r) {
       if (r < CM_G + k - 1) {
-        const float2 dyr = sDY[(tl + r) * 32 + lane];
         const float2 gr = sG[(tl + r) * 32 + lane];
 #pragma unroll
         for (int i = 0; i < CM_G; ++i) {
           const int j = r - i;
-          if (j >= 0 && j < CM_MAXK) {
-            a0[i] = fmaf(dyr.x, w0[j], a0[i]); a1[i] = fmaf(dyr.y, w1[j], a1[i]);       // dg
-            acc0[j] = fmaf(dyc[i].x, gr.x, acc0[j]); acc1[j] = fmaf(dyc[i].y, gr.y, acc1[j]);   // dw[j] += dy[t]*g[t+j-h]
-          }
+          if (j >= 0 && j < CM_MAXK) { acc0[j] = fmaf(dyc[i].x, gr.x, acc0[j]); acc1[j] = fmaf(dyc[i].y, gr.y, acc1[j]); }
         }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < CM_G; ++i) {
-      dbs0 += dyc[i].x; dbs1 += dyc[i].y;
-      const int t = t0 + tl + i;
-      if (t < T && ch_ok) {
-        const int64_t row = static_cast<int64_t>(b) * T + t;
-        const float2 av = unpack_bf16(*reinterpret_cast<const uint32_t*>(u + row * 2 * d + ch));
-        const float2 bv = unpack_bf16(*reinterpret_cast<const uint32_t*>(u + row * 2 * d + d + ch));
-        const float s0 = sigmoid_f(bv.x), s1 = sigmoid_f(bv.y);
-        *reinterpret_cast<uint32_t*>(du + row * 2 * d + ch) = pack_bf16(a0[i] * s0, a1[i] * s1);
-        *reinterpret_cast<uint32_t*>(du + row * 2 * d + d + ch) =
-            pack_bf16(a0[i] * av.x * s0 * (1.f - s0), a1[i] * av.y * s1 * (1.f - s1));
       }
     }
   }

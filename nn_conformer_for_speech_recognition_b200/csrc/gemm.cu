@@ -35,6 +35,7 @@ constexpr int GEMM_THREADS = 320;
 constexpr int EPI_WARPS = 8;
 
 struct GemmParams {
+  DropCfg drop;
   int64_t M, N, K;
   int kblocks_per_split, total_kb;
   int m_tiles, n_tiles, splits, total_tiles;
@@ -175,8 +176,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     const int half = ew >> 2;                          // which half of the BN columns
     float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF + ew * Cfg::STG_WARP_BYTES);
-    const uint32_t drop_thresh = ep.drop_p > 0.f ? static_cast<uint32_t>(ep.drop_p * 4294967296.0) : 0u;
-    const float inv_keep = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
     const int c_lane = lane % LPR;                     // float4 chunk (column group) this lane owns after the transpose
     const int r_lane = lane / LPR;
     uint32_t it = 0;
@@ -235,10 +234,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
               f[j] *= sg * fmaf(u[j], 1.f - sg, 1.f);
             }
           }
-          if (drop_thresh) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              f[j] *= drop_scale(ep.drop_seed, static_cast<uint64_t>(row) * p.N + col + j, drop_thresh, inv_keep);
+          if (p.drop.thresh16) {
+            float s0, s1, s2, s3;
+            const uint64_t di = static_cast<uint64_t>(row) * p.N + col;      // N % 8 == 0, col % 4 == 0: even
+            drop_scale2(p.drop, di, s0, s1);
+            drop_scale2(p.drop, di + 2, s2, s3);
+            f[0] *= s0; f[1] *= s1; f[2] *= s2; f[3] *= s3;
           }
           if (ep.alpha != 1.f) {
 #pragma unroll
@@ -321,6 +322,7 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   p.splits = (total_kb + p.kblocks_per_split - 1) / p.kblocks_per_split;
   p.m_tiles = static_cast<int>((M + BM - 1) / BM);
   p.ep = *ep;
+  p.drop = make_drop(ep->drop_p, ep->drop_seed);
   CUtensorMap ta, tb;
   int rc;
   if (!a_mn) rc = get_tensor_map_2d(&ta, A, 2, K, M, lda * 2, BK, BM, true);

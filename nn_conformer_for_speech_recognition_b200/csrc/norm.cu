@@ -10,10 +10,10 @@
 
 namespace b2c {
 
-constexpr int LN_MAXV = 8;        // float4 chunks per lane -> d <= 1024
+constexpr int LN_MAX_CHUNKS = 8;  // float4 chunks per lane -> d <= 1024 (kernels are instantiated for 2, 4, 8)
 constexpr int LN_WARPS = 8;
 
-template <bool OUT_BF16>
+template <bool OUT_BF16, int LN_MAXV>
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const float* __restrict__ x,
                                                                       const float* __restrict__ gamma,
                                                                       const float* __restrict__ beta, void* __restrict__ y,
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const floa
 }
 
 // dx = rstd * (g - mean_d(g) - xhat * mean_d(g*xhat)),  g = dy*gamma ; dgamma += dy*xhat ; dbeta += dy
-template <bool DY_BF16>
+template <bool DY_BF16, int LN_MAXV>
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const void* __restrict__ dy,
                                                                       const float* __restrict__ x,
                                                                       const float* __restrict__ gamma,
@@ -191,14 +191,16 @@ __global__ void multi_cast_kernel(const CastEntry* __restrict__ table) {
 }
 
 __global__ void scale_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n,
-                                  float alpha, uint32_t thresh, float inv_keep, uint64_t seed) {
+                                  float alpha, DropCfg drop) {
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;                       // n % 4 == 0 enforced by the host
   float4 a = *reinterpret_cast<const float4*>(src + i);
   float f[4] = {a.x * alpha, a.y * alpha, a.z * alpha, a.w * alpha};
-  if (thresh) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) f[j] *= drop_scale(seed, static_cast<uint64_t>(i + j), thresh, inv_keep);
+  if (drop.thresh16) {
+    float s0, s1, s2, s3;
+    drop_scale2(drop, static_cast<uint64_t>(i), s0, s1);
+    drop_scale2(drop, static_cast<uint64_t>(i) + 2, s2, s3);
+    f[0] *= s0; f[1] *= s1; f[2] *= s2; f[3] *= s3;
   }
   *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
 }
@@ -245,14 +247,15 @@ using namespace b2c;
 extern "C" int b2c_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
                                  float* mean, float* rstd, int64_t rows, int d, float eps, void* stream) {
   B2C_REQUIRE(x && gamma && beta && y, "b2c_layernorm_fwd: null pointer");
-  B2C_REQUIRE(d % 4 == 0 && d > 0 && d <= 128 * LN_MAXV, "b2c_layernorm_fwd: d=%d must be a multiple of 4, <= 1024", d);
+  B2C_REQUIRE(d % 4 == 0 && d > 0 && d <= 128 * LN_MAX_CHUNKS, "b2c_layernorm_fwd: d=%d must be a multiple of 4, <= 1024", d);
   if (rows <= 0) return 0;
   const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (y_dtype == B2C_BF16)
-    layernorm_fwd_kernel<true><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
-  else
-    layernorm_fwd_kernel<false><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
+#define B2C_LN_FWD(BF, NV) layernorm_fwd_kernel<BF, NV><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps)
+  const int nv = (d / 4 + 31) / 32;
+  if (y_dtype == B2C_BF16) { if (nv <= 2) B2C_LN_FWD(true, 2); else if (nv <= 4) B2C_LN_FWD(true, 4); else B2C_LN_FWD(true, 8); }
+  else                     { if (nv <= 2) B2C_LN_FWD(false, 2); else if (nv <= 4) B2C_LN_FWD(false, 4); else B2C_LN_FWD(false, 8); }
+#undef B2C_LN_FWD
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -261,22 +264,23 @@ extern "C" int b2c_layernorm_bwd(const void* dy, int dy_dtype, const float* x, c
                                  const float* rstd, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
                                  int64_t rows, int d, void* stream) {
   B2C_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "b2c_layernorm_bwd: null pointer");
-  B2C_REQUIRE(d % 4 == 0 && d > 0 && d <= 128 * LN_MAXV, "b2c_layernorm_bwd: d=%d must be a multiple of 4, <= 1024", d);
+  B2C_REQUIRE(d % 4 == 0 && d > 0 && d <= 128 * LN_MAX_CHUNKS, "b2c_layernorm_bwd: d=%d must be a multiple of 4, <= 1024", d);
   if (rows <= 0) return 0;
   // ~4 blocks per SM; each warp walks a contiguous run of rows so parameter-gradient atomics stay rare
-  const int64_t target_warps = static_cast<int64_t>(num_sms()) * 4 * LN_WARPS;
+  const int64_t target_warps = static_cast<int64_t>(num_sms()) * 8 * LN_WARPS;
   int rows_per_warp = static_cast<int>((rows + target_warps - 1) / target_warps);
   if (rows_per_warp < 1) rows_per_warp = 1;
   const int64_t warps = (rows + rows_per_warp - 1) / rows_per_warp;
   const unsigned grid = static_cast<unsigned>((warps + LN_WARPS - 1) / LN_WARPS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = 2 * d * sizeof(float);
-  if (dy_dtype == B2C_BF16)
-    layernorm_bwd_kernel<true><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma,
-                                                                dbeta, rows, d, rows_per_warp);
-  else
-    layernorm_bwd_kernel<false><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma,
-                                                                 dbeta, rows, d, rows_per_warp);
+#define B2C_LN_BWD(BF, NV)                                                                                      \
+  layernorm_bwd_kernel<BF, NV><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma, \
+                                                                  dbeta, rows, d, rows_per_warp)
+  const int nv = (d / 4 + 31) / 32;
+  if (dy_dtype == B2C_BF16) { if (nv <= 2) B2C_LN_BWD(true, 2); else if (nv <= 4) B2C_LN_BWD(true, 4); else B2C_LN_BWD(true, 8); }
+  else                      { if (nv <= 2) B2C_LN_BWD(false, 2); else if (nv <= 4) B2C_LN_BWD(false, 4); else B2C_LN_BWD(false, 8); }
+#undef B2C_LN_BWD
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -310,11 +314,9 @@ extern "C" int b2c_scale_cast(const float* src, void* dst, int64_t rows, int64_t
   const int64_t n = rows * cols;
   if (n <= 0) return 0;
   B2C_REQUIRE(n % 4 == 0, "b2c_scale_cast: element count must be a multiple of 4");
-  const uint32_t thresh = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
-  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int64_t threads = n / 4;
   scale_cast_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(dst), n, alpha, thresh, inv_keep, drop_seed);
+      src, static_cast<__nv_bfloat16*>(dst), n, alpha, make_drop(drop_p, drop_seed));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,188 @@
+// Fused multi-tensor Adafactor step (the optimizer of the reference's training loop:
+// transformers.Adafactor(lr=2e-5, beta1=0.9, scale_parameter=False, relative_step=False), /root/reference/lib/standard/runner.py:36,146).
+//
+// HF's implementation walks the parameters in Python and launches ~15 small kernels per tensor (~7000 launches per
+// step for Conformer-M).  Here the whole parameter set is updated by FOUR launches driven by device-side tables:
+//   1. adafactor_stats   : row / column sums of (g^2 + eps1) for factored (>= 2-D) tensors
+//   2. adafactor_factors : exp_avg_sq_row/col <- beta2t * . + (1-beta2t) * mean ; per-slab mean of the row factor
+//   3. adafactor_update  : u = g * rsqrt(row/mean(row)) * rsqrt(col)   (1-D: v <- beta2t v + (1-beta2t)(g^2+eps1), u = g rsqrt(v))
+//                          and sum(u^2) per tensor (for the RMS clip)
+//   4. adafactor_apply   : u /= max(1, rms(u)/clip); m <- beta1 m + (1-beta1) lr u; p -= m
+// Every tensor is viewed as [P slabs][R rows][C cols] (P = prod(shape[:-2]), 1-D tensors as [1][1][n]); HF's
+// exp_avg_sq_row has shape [P,R] (mean over the last dim), exp_avg_sq_col [P,C] (mean over dim -2).
+// Memory-bound: g is read 3x, m and p read+written once (28 B per parameter).
+#include "common.cuh"
+#include "b200conformer.h"
+
+namespace b2c {
+
+struct AfTensor {            // one per parameter (device table, 96 bytes)
+  float* p;                  // parameter
+  const float* g;            // gradient
+  float* m;                  // exp_avg
+  float* row;                // exp_avg_sq_row [P*R]  (factored)  | exp_avg_sq [n] (1-D)
+  float* col;                // exp_avg_sq_col [P*C]  (factored)
+  float* rowsum;             // workspace [P*R]
+  float* colsum;             // workspace [P*C]
+  float* rmean;              // workspace [P]   mean over R of the updated row factor
+  float* sumsq;              // workspace [1]   sum(u^2)
+  int32_t P, R, C, factored;
+  int64_t n;
+};
+struct AfChunk {             // a run of `nrows` flattened rows (row index in [0, P*R)) of tensor `t`
+  int32_t t, row0, nrows, pad;
+};
+
+constexpr int AF_THREADS = 256;
+
+__global__ void __launch_bounds__(AF_THREADS) adafactor_stats_kernel(const AfTensor* __restrict__ tensors,
+                                                                    const AfChunk* __restrict__ chunks, float eps1) {
+  const AfChunk ck = chunks[blockIdx.x];
+  const AfTensor T = tensors[ck.t];
+  if (!T.factored) return;
+  const int C = T.C, R = T.R;
+  if (C >= 32) {
+    // wide rows: warp w takes rows w, w+8, ...; lanes stride the columns.  Row sums by warp shuffle; column sums are
+    // kept per (warp, column) in registers only for C <= 32*8*... -> simpler: per-element atomics on the column sums
+    // are avoided by letting each THREAD own columns c = tid, tid+256, ... across all rows of the chunk.
+    const int tid = threadIdx.x;
+    for (int c = tid; c < C; c += AF_THREADS) {
+      float acc = 0.f;
+      int cur_p = -1;
+      for (int r = 0; r < ck.nrows; ++r) {
+        const int row = ck.row0 + r;
+        const int pslab = row / R;
+        if (pslab != cur_p) {
+          if (cur_p >= 0) atomicAdd(T.colsum + static_cast<int64_t>(cur_p) * C + c, acc);
+          acc = 0.f;
+          cur_p = pslab;
+        }
+        const float gv = T.g[static_cast<int64_t>(row) * C + c];
+        acc += gv * gv + eps1;
+      }
+      if (cur_p >= 0) atomicAdd(T.colsum + static_cast<int64_t>(cur_p) * C + c, acc);
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < ck.nrows; r += AF_THREADS / 32) {
+      const int row = ck.row0 + r;
+      float acc = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float gv = T.g[static_cast<int64_t>(row) * C + c];
+        acc += gv * gv + eps1;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) T.rowsum[row] = acc;           // a row belongs to exactly one chunk: plain store
+    }
+  } else {
+    // narrow rows (conv kernels, C = 3..31): one thread per row
+    for (int r = threadIdx.x; r < ck.nrows; r += AF_THREADS) {
+      const int row = ck.row0 + r;
+      const int pslab = row / R;
+      float acc = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float gv = T.g[static_cast<int64_t>(row) * C + c];
+        const float s = gv * gv + eps1;
+        acc += s;
+        atomicAdd(T.colsum + static_cast<int64_t>(pslab) * C + c, s);
+      }
+      T.rowsum[row] = acc;
+    }
+  }
+}
+
+// one block per (tensor, slab-range): updates the factored second moments and the per-slab mean of the row factor
+__global__ void __launch_bounds__(AF_THREADS) adafactor_factors_kernel(const AfTensor* __restrict__ tensors, int n_tensors,
+                                                                      float beta2t) {
+  const AfTensor T = tensors[blockIdx.x];
+  if (!T.factored) return;
+  const int C = T.C, R = T.R, P = T.P;
+  const float om = 1.f - beta2t;
+  for (int64_t i = threadIdx.x; i < static_cast<int64_t>(P) * C; i += AF_THREADS)
+    T.col[i] = beta2t * T.col[i] + om * (T.colsum[i] / R);
+  for (int64_t i = threadIdx.x; i < static_cast<int64_t>(P) * R; i += AF_THREADS)
+    T.row[i] = beta2t * T.row[i] + om * (T.rowsum[i] / C);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pslab = warp; pslab < P; pslab += AF_THREADS / 32) {
+    float acc = 0.f;
+    for (int r = lane; r < R; r += 32) acc += T.row[static_cast<int64_t>(pslab) * R + r];
+    acc = warp_sum(acc);
+    if (lane == 0) T.rmean[pslab] = acc / R;
+  }
+}
+
+template <bool APPLY>
+__global__ void __launch_bounds__(AF_THREADS) adafactor_update_kernel(const AfTensor* __restrict__ tensors,
+                                                                     const AfChunk* __restrict__ chunks, float beta2t,
+                                                                     float eps1, float lr, float beta1, float clip) {
+  const AfChunk ck = chunks[blockIdx.x];
+  const AfTensor T = tensors[ck.t];
+  const int C = T.C, R = T.R;
+  const int64_t e0 = static_cast<int64_t>(ck.row0) * C;
+  const int64_t cnt = static_cast<int64_t>(ck.nrows) * C;
+  float scale = 0.f;
+  if (APPLY) {
+    const float rms = sqrtf(*T.sumsq / static_cast<float>(T.n));
+    scale = lr / fmaxf(1.f, rms / clip);
+  }
+  float ss = 0.f;
+  for (int64_t i = threadIdx.x; i < cnt; i += AF_THREADS) {
+    const int64_t e = e0 + i;
+    const float gv = T.g[e];
+    float u;
+    if (T.factored) {
+      const int row = ck.row0 + static_cast<int>(i / C);
+      const int c = static_cast<int>(i % C);
+      const int pslab = row / R;
+      u = gv * rsqrtf(T.row[row] / T.rmean[pslab]) * rsqrtf(T.col[static_cast<int64_t>(pslab) * C + c]);
+    } else {
+      float v = T.row[e];
+      if (!APPLY) {                                  // second moment is updated once, in the first pass
+        v = beta2t * v + (1.f - beta2t) * (gv * gv + eps1);
+        T.row[e] = v;
+      }
+      u = gv * rsqrtf(v);
+    }
+    if (APPLY) {
+      const float mv = beta1 * T.m[e] + (1.f - beta1) * (scale * u);
+      T.m[e] = mv;
+      T.p[e] -= mv;
+    } else {
+      ss += u * u;
+    }
+  }
+  if (!APPLY) {
+    __shared__ float red[AF_THREADS / 32];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < AF_THREADS / 32; ++w) t += red[w];
+      atomicAdd(T.sumsq, t);
+    }
+  }
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_adafactor_step(const void* tensors_dev, int n_tensors, const void* chunks_dev, int n_chunks,
+                                  int64_t step, float lr, float beta1, float eps1, float clip, float decay_rate,
+                                  void* stream) {
+  B2C_REQUIRE(tensors_dev && chunks_dev && n_tensors > 0 && n_chunks > 0 && step >= 1, "b2c_adafactor_step: bad argument");
+  static_assert(sizeof(AfTensor) == 96, "AfTensor layout is part of the ABI (python builds the table)");
+  static_assert(sizeof(AfChunk) == 16, "AfChunk layout is part of the ABI");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float beta2t = 1.f - powf(static_cast<float>(step), decay_rate);        // HF: 1 - step^decay_rate
+  const AfTensor* T = static_cast<const AfTensor*>(tensors_dev);
+  const AfChunk* Cc = static_cast<const AfChunk*>(chunks_dev);
+  adafactor_stats_kernel<<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, eps1);
+  adafactor_factors_kernel<<<n_tensors, AF_THREADS, 0, st>>>(T, n_tensors, beta2t);
+  adafactor_update_kernel<false><<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, beta2t, eps1, lr, beta1, clip);
+  adafactor_update_kernel<true><<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, beta2t, eps1, lr, beta1, clip);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}

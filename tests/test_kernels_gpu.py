@@ -270,3 +270,36 @@ def test_cast_colsum_repack(ops):
     assert torch.equal(dst, want.view(10, 768))
     back = ops.repack_heads(dst, 12, 64, 36)
     assert torch.equal(back, src)
+
+
+# ----------------------------------------------------------------------------------------------- fused Adafactor
+def test_fused_adafactor_matches_hf():
+    """Same update as transformers.Adafactor with the reference's arguments (runner.py:36), over several steps."""
+    from transformers.optimization import Adafactor as HFAdafactor
+    from nn_conformer_for_speech_recognition_b200.optim import Adafactor
+    torch.manual_seed(0)
+    shapes = [(256,), (1024, 256), (256, 1024), (512, 256, 1), (256, 1, 31), (512, 1, 7, 7), (128, 64, 3, 3), (144,),
+              (256, 2304), (3, 5)]
+    ours = [torch.nn.Parameter(torch.randn(s, device="cuda") * 0.1) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    o1 = Adafactor(ours, lr=2e-5, beta1=0.9)
+    o2 = HFAdafactor(ref, lr=2e-5, beta1=0.9, scale_parameter=False, relative_step=False)
+    for step in range(4):
+        for a, b_ in zip(ours, ref):
+            g = torch.randn_like(a) * (10.0 if step == 1 else 0.01)       # step 1 trips the RMS clip
+            a.grad, b_.grad = g.clone(), g.clone()
+        o1.step()
+        o2.step()
+        for i, (a, b_) in enumerate(zip(ours, ref)):
+            upd_ref = (b_.detach() - (a.detach() * 0 + b_.detach())).abs().max()     # placeholder to keep shapes in scope
+            del upd_ref
+            err = (a.detach() - b_.detach()).abs().max().item()
+            assert err <= 2e-7 + 1e-3 * 2e-5, f"step {step} tensor {shapes[i]}: |dp| {err:.3e}"
+    for i, b_ in enumerate(ref):
+        st = o2.state[b_]
+        _close(o1.views[i]["exp_avg"], st["exp_avg"], rel=1e-3, abs_=1e-9, name="exp_avg")
+        if b_.dim() >= 2:
+            _close(o1.views[i]["row"].view(st["exp_avg_sq_row"].shape), st["exp_avg_sq_row"], rel=1e-3, abs_=1e-12, name="row")
+            _close(o1.views[i]["col"].view(st["exp_avg_sq_col"].shape), st["exp_avg_sq_col"], rel=1e-3, abs_=1e-12, name="col")
+        else:
+            _close(o1.views[i]["row"], st["exp_avg_sq"], rel=1e-3, abs_=1e-12, name="sq")
