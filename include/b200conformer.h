@@ -116,10 +116,11 @@ int b2c_attention_fwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off,
                       void* stream);
 
 /* backward: dqkv bf16 [B*T, ld] laid out like qkv (every row < B*T and all three head slabs are written);
- * delta fp32 [B,H,T] workspace.  Recomputes P from lse; dropout mask regenerated from (drop_p, drop_seed). */
+ * workspaces: delta fp32 [B,H,T], dq_f32 fp32 [B*T, H*64] (dQ is accumulated across key blocks with fp32 reductions,
+ * then cast).  Recomputes P from lse; the dropout mask is regenerated from (drop_p, drop_seed). */
 int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
-                      const void* out, const void* dout, int64_t ld_out, const float* lse, float* delta, void* dqkv,
-                      int B, int T, int H, float scale, float drop_p, uint64_t drop_seed, void* stream);
+                      const void* out, const void* dout, int64_t ld_out, const float* lse, float* delta, float* dq_f32,
+                      void* dqkv, int B, int T, int H, float scale, float drop_p, uint64_t drop_seed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * ConvSubSampling (/root/reference/lib/convsubsampling.py:16-45): conv_sub_2(conv_sub_1(x)), no activation

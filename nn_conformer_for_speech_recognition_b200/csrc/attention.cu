@@ -252,15 +252,16 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
   delta[(static_cast<int64_t>(b_) * H + h) * T + t] = acc;
 }
 
-// Thread r (query row q_idx) turns its S row and dP row (TMEM) into P (optionally dropped, for dV) and
-// dS = P o (dP*drop - delta) * scale, both written as bf16 [q][key] K-major SW128 tiles (2 x [128][64]).
-// sP may be nullptr (dQ kernel needs only dS).
+// Thread (row = tid & 127, column half = tid >> 7) turns 64 columns of its S row and dP row (TMEM) into
+// P (optionally dropped, feeds dV) and dS = P o (dP*drop - delta) * scale, both written as bf16 [q][key] K-major
+// SW128 tiles (2 x [128][64]; column half h is exactly 64-column block h).
 __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint32_t tm_s, uint32_t tm_dp, uint8_t* sP,
-                                                   uint8_t* sdS, int tid, int q_idx, int key0, int len, float lse_r,
-                                                   float delta_r, uint64_t drop_row) {
+                                                   uint8_t* sdS, int row, int chalf, int q_idx, int key0, int len,
+                                                   float lse_r, float delta_r, uint64_t drop_row) {
   const bool q_ok = q_idx < p.T;
 #pragma unroll 1
-  for (int c = 0; c < AT_BK; c += 32) {
+  for (int cc = 0; cc < 64; cc += 32) {
+    const int c = chalf * 64 + cc;
     uint32_t vs[32], vd[32];
     __syncwarp();
     tmem_ld32(tm_s + c, vs);
@@ -281,11 +282,10 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const uint32_t off = sw128_offset(tid, c + g * 8, 128);
-      if (sP)
-        *reinterpret_cast<uint4*>(sP + off) =
-            make_uint4(pack_bf16(pr[g * 8], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
-                       pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
+      const uint32_t off = sw128_offset(row, c + g * 8, 128);
+      *reinterpret_cast<uint4*>(sP + off) =
+          make_uint4(pack_bf16(pr[g * 8], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
+                     pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
       *reinterpret_cast<uint4*>(sdS + off) =
           make_uint4(pack_bf16(ds[g * 8], ds[g * 8 + 1]), pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]),
                      pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]), pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]));
@@ -293,51 +293,39 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
   }
 }
 
-// write a 128 x 64 fp32 TMEM tile (this thread's row) as bf16 to dst (nullptr = skip)
-__device__ __forceinline__ void attn_store_row(uint32_t tm, __nv_bfloat16* dst) {
-#pragma unroll
-  for (int c = 0; c < AT_DH; c += 32) {
-    uint32_t v[32];
-    __syncwarp();
-    tmem_ld32(tm + c, v);
-    tmem_wait_ld();
-    if (dst) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        *reinterpret_cast<uint4*>(dst + c + g * 8) =
-            make_uint4(pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
-                       pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
-                       pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
-                       pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
-    }
-  }
-}
-
-// dK, dV for one 128-key block: loops over all query blocks of the utterance.
-__global__ void __launch_bounds__(128, 1) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV,
-                                                               const __grid_constant__ CUtensorMap tmDO,
-                                                               const AttnBwdParams p) {
+// One kernel for dQ, dK, dV.  CTA = (128-key block j, head, utterance), 256 threads (two per tile row, 64 columns
+// each), loops over the utterance's query blocks i with Q_i / dO_i double-buffered by TMA:
+//   UMMA  S = Q_i K_j^T, dP = dO_i V_j^T                  -> TMEM [0,128) and [128,256)
+//   regs  P = exp2(S*scale - lse), dS = P o (dP - delta)   -> smem (bf16, K-major SW128), dropout regenerated
+//   UMMA  dV += P^T dO_i, dK += dS^T Q_i  (accumulate over i in TMEM), dQp = dS K_j (fresh)
+//   regs  dQ[i] += dQp  as fp32 red.global.add.v4 (each (i,j) pair contributes once; a cast kernel makes it bf16)
+// S and dP are recomputed here from the saved log-sum-exp, so no T x T tensor ever reaches HBM.
+__global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                          const __grid_constant__ CUtensorMap tmDO,
+                                                          const AttnBwdParams p, float* __restrict__ dq_f32) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  constexpr uint32_t OFF_K = 0, OFF_V = 16384, OFF_Q = 32768, OFF_DO = 49152, OFF_P = 65536, OFF_DS = 98304,
-                     OFF_BAR = 131072;
+  constexpr uint32_t OFF_K = 0, OFF_V = 16384, OFF_Q = 32768 /*2 bufs*/, OFF_DO = 65536 /*2 bufs*/, OFF_P = 98304,
+                     OFF_DS = 131072, OFF_BAR = 163840;
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* bar_q = bar_kv + 1;
-  uint64_t* bar_s = bar_kv + 2;
-  uint64_t* bar_acc = bar_kv + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 4);
+  uint64_t* bar_q = bar_kv + 1;            // [2]
+  uint64_t* bar_s = bar_kv + 3;
+  uint64_t* bar_acc = bar_kv + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 5);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, chalf = tid >> 7;
   const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int len = min(p.lengths[b], p.T);
   const int key0 = j * AT_BK, row_base = b * p.T;
-  const int key_idx = key0 + tid;
-  __nv_bfloat16* dk_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.k_col + h * AT_DH : nullptr;
-  __nv_bfloat16* dv_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.v_col + h * AT_DH : nullptr;
-  if (key0 >= len) {                       // every key of this block is masked: P = 0 -> dK = dV = 0
+  const int key_idx = key0 + row;
+  // this thread stores 32 of the 64 head-dim columns of its key row
+  __nv_bfloat16* dk_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.k_col + h * AT_DH + chalf * 32 : nullptr;
+  __nv_bfloat16* dv_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.v_col + h * AT_DH + chalf * 32 : nullptr;
+  if (key0 >= len) {                       // every key of this block is masked: P = 0 -> dK = dV = 0, no dQ contribution
     if (dk_dst) {
 #pragma unroll
-      for (int g = 0; g < AT_DH / 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         reinterpret_cast<uint4*>(dk_dst)[g] = make_uint4(0, 0, 0, 0);
         reinterpret_cast<uint4*>(dv_dst)[g] = make_uint4(0, 0, 0, 0);
       }
@@ -346,7 +334,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dkv_kernel(const __grid_const
   }
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO);
-    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_acc, 1);
+    mbar_init(bar_kv, 1); mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1); mbar_init(bar_s, 1); mbar_init(bar_acc, 1);
     fence_barrier_init();
   }
   if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 512); }
@@ -354,33 +342,40 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dkv_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320;
+  const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+  const int nqb = (p.T + AT_BQ - 1) / AT_BQ;
+  auto load_q = [&](int i) {
+    const int bf = i & 1;
+    mbar_expect_tx(&bar_q[bf], 32768);
+    tma_load_2d(smem + OFF_Q + bf * 16384, &tmQKV, &bar_q[bf], p.q_col + h * AT_DH, row_base + i * AT_BQ);
+    tma_load_2d(smem + OFF_DO + bf * 16384, &tmDO, &bar_q[bf], h * AT_DH, row_base + i * AT_BQ);
+  };
   if (tid == 0) {
     mbar_expect_tx(bar_kv, 32768);
     tma_load_2d(smem + OFF_K, &tmQKV, bar_kv, p.k_col + h * AT_DH, row_base + key0);
     tma_load_2d(smem + OFF_V, &tmQKV, bar_kv, p.v_col + h * AT_DH, row_base + key0);
+    load_q(0);
   }
   constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, false, false);
   constexpr uint32_t idesc_mm = umma_idesc_bf16(128, 64, true, true);
-  const int nqb = (p.T + AT_BQ - 1) / AT_BQ;
+  constexpr uint32_t idesc_km = umma_idesc_bf16(128, 64, false, true);
   for (int i = 0; i < nqb; ++i) {
-    const uint32_t ph = i & 1;
-    const int q_idx = i * AT_BQ + tid;
+    const uint32_t ph = i & 1, bf = i & 1;
+    const uint32_t q_addr = base + OFF_Q + bf * 16384, do_addr = base + OFF_DO + bf * 16384;
+    const int q_idx = i * AT_BQ + row;
     if (tid == 0) {
-      mbar_expect_tx(bar_q, 32768);
-      tma_load_2d(smem + OFF_Q, &tmQKV, bar_q, p.q_col + h * AT_DH, row_base + i * AT_BQ);
-      tma_load_2d(smem + OFF_DO, &tmDO, bar_q, h * AT_DH, row_base + i * AT_BQ);
+      if (i + 1 < nqb) load_q(i + 1);      // buffer (i+1)&1 was released by iteration i-1's bar_acc wait
       if (i == 0) mbar_wait(bar_kv, 0);
-      mbar_wait(bar_q, ph);
+      mbar_wait(&bar_q[bf], (i >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 4; ++k)          // S = Q K^T
-        umma_bf16(tmem_base + TM_S, umma_desc_sw128(base + OFF_Q + k * 32, 16, 1024),
+        umma_bf16(tmem_base + TM_S, umma_desc_sw128(q_addr + k * 32, 16, 1024),
                   umma_desc_sw128(base + OFF_K + k * 32, 16, 1024), idesc_kk, k > 0);
 #pragma unroll
       for (int k = 0; k < 4; ++k)          // dP = dO V^T
-        umma_bf16(tmem_base + TM_DP, umma_desc_sw128(base + OFF_DO + k * 32, 16, 1024),
+        umma_bf16(tmem_base + TM_DP, umma_desc_sw128(do_addr + k * 32, 16, 1024),
                   umma_desc_sw128(base + OFF_V + k * 32, 16, 1024), idesc_kk, k > 0);
       tc_commit(bar_s);
     }
@@ -388,8 +383,8 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dkv_kernel(const __grid_const
     const float lse_r = p.lse[stat], delta_r = p.delta[stat];
     mbar_wait(bar_s, ph);
     tc_fence_after();
-    attn_bwd_tile_math(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P, smem + OFF_DS, tid, q_idx, key0, len, lse_r,
-                       delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad);
+    attn_bwd_tile_math(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P, smem + OFF_DS, row, chalf, q_idx, key0, len,
+                       lse_r, delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -398,115 +393,65 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dkv_kernel(const __grid_const
 #pragma unroll
       for (int k = 0; k < 8; ++k)          // dV += P^T dO   (reduction over the 128 queries)
         umma_bf16(tmem_base + TM_DV, umma_desc_sw128(base + OFF_P + k * 2048, 16384, 1024),
-                  umma_desc_sw128(base + OFF_DO + k * 2048, 8192, 1024), idesc_mm, (i | k) ? 1u : 0u);
+                  umma_desc_sw128(do_addr + k * 2048, 8192, 1024), idesc_mm, (i | k) ? 1u : 0u);
 #pragma unroll
       for (int k = 0; k < 8; ++k)          // dK += dS^T Q
         umma_bf16(tmem_base + TM_DK, umma_desc_sw128(base + OFF_DS + k * 2048, 16384, 1024),
-                  umma_desc_sw128(base + OFF_Q + k * 2048, 8192, 1024), idesc_mm, (i | k) ? 1u : 0u);
+                  umma_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_mm, (i | k) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)          // dQp = dS K     (reduction over the 128 keys; K tile read MN-major)
+        umma_bf16(tmem_base + TM_DQ, umma_desc_sw128(base + OFF_DS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                  umma_desc_sw128(base + OFF_K + k * 2048, 8192, 1024), idesc_km, k > 0);
       tc_commit(bar_acc);
-      mbar_wait(bar_acc, ph);              // Q/dO/P/dS tiles are reused by the next query block
     }
-    __syncthreads();
-  }
-  tc_fence_after();
-  attn_store_row(tm_lane + TM_DV, dv_dst);
-  attn_store_row(tm_lane + TM_DK, dk_dst);
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
+    mbar_wait(bar_acc, ph);                // all three products done: smem tiles and S/dP are free again
     tc_fence_after();
-    __syncwarp();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// dQ for one 128-query block: loops over the key blocks below lengths[b].
-__global__ void __launch_bounds__(128, 1) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV,
-                                                              const __grid_constant__ CUtensorMap tmDO,
-                                                              const AttnBwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  constexpr uint32_t OFF_K = 0, OFF_V = 16384, OFF_Q = 32768, OFF_DO = 49152, OFF_DS = 65536, OFF_BAR = 98304;
-  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* bar_q = bar_kv + 1;
-  uint64_t* bar_s = bar_kv + 2;
-  uint64_t* bar_acc = bar_kv + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 4);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int len = min(p.lengths[b], p.T);
-  const int nkb = (len + AT_BK - 1) / AT_BK;
-  const int row_base = b * p.T;
-  const int q_idx = i * AT_BQ + tid;
-  __nv_bfloat16* dq_dst = q_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + q_idx) * p.ld + p.q_col + h * AT_DH : nullptr;
-  if (nkb == 0) {                          // zero-length utterance: the forward output was NaN; define dQ = 0
-    if (dq_dst)
+    {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(tm_lane + TM_DQ + chalf * 32, v);
+      tmem_wait_ld();
+      if (q_idx < p.T) {
+        float* dst = dq_f32 + static_cast<int64_t>(row_base + q_idx) * (p.H * AT_DH) + h * AT_DH + chalf * 32;
 #pragma unroll
-      for (int g = 0; g < AT_DH / 8; ++g) reinterpret_cast<uint4*>(dq_dst)[g] = make_uint4(0, 0, 0, 0);
-    return;
-  }
-  if (tid == 0) {
-    tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO);
-    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_acc, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 512); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256;
-  if (tid == 0) {
-    mbar_expect_tx(bar_q, 32768);
-    tma_load_2d(smem + OFF_Q, &tmQKV, bar_q, p.q_col + h * AT_DH, row_base + i * AT_BQ);
-    tma_load_2d(smem + OFF_DO, &tmDO, bar_q, h * AT_DH, row_base + i * AT_BQ);
-  }
-  constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, false, false);
-  constexpr uint32_t idesc_km = umma_idesc_bf16(128, 64, false, true);
-  const int64_t stat = static_cast<int64_t>(b * p.H + h) * p.T + min(q_idx, p.T - 1);
-  const float lse_r = p.lse[stat], delta_r = p.delta[stat];
-  for (int j = 0; j < nkb; ++j) {
-    const uint32_t ph = j & 1;
-    const int key0 = j * AT_BK;
-    if (tid == 0) {
-      mbar_expect_tx(bar_kv, 32768);
-      tma_load_2d(smem + OFF_K, &tmQKV, bar_kv, p.k_col + h * AT_DH, row_base + key0);
-      tma_load_2d(smem + OFF_V, &tmQKV, bar_kv, p.v_col + h * AT_DH, row_base + key0);
-      if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_kv, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem_base + TM_S, umma_desc_sw128(base + OFF_Q + k * 32, 16, 1024),
-                  umma_desc_sw128(base + OFF_K + k * 32, 16, 1024), idesc_kk, k > 0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem_base + TM_DP, umma_desc_sw128(base + OFF_DO + k * 32, 16, 1024),
-                  umma_desc_sw128(base + OFF_V + k * 32, 16, 1024), idesc_kk, k > 0);
-      tc_commit(bar_s);
+        for (int g = 0; g < 8; ++g)
+          asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + g * 4), "f"(__uint_as_float(v[g * 4])),
+                       "f"(__uint_as_float(v[g * 4 + 1])), "f"(__uint_as_float(v[g * 4 + 2])),
+                       "f"(__uint_as_float(v[g * 4 + 3]))
+                       : "memory");
+      }
     }
-    mbar_wait(bar_s, ph);
-    tc_fence_after();
-    attn_bwd_tile_math(p, tm_lane + TM_S, tm_lane + TM_DP, nullptr, smem + OFF_DS, tid, q_idx, key0, len, lse_r,
-                       delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad);
-    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 8; ++k)          // dQ += dS K   (reduction over the 128 keys; K tile read MN-major)
-        umma_bf16(tmem_base + TM_DQ, umma_desc_sw128(base + OFF_DS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                  umma_desc_sw128(base + OFF_K + k * 2048, 8192, 1024), idesc_km, (j | k) ? 1u : 0u);
-      tc_commit(bar_acc);
-      mbar_wait(bar_acc, ph);
-    }
-    __syncthreads();
   }
   tc_fence_after();
-  attn_store_row(tm_lane + TM_DQ, dq_dst);
+  {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld32(tm_lane + TM_DV + chalf * 32, v);
+    tmem_wait_ld();
+    if (dv_dst) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        reinterpret_cast<uint4*>(dv_dst)[g] =
+            make_uint4(pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
+                       pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
+                       pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
+                       pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+    }
+    __syncwarp();
+    tmem_ld32(tm_lane + TM_DK + chalf * 32, v);
+    tmem_wait_ld();
+    if (dk_dst) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        reinterpret_cast<uint4*>(dk_dst)[g] =
+            make_uint4(pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
+                       pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
+                       pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
+                       pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -516,9 +461,19 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dq_kernel(const __grid_consta
   }
 }
 
-constexpr uint32_t ATTN_DKV_SMEM = 131072 + 64 + 1024;
-constexpr uint32_t ATTN_DQ_SMEM = 98304 + 64 + 1024;
+// dq fp32 [rows, H*64] -> the Q slab of dqkv (bf16, pitch ld)
+__global__ void __launch_bounds__(256) attn_dq_cast_kernel(const float* __restrict__ dq, __nv_bfloat16* __restrict__ dqkv,
+                                                          int64_t rows, int cols, int64_t ld, int q_col) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i >= rows * cols) return;
+  const int64_t r = i / cols;
+  const int c = static_cast<int>(i % cols);
+  const float4 a = *reinterpret_cast<const float4*>(dq + i), b4 = *reinterpret_cast<const float4*>(dq + i + 4);
+  *reinterpret_cast<uint4*>(dqkv + r * ld + q_col + c) =
+      make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b4.x, b4.y), pack_bf16(b4.z, b4.w));
+}
 
+constexpr uint32_t ATTN_BWD_SMEM = 163840 + 64 + 1024;
 
 }  // namespace b2c
 
@@ -555,9 +510,9 @@ extern "C" int b2c_attention_fwd(const void* qkv, int64_t ld, int64_t k_off, int
 
 extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
                                  const void* out, const void* dout, int64_t ld_out, const float* lse, float* delta,
-                                 void* dqkv, int B, int T, int H, float scale, float drop_p, uint64_t drop_seed,
-                                 void* stream) {
-  B2C_REQUIRE(qkv && lengths && out && dout && lse && delta && dqkv, "b2c_attention_bwd: null pointer");
+                                 float* dq_f32, void* dqkv, int B, int T, int H, float scale, float drop_p,
+                                 uint64_t drop_seed, void* stream) {
+  B2C_REQUIRE(qkv && lengths && out && dout && lse && delta && dq_f32 && dqkv, "b2c_attention_bwd: null pointer");
   B2C_REQUIRE(B > 0 && T > 0 && H > 0, "b2c_attention_bwd: empty problem");
   B2C_REQUIRE(ld % 8 == 0 && ld_out % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
               "b2c_attention_bwd: pitches/offsets must be multiples of 8 elements");
@@ -567,13 +522,14 @@ extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int
   if (int rc = get_tensor_map_2d(&td, dout, 2, static_cast<uint64_t>(H) * AT_DH, static_cast<uint64_t>(B) * T, ld_out * 2, 64, 128, true)) return rc;
   static bool configured = false;
   if (!configured) {
-    B2C_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_DKV_SMEM));
-    B2C_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_DQ_SMEM));
+    B2C_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_BWD_SMEM));
     configured = true;
   }
-  const int64_t n = static_cast<int64_t>(B) * T * H;
+  const int64_t rows = static_cast<int64_t>(B) * T;
+  const int64_t n = rows * H;
   attn_delta_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), ld_out, delta, B, T, H);
+  B2C_CUDA(cudaMemsetAsync(dq_f32, 0, static_cast<size_t>(rows) * H * AT_DH * sizeof(float), st));
   AttnBwdParams p;
   p.lengths = lengths; p.lse = lse; p.delta = delta; p.dqkv = static_cast<__nv_bfloat16*>(dqkv); p.ld = ld;
   p.B = B; p.T = T; p.H = H;
@@ -581,9 +537,11 @@ extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int
   p.scale = scale; p.scale_log2 = scale * LOG2E;
   p.Tpad = (T + 1) & ~1;
   p.drop = make_drop(drop_p, drop_seed);
-  dim3 grid((T + AT_BQ - 1) / AT_BQ, H, B);
-  attn_bwd_dkv_kernel<<<grid, 128, ATTN_DKV_SMEM, st>>>(tq, td, p);
-  attn_bwd_dq_kernel<<<grid, 128, ATTN_DQ_SMEM, st>>>(tq, td, p);
+  dim3 grid((T + AT_BK - 1) / AT_BK, H, B);
+  attn_bwd_kernel<<<grid, 256, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
+  const int64_t n8 = rows * H * AT_DH / 8;
+  attn_dq_cast_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, st>>>(dq_f32, static_cast<__nv_bfloat16*>(dqkv),
+                                                                               rows, H * AT_DH, ld, 0);
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

@@ -41,6 +41,13 @@ __device__ __forceinline__ void stage_glu(const __nv_bfloat16* __restrict__ u, f
   }
 }
 
+// depthwise taps of this CTA's 64 channels -> smem, tap-major [k][64] (coalesced global read, conflict-free float2 reads)
+__device__ __forceinline__ void stage_taps(const float* __restrict__ wdw, float* __restrict__ sWt, int c0, int d, int k) {
+  const int nch = min(CM_CH, d - c0);
+  for (int e = threadIdx.x; e < nch * k; e += blockDim.x) sWt[(e % k) * CM_CH + e / k] = __ldg(wdw + static_cast<int64_t>(c0) * k + e);
+  for (int e = nch * k + threadIdx.x; e < CM_CH * k; e += blockDim.x) sWt[(e % k) * CM_CH + e / k] = 0.f;
+}
+
 // MODE 0: eval  -> out = SiLU(BN_running(y))            (bn_scale/bn_shift folded per channel)
 // MODE 1: train -> y (bf16) + per-channel sum / sumsq   (stats fp64 [2][d], atomics once per CTA per channel)
 template <int MODE>
@@ -51,21 +58,24 @@ __global__ void __launch_bounds__(256) convmod_fwd_kernel(const __nv_bfloat16* _
                                                           const float* __restrict__ bn_var, float eps,
                                                           __nv_bfloat16* __restrict__ out, double* __restrict__ stats,
                                                           int T, int d, int k) {
-  extern __shared__ float2 sG[];                 // [(CM_TT + k - 1)][32] float2
+  extern __shared__ float2 sG[];                 // [(CM_TT + k - 1)][32] float2, then taps [k][64] float
   __shared__ float red[2][8][CM_CH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t0 = blockIdx.x * CM_TT, c0 = blockIdx.y * CM_CH, b = blockIdx.z;
   const int half = (k - 1) / 2;
   const int ch = c0 + lane * 2;
   const bool ch_ok = ch < d;
+  float* sWt = reinterpret_cast<float*>(sG + (CM_TT + k - 1) * 32);
 
+  stage_taps(wdw, sWt, c0, d, k);
   stage_glu(u, sG, b, T, d, c0, t0 - half, CM_TT + k - 1);
+  __syncthreads();
 
   float w0[CM_MAXK], w1[CM_MAXK];
 #pragma unroll
   for (int j = 0; j < CM_MAXK; ++j) {
-    w0[j] = (j < k && ch_ok) ? __ldg(wdw + static_cast<int64_t>(ch) * k + j) : 0.f;
-    w1[j] = (j < k && ch_ok) ? __ldg(wdw + static_cast<int64_t>(ch + 1) * k + j) : 0.f;
+    const float2 wv = j < k ? *reinterpret_cast<const float2*>(sWt + j * CM_CH + lane * 2) : make_float2(0.f, 0.f);
+    w0[j] = wv.x; w1[j] = wv.y;
   }
   const float bias0 = ch_ok ? __ldg(bdw + ch) : 0.f, bias1 = ch_ok ? __ldg(bdw + ch + 1) : 0.f;
   float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
@@ -75,7 +85,6 @@ __global__ void __launch_bounds__(256) convmod_fwd_kernel(const __nv_bfloat16* _
     sh0 = __ldg(bn_b + ch) - __ldg(bn_mean + ch) * sc0;
     sh1 = __ldg(bn_b + ch + 1) - __ldg(bn_mean + ch + 1) * sc1;
   }
-  __syncthreads();
 
   float s_sum0 = 0.f, s_sum1 = 0.f, s_sq0 = 0.f, s_sq1 = 0.f;
 #pragma unroll 1
@@ -229,6 +238,7 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
   float2* sG = sbuf;                                 // GLU(u)  [nrow][32]
   float2* sDY = sbuf + nrow * 32;                    // dy      [nrow][32]
   float* sW = reinterpret_cast<float*>(sbuf + 2 * nrow * 32);   // dw partials [64][CM_MAXK] + dbdw [64]
+  float* sWt = sW + CM_CH * (CM_MAXK + 1);                       // taps [k][64]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t0 = blockIdx.x * CM_TT, c0 = blockIdx.y * CM_CH, b = blockIdx.z;
   const int half = (k - 1) / 2;
@@ -236,6 +246,7 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
   const bool ch_ok = ch < d;
   for (int i = threadIdx.x; i < CM_CH * (CM_MAXK + 1); i += blockDim.x) sW[i] = 0.f;
 
+  stage_taps(wdw, sWt, c0, d, k);
   stage_glu(u, sG, b, T, d, c0, t0 - half, nrow);
   {
     float m0 = 0, m1 = 0, q0 = 0, q1 = 0, g0 = 0, g1 = 0, b0 = 0, b1 = 0, a10 = 0, a11 = 0, a20 = 0, a21 = 0;
@@ -273,8 +284,8 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
     float w0[CM_MAXK], w1[CM_MAXK];                   // REVERSED taps: wr[j'] = w[k-1-j']
 #pragma unroll
     for (int j = 0; j < CM_MAXK; ++j) {
-      w0[j] = (j < k && ch_ok) ? __ldg(wdw + static_cast<int64_t>(ch) * k + (k - 1 - j)) : 0.f;
-      w1[j] = (j < k && ch_ok) ? __ldg(wdw + static_cast<int64_t>(ch + 1) * k + (k - 1 - j)) : 0.f;
+      const float2 wv = j < k ? *reinterpret_cast<const float2*>(sWt + (k - 1 - j) * CM_CH + lane * 2) : make_float2(0.f, 0.f);
+      w0[j] = wv.x; w1[j] = wv.y;
     }
 #pragma unroll 1
     for (int grp = 0; grp < (CM_TT / 8) / CM_G; ++grp) {
@@ -354,6 +365,16 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+static int convmod_fwd_attr() {
+  static bool configured = false;
+  if (!configured) {
+    B2C_CUDA(cudaFuncSetAttribute(convmod_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  return 0;
+}
+
 static int check_convmod(int B, int T, int d, int k, const char* who) {
   B2C_REQUIRE(B > 0 && T > 0 && d > 0, "%s: empty problem", who);
   B2C_REQUIRE(d % 8 == 0, "%s: d=%d must be a multiple of 8", who, d);
@@ -371,7 +392,8 @@ extern "C" int b2c_convmod_eval_fwd(const void* u, const float* wdw, const float
   B2C_REQUIRE(u && wdw && bdw && bn_w && bn_b && bn_mean && bn_var && out, "b2c_convmod_eval_fwd: null pointer");
   if (int rc = check_convmod(B, T, d, k, "b2c_convmod_eval_fwd")) return rc;
   dim3 grid((T + CM_TT - 1) / CM_TT, (d + CM_CH - 1) / CM_CH, B);
-  const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2);
+  const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) + CM_CH * k * sizeof(float);
+  if (int rc = convmod_fwd_attr()) return rc;
   convmod_fwd_kernel<0><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(u), wdw, bdw, bn_w, bn_b, bn_mean, bn_var, eps,
       static_cast<__nv_bfloat16*>(out), nullptr, T, d, k);
@@ -384,7 +406,8 @@ extern "C" int b2c_convmod_dw_fwd(const void* u, const float* wdw, const float* 
   B2C_REQUIRE(u && wdw && bdw && y && stats, "b2c_convmod_dw_fwd: null pointer");
   if (int rc = check_convmod(B, T, d, k, "b2c_convmod_dw_fwd")) return rc;
   dim3 grid((T + CM_TT - 1) / CM_TT, (d + CM_CH - 1) / CM_CH, B);
-  const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2);
+  const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) + CM_CH * k * sizeof(float);
+  if (int rc = convmod_fwd_attr()) return rc;
   convmod_fwd_kernel<1><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(u), wdw, bdw, nullptr, nullptr, nullptr, nullptr, 0.f,
       static_cast<__nv_bfloat16*>(y), stats, T, d, k);
@@ -440,7 +463,8 @@ extern "C" int b2c_convmod_dw_bwd(const void* dc, const void* y, const void* u, 
               "b2c_convmod_dw_bwd: null pointer");
   if (int rc = check_convmod(B, T, d, k, "b2c_convmod_dw_bwd")) return rc;
   dim3 grid((T + CM_TT - 1) / CM_TT, (d + CM_CH - 1) / CM_CH, B);
-  const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) * 2 + CM_CH * (CM_MAXK + 1) * sizeof(float);
+  const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) * 2 + CM_CH * (CM_MAXK + 1) * sizeof(float) +
+                      CM_CH * k * sizeof(float);
   static bool configured = false;
   if (!configured) {
     B2C_CUDA(cudaFuncSetAttribute(convmod_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));

@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     constexpr int CW = Cfg::CW;
     constexpr int LPR = CW / 4;                        // lanes per row in the coalesced domain (float4 each)
     constexpr int RPI = 32 / LPR;                      // rows per warp instruction
+    constexpr int NIT = 32 / RPI;                      // iterations to cover the warp's 32 rows
     const int ew = warp - 2;
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     const int half = ew >> 2;                          // which half of the BN columns
@@ -184,12 +185,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const int m_blk = (tile / p.n_tiles) % p.m_tiles;
       const int split = tile / (p.n_tiles * p.m_tiles);
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
       const float* bias = split == 0 ? static_cast<const float*>(ep.bias) : nullptr;   // once per split-K
+      const bool want_resid = ep.resid && !ep.accumulate && ep.out_dtype == B2C_F32;
+      const bool want_aux = ep.act == B2C_ACT_SILU_BWD;
 #pragma unroll 1
       for (int ch = 0; ch < Cfg::CHUNKS; ++ch) {
         const int col_t = half * (BN / 2) + ch * CW;   // first column of this chunk inside the tile
+        const int64_t col = static_cast<int64_t>(n_blk) * BN + col_t + c_lane * 4;
+        const bool col_ok = col < p.N;
+        const int64_t row0 = static_cast<int64_t>(m_blk) * BM + q * 32 + r_lane;
+        // issue every global read of this chunk BEFORE waiting for the accumulator: the loads' latency overlaps the
+        // main loop of this tile instead of serialising inside the epilogue
+        uint4 pre[NIT];
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+        if (want_resid) {
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            const int64_t row = row0 + i * RPI;
+            if (row < p.M && col_ok)
+              pre[i] = *reinterpret_cast<const uint4*>(static_cast<const float*>(ep.resid) + row * ep.ld_out + col);
+          }
+        } else if (want_aux) {
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            const int64_t row = row0 + i * RPI;
+            if (row < p.M && col_ok) {
+              const uint2 a = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(ep.aux) + row * ep.ld_aux + col);
+              pre[i].x = a.x; pre[i].y = a.y;
+            }
+          }
+        }
+        if (ch == 0) {
+          mbar_wait(&tfull_bar[as], aph);
+          tc_fence_after();
+        }
         uint32_t v[CW];
         __syncwarp();
         const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16) + col_t;
@@ -207,14 +237,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           *reinterpret_cast<uint4*>(stg + lane * CW + ((c ^ (lane & 7)) << 2)) =
               make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         __syncwarp();
-        const int64_t col = static_cast<int64_t>(n_blk) * BN + col_t + c_lane * 4;
-        const bool col_ok = col < p.N;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
-#pragma unroll 4
-        for (int i = 0; i < 32 / RPI; ++i) {
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
           const int r = i * RPI + r_lane;
-          const int64_t row = static_cast<int64_t>(m_blk) * BM + q * 32 + r;
+          const int64_t row = row0 + i * RPI;
           if (row >= p.M || !col_ok) continue;
           const float4 a4 = *reinterpret_cast<const float4*>(stg + r * CW + ((c_lane ^ (r & 7)) << 2));
           float f[4] = {a4.x + bv.x, a4.y + bv.y, a4.z + bv.z, a4.w + bv.w};
@@ -224,9 +250,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           if (ep.act == B2C_ACT_SILU) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) f[j] *= sigmoid_fast(f[j]);
-          } else if (ep.act == B2C_ACT_SILU_BWD) {     // f = dL/dh ; aux = pre-activation u ; out = f * silu'(u)
-            const uint2 a = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(ep.aux) + row * ep.ld_aux + col);
-            const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y);
+          } else if (want_aux) {                        // f = dL/dh ; aux = pre-activation u ; out = f * silu'(u)
+            const float2 a0 = unpack_bf16(pre[i].x), a1 = unpack_bf16(pre[i].y);
             const float u[4] = {a0.x, a0.y, a1.x, a1.y};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -254,9 +279,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
               asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3])
                            : "memory");
             } else {
-              if (ep.resid) {
-                const float4 r4 = *reinterpret_cast<const float4*>(static_cast<const float*>(ep.resid) + row * ep.ld_out + col);
-                f[0] += r4.x; f[1] += r4.y; f[2] += r4.z; f[3] += r4.w;
+              if (want_resid) {
+                f[0] += __uint_as_float(pre[i].x); f[1] += __uint_as_float(pre[i].y);
+                f[2] += __uint_as_float(pre[i].z); f[3] += __uint_as_float(pre[i].w);
               }
               *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
             }
