@@ -22,22 +22,35 @@ constexpr int CM_CH = 64;      // channels per CTA
 constexpr int CM_MAXK = 33;    // taps (repo default k=33, Conformer S/M/L k=31)
 constexpr int CM_G = 8;        // outputs per register window
 
-// stage GLU(u) for frames [t_lo, t_lo + nrow) of utterance b into smem (zero outside [0,T))
+// stage GLU(u) for frames [t_lo, t_lo + nrow) of utterance b into smem (zero outside [0,T)).
+// Rows are taken 4 at a time per warp with all 8 global loads issued before any is consumed (memory-level
+// parallelism: the un-batched version exposed one DRAM round trip per row and dominated the kernel).
 __device__ __forceinline__ void stage_glu(const __nv_bfloat16* __restrict__ u, float2* __restrict__ sG, int b, int T,
                                           int d, int c0, int t_lo, int nrow) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ch = c0 + lane * 2;
-  for (int r = warp; r < nrow; r += 8) {
-    const int t = t_lo + r;
-    float2 g = make_float2(0.f, 0.f);
-    if (t >= 0 && t < T && ch < d) {
-      const __nv_bfloat16* row = u + (static_cast<int64_t>(b) * T + t) * (2 * d);
-      const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(row + ch));
-      const float2 gt = unpack_bf16(*reinterpret_cast<const uint32_t*>(row + d + ch));
-      g.x = a.x * sigmoid_f(gt.x);
-      g.y = a.y * sigmoid_f(gt.y);
+  const bool ch_ok = ch < d;
+  constexpr int UN = 4;
+  for (int r0 = warp; r0 < nrow; r0 += 8 * UN) {
+    uint32_t av[UN], gv[UN];
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const int r = r0 + q * 8, t = t_lo + r;
+      av[q] = gv[q] = 0u;
+      if (r < nrow && t >= 0 && t < T && ch_ok) {
+        const __nv_bfloat16* row = u + (static_cast<int64_t>(b) * T + t) * (2 * d);
+        av[q] = *reinterpret_cast<const uint32_t*>(row + ch);
+        gv[q] = *reinterpret_cast<const uint32_t*>(row + d + ch);
+      }
     }
-    sG[r * 32 + lane] = g;
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const int r = r0 + q * 8;
+      if (r < nrow) {
+        const float2 a = unpack_bf16(av[q]), gt = unpack_bf16(gv[q]);
+        sG[r * 32 + lane] = make_float2(a.x * sigmoid_f(gt.x), a.y * sigmoid_f(gt.y));   // zero rows: 0 * 0.5 = 0
+      }
+    }
   }
 }
 
@@ -262,19 +275,35 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
         atomicAdd(dbn_w + ch, static_cast<float>(sums[d + ch])); atomicAdd(dbn_w + ch + 1, static_cast<float>(sums[d + ch + 1]));
       }
     }
-    for (int r = warp; r < nrow; r += 8) {
-      const int t = t0 - half + r;
-      float2 dyv = make_float2(0.f, 0.f);
-      if (t >= 0 && t < T && ch_ok) {
-        const int64_t row = static_cast<int64_t>(b) * T + t;
-        const float2 dcv = unpack_bf16(*reinterpret_cast<const uint32_t*>(dc + row * d + ch));
-        const float2 yv = unpack_bf16(*reinterpret_cast<const uint32_t*>(y + row * d + ch));
-        const float yh0 = (yv.x - m0) * q0, yh1 = (yv.y - m1) * q1;
-        const float dz0 = dcv.x * silu_grad_f(yh0 * g0 + b0), dz1 = dcv.y * silu_grad_f(yh1 * g1 + b1);
-        dyv.x = g0 * q0 * (BN_TRAIN ? (dz0 - a10 - yh0 * a20) : dz0);
-        dyv.y = g1 * q1 * (BN_TRAIN ? (dz1 - a11 - yh1 * a21) : dz1);
+    constexpr int UN = 4;
+    for (int r0 = warp; r0 < nrow; r0 += 8 * UN) {
+      uint32_t dcr[UN], yr[UN];
+      bool ok[UN];
+#pragma unroll
+      for (int q = 0; q < UN; ++q) {
+        const int r = r0 + q * 8, t = t0 - half + r;
+        ok[q] = r < nrow && t >= 0 && t < T && ch_ok;
+        dcr[q] = yr[q] = 0u;
+        if (ok[q]) {
+          const int64_t row = static_cast<int64_t>(b) * T + t;
+          dcr[q] = *reinterpret_cast<const uint32_t*>(dc + row * d + ch);
+          yr[q] = *reinterpret_cast<const uint32_t*>(y + row * d + ch);
+        }
       }
-      sDY[r * 32 + lane] = dyv;
+#pragma unroll
+      for (int q = 0; q < UN; ++q) {
+        const int r = r0 + q * 8;
+        if (r >= nrow) continue;
+        float2 dyv = make_float2(0.f, 0.f);
+        if (ok[q]) {
+          const float2 dcv = unpack_bf16(dcr[q]), yv = unpack_bf16(yr[q]);
+          const float yh0 = (yv.x - m0) * q0, yh1 = (yv.y - m1) * q1;
+          const float dz0 = dcv.x * silu_grad_f(yh0 * g0 + b0), dz1 = dcv.y * silu_grad_f(yh1 * g1 + b1);
+          dyv.x = g0 * q0 * (BN_TRAIN ? (dz0 - a10 - yh0 * a20) : dz0);
+          dyv.y = g1 * q1 * (BN_TRAIN ? (dz1 - a11 - yh1 * a21) : dz1);
+        }
+        sDY[r * 32 + lane] = dyv;
+      }
     }
   }
   __syncthreads();

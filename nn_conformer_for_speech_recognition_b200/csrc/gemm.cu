@@ -65,7 +65,18 @@ __device__ __forceinline__ float tanh_approx(float x) {
 // sigmoid via one MUFU.TANH: 0.5*tanh(0.5 z) + 0.5 (abs error ~1e-3 of an output that is rounded to bf16 anyway)
 __device__ __forceinline__ float sigmoid_fast(float z) { return fmaf(0.5f, tanh_approx(0.5f * z), 0.5f); }
 
-template <int BN, bool A_MN, bool B_MN>
+// Epilogue specialisations (compile-time, so the per-element code stays a few dozen instructions and fits the
+// instruction cache -- the fully generic runtime-switched version was I-cache bound: ncu stall_no_inst dominated).
+enum : int {
+  EPI_GENERIC = 0,   // everything decided at run time (any combination the ABI allows)
+  EPI_BF16 = 1,      // out = bf16(acc [+ bias])                                  QKV / pointwise-1 / plain dgrad
+  EPI_SILU = 2,      // [out2 = bf16(acc+bias)]; out = bf16(drop(SiLU(acc+bias)))  FFN first linear
+  EPI_RESID = 3,     // out = resid + alpha * drop(acc + bias)      (fp32)          FFN second linear / out-proj / pointwise-2
+  EPI_SILU_BWD = 4,  // out = bf16(drop(acc * SiLU'(aux)))                          dgrad through the FFN activation
+  EPI_ACCUM = 5,     // out += alpha * acc   (fp32 red.global.add.v4)               weight gradients (split-K)
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmB,
                                                                        const GemmParams p) {
@@ -186,34 +197,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const int split = tile / (p.n_tiles * p.m_tiles);
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const float* bias = split == 0 ? static_cast<const float*>(ep.bias) : nullptr;   // once per split-K
-      const bool want_resid = ep.resid && !ep.accumulate && ep.out_dtype == B2C_F32;
-      const bool want_aux = ep.act == B2C_ACT_SILU_BWD;
+      constexpr bool G = EPI == EPI_GENERIC;
+      const bool want_resid = G ? (ep.resid && !ep.accumulate && ep.out_dtype == B2C_F32) : (EPI == EPI_RESID);
+      const bool want_aux = G ? (ep.act == B2C_ACT_SILU_BWD) : (EPI == EPI_SILU_BWD);
+      const bool do_silu = G ? (ep.act == B2C_ACT_SILU) : (EPI == EPI_SILU);
+      const bool out_bf16 = G ? (ep.out_dtype == B2C_BF16) : (EPI == EPI_BF16 || EPI == EPI_SILU || EPI == EPI_SILU_BWD);
+      const bool do_accum = G ? (ep.accumulate != 0) : (EPI == EPI_ACCUM);
+      const bool do_out2 = (G || EPI == EPI_SILU) && ep.out2 != nullptr;
+      const bool do_drop = (EPI != EPI_BF16 && EPI != EPI_ACCUM) && p.drop.thresh16 != 0;
+      const bool do_alpha = (G || EPI == EPI_RESID || EPI == EPI_ACCUM) && ep.alpha != 1.f;
 #pragma unroll 1
       for (int ch = 0; ch < Cfg::CHUNKS; ++ch) {
         const int col_t = half * (BN / 2) + ch * CW;   // first column of this chunk inside the tile
         const int64_t col = static_cast<int64_t>(n_blk) * BN + col_t + c_lane * 4;
         const bool col_ok = col < p.N;
         const int64_t row0 = static_cast<int64_t>(m_blk) * BM + q * 32 + r_lane;
-        // issue every global read of this chunk BEFORE waiting for the accumulator: the loads' latency overlaps the
-        // main loop of this tile instead of serialising inside the epilogue
-        uint4 pre[NIT];
+        const int64_t rl64 = p.M - row0;
+        const int rows_left = rl64 > 32 ? 32 : static_cast<int>(rl64);      // rows row0 + i*RPI are valid while i*RPI < rows_left
+        // touch every line this chunk will READ (residual / saved pre-activation) BEFORE waiting for the accumulator:
+        // prefetch.global.L2 needs no registers, and the later loads then see L2-hit latency that the 4-way
+        // unrolled loop below covers
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
-        if (want_resid) {
-#pragma unroll
+        if ((G || EPI != EPI_ACCUM) && bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+        const float* rp = static_cast<const float*>(ep.resid) + row0 * ep.ld_out + col;
+        const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(ep.aux) + row0 * ep.ld_aux + col;
+        if (col_ok && (want_resid || want_aux)) {
+#pragma unroll 4
           for (int i = 0; i < NIT; ++i) {
-            const int64_t row = row0 + i * RPI;
-            if (row < p.M && col_ok)
-              pre[i] = *reinterpret_cast<const uint4*>(static_cast<const float*>(ep.resid) + row * ep.ld_out + col);
-          }
-        } else if (want_aux) {
-#pragma unroll
-          for (int i = 0; i < NIT; ++i) {
-            const int64_t row = row0 + i * RPI;
-            if (row < p.M && col_ok) {
-              const uint2 a = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(ep.aux) + row * ep.ld_aux + col);
-              pre[i].x = a.x; pre[i].y = a.y;
-            }
+            if (i * RPI >= rows_left) break;
+            const void* ptr = want_resid ? static_cast<const void*>(rp + static_cast<int64_t>(i) * RPI * ep.ld_out)
+                                         : static_cast<const void*>(ap + static_cast<int64_t>(i) * RPI * ep.ld_aux);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
           }
         }
         if (ch == 0) {
@@ -237,53 +251,59 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           *reinterpret_cast<uint4*>(stg + lane * CW + ((c ^ (lane & 7)) << 2)) =
               make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         __syncwarp();
+        if (col_ok) {
+          const uint64_t drop_base = static_cast<uint64_t>(row0) * p.N + col;
+          __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(ep.out) + row0 * ep.ld_out + col;
+          float* of = static_cast<float*>(ep.out) + row0 * ep.ld_out + col;
+          __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(ep.out2) + row0 * ep.ld_out2 + col;
+#pragma unroll 4
+          for (int i = 0; i < NIT; ++i) {
+            if (i * RPI >= rows_left) break;
+            const int r = i * RPI + r_lane;
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + r * CW + ((c_lane ^ (r & 7)) << 2));
+            float f[4] = {a4.x + bv.x, a4.y + bv.y, a4.z + bv.z, a4.w + bv.w};
+            if (do_out2)                               // pre-activation copy (saved for the backward pass)
+              *reinterpret_cast<uint2*>(o2 + static_cast<int64_t>(i) * RPI * ep.ld_out2) =
+                  make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+            if (do_silu) {
 #pragma unroll
-        for (int i = 0; i < NIT; ++i) {
-          const int r = i * RPI + r_lane;
-          const int64_t row = row0 + i * RPI;
-          if (row >= p.M || !col_ok) continue;
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + r * CW + ((c_lane ^ (r & 7)) << 2));
-          float f[4] = {a4.x + bv.x, a4.y + bv.y, a4.z + bv.z, a4.w + bv.w};
-          if (ep.out2)                                 // pre-activation copy (saved for the backward pass)
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(ep.out2) + row * ep.ld_out2 + col) =
-                make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
-          if (ep.act == B2C_ACT_SILU) {
+              for (int j = 0; j < 4; ++j) f[j] *= sigmoid_fast(f[j]);
+            } else if (want_aux) {                      // f = dL/dh ; aux = pre-activation u ; out = f * silu'(u)
+              const uint2 av = *reinterpret_cast<const uint2*>(ap + static_cast<int64_t>(i) * RPI * ep.ld_aux);
+              const float2 a0 = unpack_bf16(av.x), a1 = unpack_bf16(av.y);
+              const float u[4] = {a0.x, a0.y, a1.x, a1.y};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) f[j] *= sigmoid_fast(f[j]);
-          } else if (want_aux) {                        // f = dL/dh ; aux = pre-activation u ; out = f * silu'(u)
-            const float2 a0 = unpack_bf16(pre[i].x), a1 = unpack_bf16(pre[i].y);
-            const float u[4] = {a0.x, a0.y, a1.x, a1.y};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float sg = sigmoid_fast(u[j]);
-              f[j] *= sg * fmaf(u[j], 1.f - sg, 1.f);
-            }
-          }
-          if (p.drop.thresh16) {
-            float s0, s1, s2, s3;
-            const uint64_t di = static_cast<uint64_t>(row) * p.N + col;      // N % 8 == 0, col % 4 == 0: even
-            drop_scale2(p.drop, di, s0, s1);
-            drop_scale2(p.drop, di + 2, s2, s3);
-            f[0] *= s0; f[1] *= s1; f[2] *= s2; f[3] *= s3;
-          }
-          if (ep.alpha != 1.f) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) f[j] *= ep.alpha;
-          }
-          if (ep.out_dtype == B2C_BF16) {
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(ep.out) + row * ep.ld_out + col) =
-                make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
-          } else {
-            float* o = static_cast<float*>(ep.out) + row * ep.ld_out + col;
-            if (ep.accumulate) {                       // split-K / gradient accumulation: fp32 reductions in L2
-              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3])
-                           : "memory");
-            } else {
-              if (want_resid) {
-                f[0] += __uint_as_float(pre[i].x); f[1] += __uint_as_float(pre[i].y);
-                f[2] += __uint_as_float(pre[i].z); f[3] += __uint_as_float(pre[i].w);
+              for (int j = 0; j < 4; ++j) {
+                const float sg = sigmoid_fast(u[j]);
+                f[j] *= sg * fmaf(u[j], 1.f - sg, 1.f);
               }
-              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+            }
+            if (do_drop) {
+              float s0, s1, s2, s3;
+              const uint64_t di = drop_base + static_cast<uint64_t>(i) * RPI * p.N;   // N % 8 == 0, col % 4 == 0: even
+              drop_scale2(p.drop, di, s0, s1);
+              drop_scale2(p.drop, di + 2, s2, s3);
+              f[0] *= s0; f[1] *= s1; f[2] *= s2; f[3] *= s3;
+            }
+            if (do_alpha) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) f[j] *= ep.alpha;
+            }
+            if (out_bf16) {
+              *reinterpret_cast<uint2*>(ob + static_cast<int64_t>(i) * RPI * ep.ld_out) =
+                  make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+            } else {
+              float* o = of + static_cast<int64_t>(i) * RPI * ep.ld_out;
+              if (do_accum) {                          // split-K / gradient accumulation: fp32 reductions in L2
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3])
+                             : "memory");
+              } else {
+                if (want_resid) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(rp + static_cast<int64_t>(i) * RPI * ep.ld_out);
+                  f[0] += r4.x; f[1] += r4.y; f[2] += r4.z; f[3] += r4.w;
+                }
+                *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+              }
             }
           }
         }
@@ -298,10 +318,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -357,16 +377,38 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   else       rc = get_tensor_map_2d(&tb, B, 2, N, K, ldb * 2, 64, BK, true);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define B2C_DISPATCH(BN_)                                                         \
-  if (bn == BN_) {                                                                \
-    if (!a_mn && !b_mn) return launch_gemm<BN_, false, false>(ta, tb, p, st);     \
-    if (!a_mn && b_mn) return launch_gemm<BN_, false, true>(ta, tb, p, st);       \
-    if (a_mn && b_mn) return launch_gemm<BN_, true, true>(ta, tb, p, st);         \
-    return launch_gemm<BN_, true, false>(ta, tb, p, st);                          \
+  // pick the specialised epilogue when the request matches one of the hot-path patterns, else the generic kernel
+  int epi = EPI_GENERIC;
+  const bool plain = !ep->out2 && !ep->aux && !ep->resid && !ep->accumulate && ep->act == B2C_ACT_NONE && ep->alpha == 1.f;
+  if (ep->out_dtype == B2C_BF16 && plain && ep->drop_p == 0.f) epi = EPI_BF16;
+  else if (ep->out_dtype == B2C_BF16 && ep->act == B2C_ACT_SILU && !ep->resid && ep->alpha == 1.f) epi = EPI_SILU;
+  else if (ep->out_dtype == B2C_F32 && ep->resid && !ep->accumulate && ep->act == B2C_ACT_NONE && !ep->out2) epi = EPI_RESID;
+  else if (ep->out_dtype == B2C_BF16 && ep->act == B2C_ACT_SILU_BWD && !ep->out2 && !ep->bias && ep->alpha == 1.f) epi = EPI_SILU_BWD;
+  else if (ep->out_dtype == B2C_F32 && ep->accumulate && ep->act == B2C_ACT_NONE && !ep->out2 && !ep->bias && ep->drop_p == 0.f) epi = EPI_ACCUM;
+#define B2C_LAUNCH(BN_, AM, BMN, E) return launch_gemm<BN_, AM, BMN, E>(ta, tb, p, st)
+#define B2C_DISPATCH(BN_)                                                                          \
+  if (bn == BN_) {                                                                                 \
+    if (!a_mn && !b_mn) {                                                                          \
+      if (epi == EPI_BF16) B2C_LAUNCH(BN_, false, false, EPI_BF16);                                \
+      if (epi == EPI_SILU) B2C_LAUNCH(BN_, false, false, EPI_SILU);                                \
+      if (epi == EPI_RESID) B2C_LAUNCH(BN_, false, false, EPI_RESID);                              \
+      B2C_LAUNCH(BN_, false, false, EPI_GENERIC);                                                  \
+    }                                                                                              \
+    if (!a_mn && b_mn) {                                                                           \
+      if (epi == EPI_BF16) B2C_LAUNCH(BN_, false, true, EPI_BF16);                                 \
+      if (epi == EPI_SILU_BWD) B2C_LAUNCH(BN_, false, true, EPI_SILU_BWD);                         \
+      B2C_LAUNCH(BN_, false, true, EPI_GENERIC);                                                   \
+    }                                                                                              \
+    if (a_mn && b_mn) {                                                                            \
+      if (epi == EPI_ACCUM) B2C_LAUNCH(BN_, true, true, EPI_ACCUM);                                \
+      B2C_LAUNCH(BN_, true, true, EPI_GENERIC);                                                    \
+    }                                                                                              \
+    B2C_LAUNCH(BN_, true, false, EPI_GENERIC);                                                     \
   }
   B2C_DISPATCH(64)
   B2C_DISPATCH(128)
   B2C_DISPATCH(256)
+#undef B2C_LAUNCH
 #undef B2C_DISPATCH
   return -1;
 }
