@@ -63,14 +63,17 @@ __device__ __forceinline__ void stage_taps(const float* __restrict__ wdw, float*
 
 // MODE 0: eval  -> out = SiLU(BN_running(y))            (bn_scale/bn_shift folded per channel)
 // MODE 1: train -> y (bf16) + per-channel sum / sumsq   (stats fp64 [2][d], atomics once per CTA per channel)
-template <int MODE>
+// KT = compile-time tap count (31, 33) or 0 = run-time k: with KT known the window loop has no branches and no dead taps
+template <int MODE, int KT>
 __global__ void __launch_bounds__(256) convmod_fwd_kernel(const __nv_bfloat16* __restrict__ u,
                                                           const float* __restrict__ wdw, const float* __restrict__ bdw,
                                                           const float* __restrict__ bn_w, const float* __restrict__ bn_b,
                                                           const float* __restrict__ bn_mean,
                                                           const float* __restrict__ bn_var, float eps,
                                                           __nv_bfloat16* __restrict__ out, double* __restrict__ stats,
-                                                          int T, int d, int k) {
+                                                          int T, int d, int k_rt) {
+  const int k = KT ? KT : k_rt;
+  constexpr int NTAP = KT ? KT : CM_MAXK;
   extern __shared__ float2 sG[];                 // [(CM_TT + k - 1)][32] float2, then taps [k][64] float
   __shared__ float red[2][8][CM_CH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -84,9 +87,9 @@ __global__ void __launch_bounds__(256) convmod_fwd_kernel(const __nv_bfloat16* _
   stage_glu(u, sG, b, T, d, c0, t0 - half, CM_TT + k - 1);
   __syncthreads();
 
-  float w0[CM_MAXK], w1[CM_MAXK];
+  float w0[NTAP], w1[NTAP];
 #pragma unroll
-  for (int j = 0; j < CM_MAXK; ++j) {
+  for (int j = 0; j < NTAP; ++j) {
     const float2 wv = j < k ? *reinterpret_cast<const float2*>(sWt + j * CM_CH + lane * 2) : make_float2(0.f, 0.f);
     w0[j] = wv.x; w1[j] = wv.y;
   }
@@ -108,13 +111,13 @@ __global__ void __launch_bounds__(256) convmod_fwd_kernel(const __nv_bfloat16* _
     for (int i = 0; i < CM_G; ++i) { a0[i] = bias0; a1[i] = bias1; }
     // window rows tl .. tl + CM_G + k - 2 ; output i uses rows tl+i .. tl+i+k-1 with taps 0..k-1
 #pragma unroll
-    for (int r = 0; r < CM_G + CM_MAXK - 1; ++r) {
-      if (r < CM_G + k - 1) {
+    for (int r = 0; r < CM_G + NTAP - 1; ++r) {
+      if (KT || r < CM_G + k - 1) {
         const float2 g = sG[(tl + r) * 32 + lane];
 #pragma unroll
         for (int i = 0; i < CM_G; ++i) {
           const int j = r - i;
-          if (j >= 0 && j < CM_MAXK) { a0[i] = fmaf(g.x, w0[j], a0[i]); a1[i] = fmaf(g.y, w1[j], a1[i]); }
+          if (j >= 0 && j < NTAP) { a0[i] = fmaf(g.x, w0[j], a0[i]); a1[i] = fmaf(g.y, w1[j], a1[i]); }
         }
       }
     }
@@ -397,8 +400,12 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
 static int convmod_fwd_attr() {
   static bool configured = false;
   if (!configured) {
-    B2C_CUDA(cudaFuncSetAttribute(convmod_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    B2C_CUDA(cudaFuncSetAttribute(convmod_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_fwd_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_fwd_kernel<0, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_fwd_kernel<1, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_fwd_kernel<0, 33>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_fwd_kernel<1, 33>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     configured = true;
   }
   return 0;
@@ -423,9 +430,12 @@ extern "C" int b2c_convmod_eval_fwd(const void* u, const float* wdw, const float
   dim3 grid((T + CM_TT - 1) / CM_TT, (d + CM_CH - 1) / CM_CH, B);
   const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) + CM_CH * k * sizeof(float);
   if (int rc = convmod_fwd_attr()) return rc;
-  convmod_fwd_kernel<0><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(u), wdw, bdw, bn_w, bn_b, bn_mean, bn_var, eps,
-      static_cast<__nv_bfloat16*>(out), nullptr, T, d, k);
+#define B2C_CM_FWD(KT_)                                                                                          \
+  convmod_fwd_kernel<0, KT_><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(                           \
+      static_cast<const __nv_bfloat16*>(u), wdw, bdw, bn_w, bn_b, bn_mean, bn_var, eps, static_cast<__nv_bfloat16*>(out), \
+      nullptr, T, d, k)
+  if (k == 31) B2C_CM_FWD(31); else if (k == 33) B2C_CM_FWD(33); else B2C_CM_FWD(0);
+#undef B2C_CM_FWD
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -437,9 +447,12 @@ extern "C" int b2c_convmod_dw_fwd(const void* u, const float* wdw, const float* 
   dim3 grid((T + CM_TT - 1) / CM_TT, (d + CM_CH - 1) / CM_CH, B);
   const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) + CM_CH * k * sizeof(float);
   if (int rc = convmod_fwd_attr()) return rc;
-  convmod_fwd_kernel<1><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(u), wdw, bdw, nullptr, nullptr, nullptr, nullptr, 0.f,
-      static_cast<__nv_bfloat16*>(y), stats, T, d, k);
+#define B2C_CM_FWD(KT_)                                                                                          \
+  convmod_fwd_kernel<1, KT_><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(                           \
+      static_cast<const __nv_bfloat16*>(u), wdw, bdw, nullptr, nullptr, nullptr, nullptr, 0.f,                   \
+      static_cast<__nv_bfloat16*>(y), stats, T, d, k)
+  if (k == 31) B2C_CM_FWD(31); else if (k == 33) B2C_CM_FWD(33); else B2C_CM_FWD(0);
+#undef B2C_CM_FWD
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

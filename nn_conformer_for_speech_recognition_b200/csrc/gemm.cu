@@ -57,13 +57,7 @@ struct GemmCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// sigmoid via one MUFU.TANH: 0.5*tanh(0.5 z) + 0.5 (abs error ~1e-3 of an output that is rounded to bf16 anyway)
-__device__ __forceinline__ float sigmoid_fast(float z) { return fmaf(0.5f, tanh_approx(0.5f * z), 0.5f); }
+__device__ __forceinline__ float sigmoid_fast(float z) { return sigmoid_f(z); }
 
 // Epilogue specialisations (compile-time, so the per-element code stays a few dozen instructions and fits the
 // instruction cache -- the fully generic runtime-switched version was I-cache bound: ncu stall_no_inst dominated).
@@ -221,13 +215,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if ((G || EPI != EPI_ACCUM) && bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
         const float* rp = static_cast<const float*>(ep.resid) + row0 * ep.ld_out + col;
         const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(ep.aux) + row0 * ep.ld_aux + col;
-        if (col_ok && (want_resid || want_aux)) {
+        if (want_resid || want_aux) {
+          // lines of THIS chunk on the CTA's first tile, lines of the NEXT tile's chunk otherwise (one tile ~ a few
+          // microseconds ahead: enough to cover a DRAM round trip; 126 MB of L2 keeps them until they are used)
+          const int ptile = it == 0 ? tile : tile + static_cast<int>(gridDim.x);
+          for (int pt = ptile; pt <= tile + static_cast<int>(gridDim.x) && pt < p.total_tiles; pt += gridDim.x) {
+            const int pn = pt % p.n_tiles, pm = (pt / p.n_tiles) % p.m_tiles;
+            const int64_t pcol = static_cast<int64_t>(pn) * BN + col_t + c_lane * 4;
+            const int64_t prow0 = static_cast<int64_t>(pm) * BM + q * 32 + r_lane;
+            if (pcol < p.N) {
 #pragma unroll 4
-          for (int i = 0; i < NIT; ++i) {
-            if (i * RPI >= rows_left) break;
-            const void* ptr = want_resid ? static_cast<const void*>(rp + static_cast<int64_t>(i) * RPI * ep.ld_out)
-                                         : static_cast<const void*>(ap + static_cast<int64_t>(i) * RPI * ep.ld_aux);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+              for (int i = 0; i < NIT; ++i) {
+                const int64_t prow = prow0 + i * RPI;
+                if (prow >= p.M) break;
+                const void* ptr = want_resid ? static_cast<const void*>(static_cast<const float*>(ep.resid) + prow * ep.ld_out + pcol)
+                                             : static_cast<const void*>(static_cast<const __nv_bfloat16*>(ep.aux) + prow * ep.ld_aux + pcol);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+              }
+            }
           }
         }
         if (ch == 0) {
