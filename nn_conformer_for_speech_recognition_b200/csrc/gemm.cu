@@ -13,17 +13,18 @@
 // torchaudio/models/conformer.py:44-51,66-73,102-109 and the in/out projections of nn.MultiheadAttention
 // (torch/nn/functional.py:5798,6690), with the bias / SiLU / 0.5*residual / dropout elementwise kernels fused as epilogue.
 //
-// Structure: PERSISTENT kernel, one CTA per SM, 320 threads, static round-robin over 128 x BN output tiles
+// Structure: PERSISTENT kernel, one CTA per SM, 576 threads, static round-robin over 128 x BN output tiles
 // (n fastest, so CTAs running side by side share the same A rows in L2):
 //   warp 0     TMA producer (one elected lane) -> 128B-swizzled smem ring (mbarrier full/empty), runs ahead across tiles
 //   warp 1     TMEM allocator + MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16,
 //              accumulators DOUBLE-BUFFERED in TMEM (2 x BN columns): tile i+1's main loop overlaps tile i's epilogue
-//   warps 2-9  epilogue (8 warps; warp w owns TMEM lanes 32*(w%4).. and one half of the BN columns):
+//   warps 2-17 epilogue (16 warps; warp w owns TMEM lanes 32*(w%4).. and one quarter of the BN columns):
 //              tcgen05.ld (thread = row) -> release the TMEM buffer -> XOR-swizzled smem transpose (per warp, no CTA
 //              barrier) -> coalesced domain (lanes along columns): bias / SiLU / SiLU' / dropout / residual and
 //              128-byte coalesced global loads & stores (or red.global.add.v4.f32 for split-K / gradient accumulation)
 // The problems here are skinny (K = 144..2304) so a tile's main loop is only 3-16 k-blocks: the epilogue, not the MMA,
-// is the critical resource -- hence 8 epilogue warps, MUFU.TANH-based SiLU and the overlap through TMEM.
+// is the critical resource -- hence 16 epilogue warps (4 per scheduler: the per-element math is latency bound with
+// fewer), MUFU.TANH-based SiLU, compile-time epilogue variants and the overlap through TMEM.
 #include "common.cuh"
 #include "b200conformer.h"
 
@@ -31,8 +32,8 @@ namespace b2c {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 320;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;                 // 4 per TMEM lane quarter, each owning BN/4 columns of the tile
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 
 struct GemmParams {
   DropCfg drop;
@@ -48,8 +49,9 @@ struct GemmCfg {
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int CW = (BN / 2 < 64) ? BN / 2 : 64;                 // columns per epilogue chunk
-  static constexpr int CHUNKS = (BN / 2) / CW;                           // chunks per epilogue warp per tile
+  static constexpr int SPAN = BN / (EPI_WARPS / 4);                      // columns owned by one epilogue warp
+  static constexpr int CW = SPAN < 32 ? SPAN : 32;                       // columns per epilogue chunk (one tcgen05.ld)
+  static constexpr int CHUNKS = SPAN / CW;                               // chunks per epilogue warp per tile
   static constexpr uint32_t STG_WARP_BYTES = 32 * CW * 4;                // fp32 transpose buffer per warp
   static constexpr uint32_t STG_OFF = STAGES * STAGE_BYTES;
   static constexpr uint32_t BAR_OFF = STG_OFF + EPI_WARPS * STG_WARP_BYTES;
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;     // [2] accumulator ready
-  uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained (8 epilogue warps arrive)
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained (every epilogue warp arrives)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     constexpr int NIT = 32 / RPI;                      // iterations to cover the warp's 32 rows
     const int ew = warp - 2;
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                          // which half of the BN columns
+    const int part = ew >> 2;                          // which slice of the BN columns
     float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF + ew * Cfg::STG_WARP_BYTES);
     const int c_lane = lane % LPR;                     // float4 chunk (column group) this lane owns after the transpose
     const int r_lane = lane / LPR;
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const bool do_alpha = (G || EPI == EPI_RESID || EPI == EPI_ACCUM) && ep.alpha != 1.f;
 #pragma unroll 1
       for (int ch = 0; ch < Cfg::CHUNKS; ++ch) {
-        const int col_t = half * (BN / 2) + ch * CW;   // first column of this chunk inside the tile
+        const int col_t = part * Cfg::SPAN + ch * CW;  // first column of this chunk inside the tile
         const int64_t col = static_cast<int64_t>(n_blk) * BN + col_t + c_lane * 4;
         const bool col_ok = col < p.N;
         const int64_t row0 = static_cast<int64_t>(m_blk) * BM + q * 32 + r_lane;
@@ -242,8 +244,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         uint32_t v[CW];
         __syncwarp();
         const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16) + col_t;
-        tmem_ld32(taddr, v);
-        if constexpr (CW == 64) tmem_ld32(taddr + 32, v + 32);
+        if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         tmem_wait_ld();
         if (ch == Cfg::CHUNKS - 1) {                   // all of this warp's TMEM reads for the tile are done
           tc_fence_before();

@@ -126,14 +126,17 @@ __global__ void __launch_bounds__(AF_THREADS) adafactor_update_kernel(const AfTe
     scale = lr / fmaxf(1.f, rms / clip);
   }
   float ss = 0.f;
-  for (int64_t i = threadIdx.x; i < cnt; i += AF_THREADS) {
+  // (row, col) of this thread's element advance incrementally: no per-element 64-bit division
+  const int icnt = static_cast<int>(cnt);
+  const int step_r = AF_THREADS / C, step_c = AF_THREADS % C;
+  int rr = static_cast<int>(threadIdx.x) / C, c = static_cast<int>(threadIdx.x) % C;
+  for (int i = threadIdx.x; i < icnt; i += AF_THREADS) {
     const int64_t e = e0 + i;
     const float gv = T.g[e];
     float u;
     if (T.factored) {
-      const int row = ck.row0 + static_cast<int>(i / C);
-      const int c = static_cast<int>(i % C);
-      const int pslab = row / R;
+      const int row = ck.row0 + rr;
+      const int pslab = R == 1 ? row : row / R;
       u = gv * rsqrtf(T.row[row] / T.rmean[pslab]) * rsqrtf(T.col[static_cast<int64_t>(pslab) * C + c]);
     } else {
       float v = T.row[e];
@@ -150,6 +153,8 @@ __global__ void __launch_bounds__(AF_THREADS) adafactor_update_kernel(const AfTe
     } else {
       ss += u * u;
     }
+    rr += step_r; c += step_c;
+    if (c >= C) { c -= C; ++rr; }
   }
   if (!APPLY) {
     __shared__ float red[AF_THREADS / 32];

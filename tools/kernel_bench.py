@@ -105,6 +105,15 @@ def main():
     tok = ops.convsub_fwd(xin, Wc, bc, 11, 4)
     dWc = torch.zeros(128, 128, device=dev)
     rec("convsub wgrad", timeit(lambda: ops.convsub_wgrad(xin, tok.view(M, 18 * 128), dWc, 11, 4), 5), 2 * 121 * 128 * 18 * 373 * B, 0)
+    from nn_conformer_for_speech_recognition_b200.optim import Adafactor
+    import nn_conformer_for_speech_recognition_b200 as b2c
+    model = b2c.Conformer(256, 4, 1024, 16, 31).to(dev)
+    params = list(model.parameters())
+    nparam = sum(p.numel() for p in params)
+    for p_ in params:
+        p_.grad = torch.randn_like(p_) * 0.01
+    opt = Adafactor(params, lr=2e-5, beta1=0.9)
+    rec(f"fused Adafactor step ({nparam/1e6:.1f} M params)", timeit(lambda: opt.step(), 5), 0, nparam * 28)
     if "--json" in sys.argv:
         json.dump(res, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
 
