@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     constexpr int LPR = CW / 4;                        // lanes per row in the coalesced domain (float4 each)
     constexpr int RPI = 32 / LPR;                      // rows per warp instruction
     constexpr int NIT = 32 / RPI;                      // iterations to cover the warp's 32 rows
+    constexpr int SWZ = LPR < 8 ? LPR - 1 : 7;         // XOR swizzle mask of the transpose buffer (chunks per row - 1, max 7)
     const int ew = warp - 2;
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     const int part = ew >> 2;                          // which slice of the BN columns
@@ -251,10 +252,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
-        // transpose through smem: row = lane, 16-byte chunk c stored at (c ^ (lane & 7))
+        // transpose through smem: row = lane, 16-byte chunk c stored at (c ^ (lane & SWZ))
 #pragma unroll
         for (int c = 0; c < LPR; ++c)
-          *reinterpret_cast<uint4*>(stg + lane * CW + ((c ^ (lane & 7)) << 2)) =
+          *reinterpret_cast<uint4*>(stg + lane * CW + ((c ^ (lane & SWZ)) << 2)) =
               make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         __syncwarp();
         if (col_ok) {
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           for (int i = 0; i < NIT; ++i) {
             if (i * RPI >= rows_left) break;
             const int r = i * RPI + r_lane;
-            const float4 a4 = *reinterpret_cast<const float4*>(stg + r * CW + ((c_lane ^ (r & 7)) << 2));
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + r * CW + ((c_lane ^ (r & SWZ)) << 2));
             float f[4] = {a4.x + bv.x, a4.y + bv.y, a4.z + bv.z, a4.w + bv.w};
             if (do_out2)                               // pre-activation copy (saved for the backward pass)
               *reinterpret_cast<uint2*>(o2 + static_cast<int64_t>(i) * RPI * ep.ld_out2) =
