@@ -28,6 +28,10 @@ enum { B2C_ACT_NONE = 0, B2C_ACT_SILU = 1, B2C_ACT_SILU_BWD = 2 };
 
 const char* b2c_last_error(void);
 int b2c_version(void);
+/* Dropout masks are a pure function of (seed, element index, epoch).  The epoch is a device-side counter this call
+ * increments (one tiny launch): call it once at the start of every training step -- forward and backward of the step
+ * then regenerate identical masks, and a replayed CUDA graph still draws fresh masks each step. */
+int b2c_dropout_epoch_bump(void* stream);
 /* fails (returns <0) unless the current CUDA device is compute capability 10.x -- there is no fallback path */
 int b2c_device_check(void);
 
@@ -168,10 +172,11 @@ int64_t b2c_mt19937_randint_host(uint32_t* state_host, int64_t a, int64_t b);
  *   { float* p; const float* g; float* exp_avg; float* row_or_sq; float* col; float* rowsum_ws; float* colsum_ws;
  *     float* rmean_ws; float* sumsq_ws; int32 P, R, C, factored; int64 n }      (tensor viewed as [P][R][C])
  * chunks_dev: device array of { int32 tensor, row0, nrows, pad } covering every flattened row once.  The workspace
- * fields must be zero on entry.  step >= 1 is the update count (beta2_t = 1 - step^decay_rate).
+ * fields must be zero on entry.  step_dev (int64, starts at 0) is incremented on the device and beta2t_dev receives
+ * 1 - step^decay_rate, so a captured CUDA graph advances the schedule on every replay.  Five launches.
  * ------------------------------------------------------------------------------------------------------- */
-int b2c_adafactor_step(const void* tensors_dev, int n_tensors, const void* chunks_dev, int n_chunks, int64_t step,
-                       float lr, float beta1, float eps1, float clip, float decay_rate, void* stream);
+int b2c_adafactor_step(const void* tensors_dev, int n_tensors, const void* chunks_dev, int n_chunks, int64_t* step_dev,
+                       float* beta2t_dev, float lr, float beta1, float eps1, float clip, float decay_rate, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Small memory-bound helpers

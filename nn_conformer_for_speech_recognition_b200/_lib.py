@@ -49,7 +49,8 @@ SIGNATURES = {
     "b2c_convsub_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "b2c_convsub_compose_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "b2c_specaug_apply": [_P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _F, _I, _I, _I, _P],
-    "b2c_adafactor_step": [_P, _I, _P, _I, _L, _F, _F, _F, _F, _F, _P],
+    "b2c_adafactor_step": [_P, _I, _P, _I, _P, _P, _F, _F, _F, _F, _F, _P],
+    "b2c_dropout_epoch_bump": [_P],
     "b2c_cast_f32_bf16": [_P, _P, _L, _P],
     "b2c_multi_cast_f32_bf16": [_P, _I, _L, _P],
     "b2c_scale_cast": [_P, _P, _L, _L, _F, _F, c_uint64, _P],
@@ -64,7 +65,7 @@ HOST_SIGNATURES = {
 
 _lib = None
 LAUNCHES = 0          # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 2, "b2c_convsub_compose_bwd": 2, "b2c_attention_bwd": 4, "b2c_adafactor_step": 4, "b2c_version": 0, "b2c_device_check": 0}
+_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 2, "b2c_convsub_compose_bwd": 2, "b2c_attention_bwd": 4, "b2c_adafactor_step": 5, "b2c_version": 0, "b2c_device_check": 0}
 
 
 def load() -> ctypes.CDLL:

@@ -14,7 +14,7 @@ from typing import List
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .conformer import _LAYER_PARAMS, HEAD_PAD, Conformer, _get, run_layers
 
 
@@ -23,6 +23,8 @@ def conformer_apply(model: Conformer, inp: torch.Tensor, lengths_i32: torch.Tens
     params = [_get(layer, n) for layer in model.conformer_layers for n in _LAYER_PARAMS]
     need_grad = torch.is_grad_enabled() and (inp.requires_grad or any(p.requires_grad for p in params))
     drop_p = model.dropout_p if model.training else 0.0
+    if drop_p > 0.0:            # one device-side tick per training forward: fresh masks even when a CUDA graph replays
+        _lib.call("b2c_dropout_epoch_bump", _lib.stream_ptr())
     if not need_grad:
         x = inp.detach().reshape(B * T, d).to(torch.float32).clone(memory_format=torch.contiguous_format)
         y = run_layers(model, x, lengths_i32, B, T, None, model.training, drop_p, model.next_seed())

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 #pragma unroll
   for (int i = 0; i < AT_DH; ++i) o[i] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
+  const DropCfg drop = drop_resolve(p.drop);
   const int q_idx = q0 + tid;                           // query position inside the utterance
   const uint64_t drop_row = (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad;
 
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float s0, s1;
-          drop_scale2(p.drop, drop_row + key0 + c + i, s0, s1);
+          drop_scale2(drop, drop_row + key0 + c + i, s0, s1);
           pr[i] *= s0; pr[i + 1] *= s1;
         }
       }
@@ -259,6 +260,7 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
                                                    uint8_t* sdS, int row, int chalf, int q_idx, int key0, int len,
                                                    float lse_r, float delta_r, uint64_t drop_row) {
   const bool q_ok = q_idx < p.T;
+  const DropCfg drop = drop_resolve(p.drop);
 #pragma unroll 1
   for (int cc = 0; cc < 64; cc += 32) {
     const int c = chalf * 64 + cc;
@@ -271,7 +273,7 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       float dsc[2] = {1.f, 1.f};
-      if (p.drop.thresh16) drop_scale2(p.drop, drop_row + key0 + c + i, dsc[0], dsc[1]);
+      if (drop.thresh16) drop_scale2(drop, drop_row + key0 + c + i, dsc[0], dsc[1]);
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const bool ok = q_ok && (key0 + c + i + e < len);

@@ -77,10 +77,13 @@ __host__ __device__ __forceinline__ uint32_t drop_hash32(uint64_t seed, uint64_t
   return x;
 }
 struct DropCfg {
-  uint64_t seed;       // well-mixed 64-bit key (host side runs the user seed through splitmix64)
-  uint32_t thresh16;   // 0 = dropout off
+  uint64_t seed;             // well-mixed 64-bit key (host side runs the user seed through splitmix64)
+  const uint64_t* epoch;     // device counter bumped once per training step (b2c_dropout_epoch_bump): lets a CUDA graph
+                             // replay the same launches with fresh masks; forward and backward of a step see one value
+  uint32_t thresh16;         // 0 = dropout off
   float inv_keep;
 };
+const uint64_t* dropout_epoch_ptr();       // host.cpp: lazily allocated per-process device word
 __host__ __device__ __forceinline__ uint64_t drop_mix_seed(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -90,9 +93,15 @@ __host__ __device__ __forceinline__ uint64_t drop_mix_seed(uint64_t z) {
 inline DropCfg make_drop(float p, uint64_t seed) {
   DropCfg d;
   d.seed = drop_mix_seed(seed);
+  d.epoch = p > 0.f ? dropout_epoch_ptr() : nullptr;
   d.thresh16 = p > 0.f ? static_cast<uint32_t>(p * 65536.0 + 0.5) : 0u;
   if (d.thresh16 > 65535u) d.thresh16 = 65535u;
   d.inv_keep = p > 0.f ? 65536.f / static_cast<float>(65536u - d.thresh16) : 1.f;
+  return d;
+}
+// fold the step epoch into the key (call once per thread, before the first drop_scale2)
+__device__ __forceinline__ DropCfg drop_resolve(DropCfg d) {
+  if (d.thresh16 && d.epoch) d.seed += (*d.epoch) * 0x9E3779B97F4A7C15ull;
   return d;
 }
 // scales for elements idx (even) and idx+1

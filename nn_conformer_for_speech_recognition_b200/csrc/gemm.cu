@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   } else {
     // ================================ epilogue (8 warps) ================================
     const b2c_epilogue& ep = p.ep;
+    const DropCfg drop = drop_resolve(p.drop);
     constexpr int CW = Cfg::CW;
     constexpr int LPR = CW / 4;                        // lanes per row in the coalesced domain (float4 each)
     constexpr int RPI = 32 / LPR;                      // rows per warp instruction
@@ -288,8 +289,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             if (do_drop) {
               float s0, s1, s2, s3;
               const uint64_t di = drop_base + static_cast<uint64_t>(i) * RPI * p.N;   // N % 8 == 0, col % 4 == 0: even
-              drop_scale2(p.drop, di, s0, s1);
-              drop_scale2(p.drop, di + 2, s2, s3);
+              drop_scale2(drop, di, s0, s1);
+              drop_scale2(drop, di + 2, s2, s3);
               f[0] *= s0; f[1] *= s1; f[2] *= s2; f[3] *= s3;
             }
             if (do_alpha) {

@@ -98,6 +98,18 @@ int get_tensor_map_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64
   return 0;
 }
 
+static uint64_t* g_epoch = nullptr;
+const uint64_t* dropout_epoch_ptr() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    if (cudaMalloc(&g_epoch, sizeof(uint64_t)) == cudaSuccess) cudaMemset(g_epoch, 0, sizeof(uint64_t));
+    else g_epoch = nullptr;
+  });
+  return g_epoch;
+}
+
+__global__ void epoch_bump_kernel(uint64_t* e) { *e += 1; }
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -113,6 +125,14 @@ int num_sms() {
 extern "C" const char* b2c_last_error(void) { return b2c::g_err; }
 
 extern "C" int b2c_version(void) { return B2C_VERSION; }
+
+extern "C" int b2c_dropout_epoch_bump(void* stream) {
+  uint64_t* e = const_cast<uint64_t*>(b2c::dropout_epoch_ptr());
+  B2C_REQUIRE(e != nullptr, "b2c_dropout_epoch_bump: could not allocate the epoch word");
+  b2c::epoch_bump_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(e);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int b2c_device_check(void) {
   int dev = 0;

@@ -197,6 +197,7 @@ __global__ void scale_cast_kernel(const float* __restrict__ src, __nv_bfloat16* 
   float4 a = *reinterpret_cast<const float4*>(src + i);
   float f[4] = {a.x * alpha, a.y * alpha, a.z * alpha, a.w * alpha};
   if (drop.thresh16) {
+    drop = drop_resolve(drop);
     float s0, s1, s2, s3;
     drop_scale2(drop, static_cast<uint64_t>(i), s0, s1);
     drop_scale2(drop, static_cast<uint64_t>(i) + 2, s2, s3);

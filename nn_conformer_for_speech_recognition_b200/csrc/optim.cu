@@ -90,9 +90,17 @@ __global__ void __launch_bounds__(AF_THREADS) adafactor_stats_kernel(const AfTen
   }
 }
 
+// step counter and beta2_t live on the device so a captured CUDA graph advances them on every replay
+__global__ void adafactor_tick_kernel(int64_t* __restrict__ step, float* __restrict__ beta2t, float decay_rate) {
+  const int64_t s = *step + 1;
+  *step = s;
+  *beta2t = 1.f - powf(static_cast<float>(s), decay_rate);          // HF: 1 - step^decay_rate
+}
+
 // one block per (tensor, slab-range): updates the factored second moments and the per-slab mean of the row factor
 __global__ void __launch_bounds__(AF_THREADS) adafactor_factors_kernel(const AfTensor* __restrict__ tensors, int n_tensors,
-                                                                      float beta2t) {
+                                                                      const float* __restrict__ beta2t_ptr) {
+  const float beta2t = *beta2t_ptr;
   const AfTensor T = tensors[blockIdx.x];
   if (!T.factored) return;
   const int C = T.C, R = T.R, P = T.P;
@@ -113,8 +121,10 @@ __global__ void __launch_bounds__(AF_THREADS) adafactor_factors_kernel(const AfT
 
 template <bool APPLY>
 __global__ void __launch_bounds__(AF_THREADS) adafactor_update_kernel(const AfTensor* __restrict__ tensors,
-                                                                     const AfChunk* __restrict__ chunks, float beta2t,
-                                                                     float eps1, float lr, float beta1, float clip) {
+                                                                     const AfChunk* __restrict__ chunks,
+                                                                     const float* __restrict__ beta2t_ptr, float eps1,
+                                                                     float lr, float beta1, float clip) {
+  const float beta2t = *beta2t_ptr;
   const AfChunk ck = chunks[blockIdx.x];
   const AfTensor T = tensors[ck.t];
   const int C = T.C, R = T.R;
@@ -175,19 +185,20 @@ __global__ void __launch_bounds__(AF_THREADS) adafactor_update_kernel(const AfTe
 using namespace b2c;
 
 extern "C" int b2c_adafactor_step(const void* tensors_dev, int n_tensors, const void* chunks_dev, int n_chunks,
-                                  int64_t step, float lr, float beta1, float eps1, float clip, float decay_rate,
-                                  void* stream) {
-  B2C_REQUIRE(tensors_dev && chunks_dev && n_tensors > 0 && n_chunks > 0 && step >= 1, "b2c_adafactor_step: bad argument");
+                                  int64_t* step_dev, float* beta2t_dev, float lr, float beta1, float eps1, float clip,
+                                  float decay_rate, void* stream) {
+  B2C_REQUIRE(tensors_dev && chunks_dev && step_dev && beta2t_dev && n_tensors > 0 && n_chunks > 0,
+              "b2c_adafactor_step: bad argument");
   static_assert(sizeof(AfTensor) == 96, "AfTensor layout is part of the ABI (python builds the table)");
   static_assert(sizeof(AfChunk) == 16, "AfChunk layout is part of the ABI");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const float beta2t = 1.f - powf(static_cast<float>(step), decay_rate);        // HF: 1 - step^decay_rate
   const AfTensor* T = static_cast<const AfTensor*>(tensors_dev);
   const AfChunk* Cc = static_cast<const AfChunk*>(chunks_dev);
+  adafactor_tick_kernel<<<1, 1, 0, st>>>(step_dev, beta2t_dev, decay_rate);
   adafactor_stats_kernel<<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, eps1);
-  adafactor_factors_kernel<<<n_tensors, AF_THREADS, 0, st>>>(T, n_tensors, beta2t);
-  adafactor_update_kernel<false><<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, beta2t, eps1, lr, beta1, clip);
-  adafactor_update_kernel<true><<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, beta2t, eps1, lr, beta1, clip);
+  adafactor_factors_kernel<<<n_tensors, AF_THREADS, 0, st>>>(T, n_tensors, beta2t_dev);
+  adafactor_update_kernel<false><<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, beta2t_dev, eps1, lr, beta1, clip);
+  adafactor_update_kernel<true><<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, beta2t_dev, eps1, lr, beta1, clip);
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

@@ -83,9 +83,12 @@ class ConformerEncoder(nn.Module):
         return self._bridge_bf16
 
     def forward(self, x: torch.Tensor, input_lens: torch.Tensor, SpecAugment: bool = False,
-                lens_host: Optional[list] = None):
-        """x (B,1,F,T) fp32 log-mel on the GPU, input_lens (B,) frames.  Returns (encoded (B,T',d) fp32, lengths (B,))."""
-        if SpecAugment:
+                lens_host: Optional[list] = None, specaug_plan: "Optional[specaugment.SpecAugPlan]" = None):
+        """x (B,1,F,T) fp32 log-mel on the GPU, input_lens (B,) frames.  Returns (encoded (B,T',d) fp32, lengths (B,)).
+        `specaug_plan`: pre-drawn parameters (SpecAugPlan.draw was called on the host) -- the CUDA-graph friendly form."""
+        if SpecAugment and specaug_plan is not None:
+            x = specaug_plan.apply(x)
+        elif SpecAugment:
             x = specaugment.SpecAugment(self, x, lens_host if lens_host is not None else input_lens)
         tok = self.conv_sub_sampling.forward_tokens(x)                  # (B, T', F', C) bf16
         B, To, Fo, C = tok.shape

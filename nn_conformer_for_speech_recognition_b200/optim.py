@@ -34,7 +34,9 @@ class Adafactor:
             if p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous():
                 raise ValueError("fused Adafactor needs contiguous fp32 CUDA parameters (no fallback)")
         self.lr, self.beta1, self.eps1, self.clip, self.decay_rate = lr, beta1, eps[0], clip_threshold, decay_rate
-        self.step_count = 0
+        self.step_count = 0                               # host mirror; the authoritative counter lives on the device
+        self._step_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+        self._beta2t_dev = torch.zeros(1, device=dev, dtype=torch.float32)
         geo = []
         for p in self.params:
             if p.dim() >= 2:
@@ -111,5 +113,7 @@ class Adafactor:
         self.step_count += 1
         self.ws.zero_()
         _lib.call("b2c_adafactor_step", self._tab_dev.data_ptr(), len(self.params), self._chunks_dev.data_ptr(),
-                  self.n_chunks, self.step_count, self.lr, self.beta1, self.eps1, self.clip, self.decay_rate,
-                  _lib.stream_ptr())
+                  self.n_chunks, self._step_dev.data_ptr(), self._beta2t_dev.data_ptr(), self.lr, self.beta1, self.eps1,
+                  self.clip, self.decay_rate, _lib.stream_ptr())
+        # the kernels wrote the parameters through raw pointers: tell autograd / the bf16 weight caches they changed
+        torch.autograd.graph.increment_version(self.params)

@@ -119,3 +119,60 @@ def SpecAugment(self, x, tau):
     tmasks = [_draw_tmask(hp, B, tau) for _ in range(Mt)]                                   # asrnn.py:190-191
     out = _launch(x, tau, warps, fmasks, tmasks, _mode(self) == "paper", hp.mask_value)
     return out.unsqueeze(1)
+
+
+class SpecAugPlan:
+    """Pre-drawn SpecAugment for a CUDA-graph-captured step.
+
+    `draw(...)` runs on the host BEFORE the replay (same draws, same order, same global `random` stream as
+    `SpecAugment`) and writes the parameters into a pinned buffer; `apply(x)` only enqueues a pinned->device copy and the
+    kernel, so it can be captured once and replayed with new parameters every step.
+    """
+
+    def __init__(self, hp, B: int, device, mode: str = "reference"):
+        self.hp, self.B, self.mode = hp, B, mode
+        Mt = hp.time_multiplicity
+        if hp.adaptive_multiplicity:
+            Mt = min(Mt, floor(hp.pm))
+        self.n_warp, self.n_f, self.n_t = hp.warping_ntimes, hp.frequency_mask_ntimes, Mt
+        n = B + 2 * self.n_warp * B + 2 * self.n_f + 2 * self.n_t * B
+        self.host = torch.zeros(max(n, 1), dtype=torch.int32).pin_memory()
+        self.dev = torch.zeros(max(n, 1), dtype=torch.int32, device=device)
+        o = 0
+        self.sl = {}
+        for name, cnt in (("tau", B), ("w", self.n_warp * B), ("w0", self.n_warp * B), ("fm", 2 * self.n_f),
+                          ("tm", 2 * self.n_t * B)):
+            self.sl[name] = (o, o + cnt)
+            o += cnt
+
+    def draw(self, F: int, tau):
+        hp, B = self.hp, self.B
+        tau = _tau_list(tau)
+        warps = [_draw_warp(hp, B, tau) for _ in range(self.n_warp)]
+        fmasks = [_draw_fmask(hp, F) for _ in range(self.n_f)]
+        tmasks = [_draw_tmask(hp, B, tau) for _ in range(self.n_t)]
+        h = self.host
+
+        def put(name, values):
+            a, b = self.sl[name]
+            if b > a:
+                h[a:b] = torch.tensor(values, dtype=torch.int32).reshape(-1)
+        put("tau", tau)
+        put("w", [w[0] for w in warps])
+        put("w0", [w[1] for w in warps])
+        put("fm", fmasks)
+        put("tm", tmasks)
+
+    def apply(self, x4: torch.Tensor) -> torch.Tensor:
+        """x4 (B,1,F,T) fp32 on the GPU -> (B,1,F,T); capturable."""
+        x = x4[:, 0] if x4.dim() == 4 else x4
+        self.dev.copy_(self.host, non_blocking=True)
+        d = self.dev
+
+        def view(name, shape):
+            a, b = self.sl[name]
+            return d[a:b].view(shape) if b > a else None
+        out = ops.specaug_apply(x.to(torch.float32).contiguous(), view("tau", (self.B,)), view("w", (self.n_warp, self.B)),
+                                view("w0", (self.n_warp, self.B)), view("fm", (self.n_f, 2)), view("tm", (self.n_t, self.B, 2)),
+                                self.mode == "paper", float(self.hp.mask_value))
+        return out.unsqueeze(1)
