@@ -44,7 +44,8 @@ int b2c_device_check(void);
  * a_mn / b_mn: 0 = the operand is [rows][K] with K contiguous; 1 = it is stored [K][rows] (rows contiguous).
  *   forward (0,0) with B = weight (out,in);  dX = dY*W is (0,1) with B = W;  dW = dY^T*X is (1,1).
  * epilogue, in this order:  v = acc (+ bias[n]);  out2 = bf16(v) if out2;  v = act(v);  v *= dropout(seed, m*N+n);
- *                           v *= alpha;  then  out = bf16(v) | out = v + resid (fp32) | atomicAdd(out, v) (fp32).
+ *                           v *= alpha;  then  out = bf16(v) | out = v + resid (fp32) | atomicAdd(out, v) (fp32);
+ *                           colsum[n] += sum_m v  (optional, bf16 outputs).
  * ------------------------------------------------------------------------------------------------------- */
 typedef struct b2c_epilogue {
   const void* bias;   /* fp32 [N] or NULL */
@@ -60,6 +61,7 @@ typedef struct b2c_epilogue {
   int out_dtype;      /* B2C_BF16 | B2C_F32 */
   int accumulate;     /* 1: fp32 atomicAdd into out (split-K / gradient accumulation) */
   int reserved;
+  float* colsum;      /* optional fp32 [N]: += column sums of the values written to `out` (bias gradient of the next op) */
 } b2c_epilogue;
 
 int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M, int64_t N,
@@ -187,9 +189,10 @@ int b2c_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* one launch for a whole parameter set: table_dev = device array of {const float* src; bf16* dst; int64 n} (24 B each,
  * sources/destinations 16-byte aligned); max_n = largest n (sizes the grid) */
 int b2c_multi_cast_f32_bf16(const void* table_dev, int n_tensors, int64_t max_n, void* stream);
-/* dst bf16 [rows, cols] = alpha * dropout(src fp32 [rows, cols]) -- gradient of  x + alpha*drop(y)  wrt y */
+/* dst bf16 [rows, cols] = alpha * dropout(src fp32 [rows, cols]) -- gradient of  x + alpha*drop(y)  wrt y;
+ * colsum (optional fp32 [cols]) += column sums of dst: the bias gradient of the linear layer that produced y */
 int b2c_scale_cast(const float* src, void* dst, int64_t rows, int64_t cols, float alpha, float drop_p,
-                   uint64_t drop_seed, void* stream);
+                   uint64_t drop_seed, float* colsum, void* stream);
 /* out fp32 [cols] += column sums of a bf16 [rows, ld] matrix (bias gradients) */
 int b2c_colsum_bf16(const void* a, int64_t ld, int64_t rows, int64_t cols, float* out, void* stream);
 /* pads / unpads per-head columns:  dst[r, h*dst_dh + c] = src[r, h*src_dh + c] (zero fill), nblk = blocks per row */

@@ -25,7 +25,8 @@ class B2CError(RuntimeError):
 class Epilogue(Structure):
     _fields_ = [("bias", c_void_p), ("aux", c_void_p), ("resid", c_void_p), ("out", c_void_p), ("out2", c_void_p),
                 ("ld_out", c_int64), ("ld_out2", c_int64), ("ld_aux", c_int64), ("alpha", c_float), ("drop_p", c_float),
-                ("drop_seed", c_uint64), ("act", c_int), ("out_dtype", c_int), ("accumulate", c_int), ("reserved", c_int)]
+                ("drop_seed", c_uint64), ("act", c_int), ("out_dtype", c_int), ("accumulate", c_int), ("reserved", c_int),
+                ("colsum", c_void_p)]
 
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
@@ -53,7 +54,7 @@ SIGNATURES = {
     "b2c_dropout_epoch_bump": [_P],
     "b2c_cast_f32_bf16": [_P, _P, _L, _P],
     "b2c_multi_cast_f32_bf16": [_P, _I, _L, _P],
-    "b2c_scale_cast": [_P, _P, _L, _L, _F, _F, c_uint64, _P],
+    "b2c_scale_cast": [_P, _P, _L, _L, _F, _F, c_uint64, _P, _P],
     "b2c_colsum_bf16": [_P, _L, _L, _L, _P, _P],
     "b2c_repack_heads": [_P, _P, _L, _I, _I, _I, _P],
 }

@@ -117,12 +117,11 @@ class _ConformerFn(torch.autograd.Function):
 
             def ffn_bwd(pre, site):
                 s = st[pre]
-                dyb = ops.scale_cast(dx, 0.5, drop_p, sd + site + 1)                       # d(0.5*drop(.))
-                ops.colsum(dyb, G(li, pre + ".sequential.4.bias"))
+                # d(0.5*drop(.)) as bf16, with the bias gradient (column sums) fused into the same pass
+                dyb = ops.scale_cast(dx, 0.5, drop_p, sd + site + 1, colsum=G(li, pre + ".sequential.4.bias"))
                 wgrad(dyb, s["h"], d, f, G(li, pre + ".sequential.4.weight"))
                 du = ops.gemm(dyb, w[pre + ".sequential.4.weight"], M=M, N=f, K=d, b_mn=True, act=ops.ACT_SILU_BWD,
-                              aux=s["u"], drop_p=drop_p, drop_seed=sd + site)
-                ops.colsum(du, G(li, pre + ".sequential.1.bias"))
+                              aux=s["u"], drop_p=drop_p, drop_seed=sd + site, colsum=G(li, pre + ".sequential.1.bias"))
                 wgrad(du, s["a"], f, d, G(li, pre + ".sequential.1.weight"))
                 da = ops.gemm(du, w[pre + ".sequential.1.weight"], M=M, N=d, K=f, b_mn=True)
                 ops.layernorm_bwd(da, s["x"], P(pre + ".sequential.0.weight"), s["mean"], s["rstd"], dx, True,
@@ -134,8 +133,7 @@ class _ConformerFn(torch.autograd.Function):
             # ---- 3. conv module
             s = st["conv"]
             bn = layer.conv_module.sequential[3]
-            dyb = ops.scale_cast(dx, 1.0, drop_p, sd + 8)
-            ops.colsum(dyb, G(li, "conv_module.sequential.5.bias"))
+            dyb = ops.scale_cast(dx, 1.0, drop_p, sd + 8, colsum=G(li, "conv_module.sequential.5.bias"))
             wgrad(dyb, s["c"], d, d, G(li, "conv_module.sequential.5.weight"))
             dc = ops.gemm(dyb, w["conv_module.sequential.5.weight"], M=M, N=d, K=d, b_mn=True)
             sums = ops.convmod_bn_bwd_reduce(dc, s["y"], s["bmean"], s["brstd"], bn.weight, bn.bias)
@@ -151,8 +149,7 @@ class _ConformerFn(torch.autograd.Function):
 
             # ---- 2. attention
             s = st["attn"]
-            dyb = ops.scale_cast(dx, 1.0, drop_p, sd + 5)
-            ops.colsum(dyb, G(li, "self_attn.out_proj.bias"))
+            dyb = ops.scale_cast(dx, 1.0, drop_p, sd + 5, colsum=G(li, "self_attn.out_proj.bias"))
             wgrad(dyb, s["att"], d, Hd, G(li, "self_attn.out_proj.weight"))
             datt = ops.gemm(dyb, w["self_attn.out_proj.weight"], M=M, N=Hd, K=d, b_mn=True)
             dqkv = ops.attention_bwd(s["qkv"], ctx.lengths, s["att"], datt, s["lse"], B, T, H, scale, drop_p, sd + 4)

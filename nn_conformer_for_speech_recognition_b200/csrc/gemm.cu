@@ -25,6 +25,8 @@
 // The problems here are skinny (K = 144..2304) so a tile's main loop is only 3-16 k-blocks: the epilogue, not the MMA,
 // is the critical resource -- hence 16 epilogue warps (4 per scheduler: the per-element math is latency bound with
 // fewer), MUFU.TANH-based SiLU, compile-time epilogue variants and the overlap through TMEM.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "b200conformer.h"
 
@@ -43,11 +45,12 @@ struct GemmParams {
   b2c_epilogue ep;
 };
 
-template <int BN>
+template <int BN, bool CTA2 = false>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
+  static constexpr int BNH = CTA2 ? BN / 2 : BN;                         // B rows held by ONE CTA
+  static constexpr int STAGES = (BNH == 256) ? 3 : (BNH == 128 ? 4 : 6);
   static constexpr uint32_t A_BYTES = BM * BK * 2;
-  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t B_BYTES = BNH * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SPAN = BN / (EPI_WARPS / 4);                      // columns owned by one epilogue warp
   static constexpr int CW = SPAN < 32 ? SPAN : 32;                       // columns per epilogue chunk (one tcgen05.ld)
@@ -72,11 +75,18 @@ enum : int {
   EPI_ACCUM = 5,     // out += alpha * acc   (fp32 red.global.add.v4)               weight gradients (split-K)
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+// CTA2 = true: launched as clusters of two CTAs; tile = 256 x BN per pair (tcgen05.mma.cta_group::2, M = 256).  CTA r of
+// the pair owns rows [128 r, 128 r + 128) of the tile (A slab, accumulator, epilogue) and loads B rows
+// [r BN/2, (r+1) BN/2); the leader (r = 0) issues every MMA and its commits fan out to both CTAs' barriers.
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmB,
                                                                        const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTA2>;
+  constexpr int BNH = Cfg::BNH;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const int tile0 = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -97,13 +107,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], EPI_WARPS);
+      mbar_init(&tempty_bar[s], CTA2 ? 2 * EPI_WARPS : EPI_WARPS);     // pair: both CTAs' epilogues release the leader
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (CTA2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS); else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();                // peer barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -112,28 +125,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
         const int n_blk = tile % p.n_tiles;
-        const int m_blk = (tile / p.n_tiles) % p.m_tiles;
+        const int m_blk = ((tile / p.n_tiles) % p.m_tiles) * (CTA2 ? 2 : 1) + static_cast<int>(rank);
         const int split = tile / (p.n_tiles * p.m_tiles);
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(p.total_kb, kb0 + p.kblocks_per_split);
+        const int b_row0 = n_blk * BN + static_cast<int>(rank) * BNH;      // this CTA's slice of B's N rows
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          if constexpr (!A_MN) {
-            tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m_blk * BM);
-          } else {
+          if constexpr (!CTA2) {
+            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+            if constexpr (!A_MN) {
+              tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m_blk * BM);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sA + c * 8192, &tmA, &full_bar[s], m_blk * BM + c * 64, kb * BK);
-          }
-          if constexpr (!B_MN) {
-            tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n_blk * BN);
-          } else {
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d(sA + c * 8192, &tmA, &full_bar[s], m_blk * BM + c * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, b_row0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sB + c * 8192, &tmB, &full_bar[s], n_blk * BN + c * 64, kb * BK);
+              for (int c = 0; c < BNH / 64; ++c) tma_load_2d(sB + c * 8192, &tmB, &full_bar[s], b_row0 + c * 64, kb * BK);
+            }
+          } else {
+            // both CTAs' bytes land on the LEADER's full barrier (it alone waits before issuing the pair MMA)
+            const uint32_t lead_bar = mapa_u32(&full_bar[s], 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+            if constexpr (!A_MN) {
+              tma_load_2d_2sm(sA, &tmA, lead_bar, kb * BK, m_blk * BM);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d_2sm(sA + c * 8192, &tmA, lead_bar, m_blk * BM + c * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d_2sm(sB, &tmB, lead_bar, kb * BK, b_row0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BNH / 64; ++c) tma_load_2d_2sm(sB + c * 8192, &tmB, lead_bar, b_row0 + c * 64, kb * BK);
+            }
           }
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
         }
@@ -141,12 +173,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BM : BM, BN, A_MN, B_MN);
       int s = 0;
       uint32_t ph = 0;
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++it) {
         const int split = tile / (p.n_tiles * p.m_tiles);
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(p.total_kb, kb0 + p.kblocks_per_split);
@@ -165,12 +197,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                                      : umma_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_desc_sw128(b_addr + k * 2048, 8192, 1024)
                                      : umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(tm_acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CTA2) umma_bf16_2sm(tm_acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tm_acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[s]);                    // smem slot free once these MMAs retire
+          // smem slot free once these MMAs retire (pair: in both CTAs)
+          if constexpr (CTA2) tc_commit_2sm(&empty_bar[s]); else tc_commit(&empty_bar[s]);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
         }
-        tc_commit(&tfull_bar[as]);                     // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (pair: each CTA's epilogue drains its own 128 rows)
+        if constexpr (CTA2) tc_commit_2sm(&tfull_bar[as]); else tc_commit(&tfull_bar[as]);
       }
     }
   } else {
@@ -188,10 +223,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF + ew * Cfg::STG_WARP_BYTES);
     const int c_lane = lane % LPR;                     // float4 chunk (column group) this lane owns after the transpose
     const int r_lane = lane / LPR;
+    const uint32_t tempty_lead0 = CTA2 ? mapa_u32(&tempty_bar[0], 0) : 0u;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++it) {
       const int n_blk = tile % p.n_tiles;
-      const int m_blk = (tile / p.n_tiles) % p.m_tiles;
+      const int m_blk = ((tile / p.n_tiles) % p.m_tiles) * (CTA2 ? 2 : 1) + static_cast<int>(rank);
       const int split = tile / (p.n_tiles * p.m_tiles);
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const float* bias = split == 0 ? static_cast<const float*>(ep.bias) : nullptr;   // once per split-K
@@ -219,25 +255,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if ((G || EPI != EPI_ACCUM) && bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
         const float* rp = static_cast<const float*>(ep.resid) + row0 * ep.ld_out + col;
         const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(ep.aux) + row0 * ep.ld_aux + col;
-        if (want_resid || want_aux) {
-          // lines of THIS chunk on the CTA's first tile, lines of the NEXT tile's chunk otherwise (one tile ~ a few
-          // microseconds ahead: enough to cover a DRAM round trip; 126 MB of L2 keeps them until they are used)
-          const int ptile = it == 0 ? tile : tile + static_cast<int>(gridDim.x);
-          for (int pt = ptile; pt <= tile + static_cast<int>(gridDim.x) && pt < p.total_tiles; pt += gridDim.x) {
-            const int pn = pt % p.n_tiles, pm = (pt / p.n_tiles) % p.m_tiles;
-            const int64_t pcol = static_cast<int64_t>(pn) * BN + col_t + c_lane * 4;
-            const int64_t prow0 = static_cast<int64_t>(pm) * BM + q * 32 + r_lane;
-            if (pcol < p.N) {
-#pragma unroll 4
-              for (int i = 0; i < NIT; ++i) {
-                const int64_t prow = prow0 + i * RPI;
-                if (prow >= p.M) break;
-                const void* ptr = want_resid ? static_cast<const void*>(static_cast<const float*>(ep.resid) + prow * ep.ld_out + pcol)
-                                             : static_cast<const void*>(static_cast<const __nv_bfloat16*>(ep.aux) + prow * ep.ld_aux + pcol);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-              }
+        // every global READ of this chunk (residual / saved pre-activation) is issued into registers BEFORE waiting
+        // for the accumulator, so its DRAM/L2 latency overlaps this tile's main loop (NIT <= 8: at most 32 registers)
+        uint4 pre[NIT];
+        if (col_ok && want_resid) {
+#pragma unroll
+          for (int i = 0; i < NIT; ++i)
+            if (i * RPI < rows_left) pre[i] = *reinterpret_cast<const uint4*>(rp + static_cast<int64_t>(i) * RPI * ep.ld_out);
+        } else if (col_ok && want_aux) {
+#pragma unroll
+          for (int i = 0; i < NIT; ++i)
+            if (i * RPI < rows_left) {
+              const uint2 a = *reinterpret_cast<const uint2*>(ap + static_cast<int64_t>(i) * RPI * ep.ld_aux);
+              pre[i].x = a.x; pre[i].y = a.y;
             }
-          }
         }
         if (ch == 0) {
           mbar_wait(&tfull_bar[as], aph);
@@ -251,7 +282,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if (ch == Cfg::CHUNKS - 1) {                   // all of this warp's TMEM reads for the tile are done
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          if (lane == 0) {
+            if constexpr (CTA2) mbar_arrive_cluster(tempty_lead0 + as * 8); else mbar_arrive(&tempty_bar[as]);
+          }
         }
         // transpose through smem: row = lane, 16-byte chunk c stored at (c ^ (lane & SWZ))
 #pragma unroll
@@ -259,12 +292,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           *reinterpret_cast<uint4*>(stg + lane * CW + ((c ^ (lane & SWZ)) << 2)) =
               make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         __syncwarp();
+        const bool do_colsum = (EPI != EPI_RESID && EPI != EPI_ACCUM) && ep.colsum != nullptr && out_bf16;
+        float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
         if (col_ok) {
           const uint64_t drop_base = static_cast<uint64_t>(row0) * p.N + col;
           __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(ep.out) + row0 * ep.ld_out + col;
           float* of = static_cast<float*>(ep.out) + row0 * ep.ld_out + col;
           __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(ep.out2) + row0 * ep.ld_out2 + col;
-#pragma unroll 4
+          // variants that index the prefetch registers need the full unroll; the others stay compact (I-cache)
+          constexpr int UNR = (EPI == EPI_RESID || EPI == EPI_SILU_BWD || EPI == EPI_GENERIC) ? NIT : (NIT < 4 ? NIT : 4);
+#pragma unroll UNR
           for (int i = 0; i < NIT; ++i) {
             if (i * RPI >= rows_left) break;
             const int r = i * RPI + r_lane;
@@ -277,8 +314,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
               for (int j = 0; j < 4; ++j) f[j] *= sigmoid_fast(f[j]);
             } else if (want_aux) {                      // f = dL/dh ; aux = pre-activation u ; out = f * silu'(u)
-              const uint2 av = *reinterpret_cast<const uint2*>(ap + static_cast<int64_t>(i) * RPI * ep.ld_aux);
-              const float2 a0 = unpack_bf16(av.x), a1 = unpack_bf16(av.y);
+              const float2 a0 = unpack_bf16(pre[i].x), a1 = unpack_bf16(pre[i].y);
               const float u[4] = {a0.x, a0.y, a1.x, a1.y};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -298,8 +334,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
               for (int j = 0; j < 4; ++j) f[j] *= ep.alpha;
             }
             if (out_bf16) {
-              *reinterpret_cast<uint2*>(ob + static_cast<int64_t>(i) * RPI * ep.ld_out) =
-                  make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+              const uint2 packed = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+              *reinterpret_cast<uint2*>(ob + static_cast<int64_t>(i) * RPI * ep.ld_out) = packed;
+              if (do_colsum) {                         // column sums of the ROUNDED values (what the next GEMM consumes)
+                const float2 p0 = unpack_bf16(packed.x), p1 = unpack_bf16(packed.y);
+                cs0 += p0.x; cs1 += p0.y; cs2 += p1.x; cs3 += p1.y;
+              }
             } else {
               float* o = of + static_cast<int64_t>(i) * RPI * ep.ld_out;
               if (do_accum) {                          // split-K / gradient accumulation: fp32 reductions in L2
@@ -307,12 +347,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                              : "memory");
               } else {
                 if (want_resid) {
-                  const float4 r4 = *reinterpret_cast<const float4*>(rp + static_cast<int64_t>(i) * RPI * ep.ld_out);
-                  f[0] += r4.x; f[1] += r4.y; f[2] += r4.z; f[3] += r4.w;
+                  f[0] += __uint_as_float(pre[i].x); f[1] += __uint_as_float(pre[i].y);
+                  f[2] += __uint_as_float(pre[i].z); f[3] += __uint_as_float(pre[i].w);
                 }
                 *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
               }
             }
+          }
+        }
+        if (do_colsum) {                               // warp-level: lanes sharing c_lane hold partials of the same columns
+#pragma unroll
+          for (int o = LPR; o < 32; o <<= 1) {
+            cs0 += __shfl_xor_sync(0xffffffffu, cs0, o); cs1 += __shfl_xor_sync(0xffffffffu, cs1, o);
+            cs2 += __shfl_xor_sync(0xffffffffu, cs2, o); cs3 += __shfl_xor_sync(0xffffffffu, cs3, o);
+          }
+          if (r_lane == 0 && col_ok) {
+            atomicAdd(ep.colsum + col, cs0); atomicAdd(ep.colsum + col + 1, cs1);
+            atomicAdd(ep.colsum + col + 2, cs2); atomicAdd(ep.colsum + col + 3, cs3);
           }
         }
       }
@@ -320,25 +371,43 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();                // the peer may still be reading operands / signalling barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CTA2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>;
+  using Cfg = GemmCfg<BN, CTA2>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CTA2>;
   static bool configured = false;
   if (!configured) {
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
   p.n_tiles = static_cast<int>((p.N + BN - 1) / BN);
+  p.m_tiles = static_cast<int>((p.M + (CTA2 ? 2 * BM : BM) - 1) / (CTA2 ? 2 * BM : BM));      // M units: blocks or pairs
   p.total_tiles = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
+  if constexpr (!CTA2) {
+    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
+  } else {
+    const int pairs = num_sms() / 2;
+    const int npair = p.total_tiles < pairs ? p.total_tiles : pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * npair);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  }
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -361,8 +430,18 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
               "b2c_gemm_bf16: pointers must be 16-byte aligned");
   B2C_REQUIRE(!(ep->accumulate && ep->out_dtype != B2C_F32), "b2c_gemm_bf16: accumulate needs fp32 output");
   B2C_REQUIRE(!(ep->act == B2C_ACT_SILU_BWD && !ep->aux), "b2c_gemm_bf16: SILU_BWD needs aux");
+  // block_n: 0 = automatic; 64/128/256 = one CTA per 128 x block_n tile; -128/-256 = CTA pair per 256 x |block_n| tile
   int bn = block_n;
-  if (bn == 0) bn = (N >= 128) ? 128 : 64;
+  bool cta2 = false;
+  if (bn == 0) {
+    static const bool allow2 = [] { const char* e = getenv("B2C_GEMM_2SM"); return !(e && e[0] == '0'); }();
+    if (allow2 && N >= 256 && M >= 256) { bn = 256; cta2 = true; }
+    else bn = (N >= 128) ? 128 : 64;
+  } else if (bn < 0) {
+    bn = -bn;
+    cta2 = true;
+    B2C_REQUIRE(bn == 128 || bn == 256, "b2c_gemm_bf16: CTA-pair tiles need block_n -128 or -256");
+  }
   B2C_REQUIRE(bn == 64 || bn == 128 || bn == 256, "b2c_gemm_bf16: block_n must be 64, 128 or 256");
   const int total_kb = static_cast<int>((K + BK - 1) / BK);
   int splits = split_k < 1 ? 1 : split_k;
@@ -381,7 +460,7 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   if (!a_mn) rc = get_tensor_map_2d(&ta, A, 2, K, M, lda * 2, BK, BM, true);
   else       rc = get_tensor_map_2d(&ta, A, 2, M, K, lda * 2, 64, BK, true);
   if (rc) return rc;
-  if (!b_mn) rc = get_tensor_map_2d(&tb, B, 2, K, N, ldb * 2, BK, bn, true);
+  if (!b_mn) rc = get_tensor_map_2d(&tb, B, 2, K, N, ldb * 2, BK, cta2 ? bn / 2 : bn, true);
   else       rc = get_tensor_map_2d(&tb, B, 2, N, K, ldb * 2, 64, BK, true);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -393,29 +472,31 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   else if (ep->out_dtype == B2C_F32 && ep->resid && !ep->accumulate && ep->act == B2C_ACT_NONE && !ep->out2) epi = EPI_RESID;
   else if (ep->out_dtype == B2C_BF16 && ep->act == B2C_ACT_SILU_BWD && !ep->out2 && !ep->bias && ep->alpha == 1.f) epi = EPI_SILU_BWD;
   else if (ep->out_dtype == B2C_F32 && ep->accumulate && ep->act == B2C_ACT_NONE && !ep->out2 && !ep->bias && ep->drop_p == 0.f) epi = EPI_ACCUM;
-#define B2C_LAUNCH(BN_, AM, BMN, E) return launch_gemm<BN_, AM, BMN, E>(ta, tb, p, st)
-#define B2C_DISPATCH(BN_)                                                                          \
-  if (bn == BN_) {                                                                                 \
+#define B2C_LAUNCH(BN_, AM, BMN, E, C2) return launch_gemm<BN_, AM, BMN, E, C2>(ta, tb, p, st)
+#define B2C_DISPATCH(BN_, C2)                                                                      \
+  if (bn == BN_ && cta2 == C2) {                                                                   \
     if (!a_mn && !b_mn) {                                                                          \
-      if (epi == EPI_BF16) B2C_LAUNCH(BN_, false, false, EPI_BF16);                                \
-      if (epi == EPI_SILU) B2C_LAUNCH(BN_, false, false, EPI_SILU);                                \
-      if (epi == EPI_RESID) B2C_LAUNCH(BN_, false, false, EPI_RESID);                              \
-      B2C_LAUNCH(BN_, false, false, EPI_GENERIC);                                                  \
+      if (epi == EPI_BF16) B2C_LAUNCH(BN_, false, false, EPI_BF16, C2);                            \
+      if (epi == EPI_SILU) B2C_LAUNCH(BN_, false, false, EPI_SILU, C2);                            \
+      if (epi == EPI_RESID) B2C_LAUNCH(BN_, false, false, EPI_RESID, C2);                          \
+      B2C_LAUNCH(BN_, false, false, EPI_GENERIC, C2);                                              \
     }                                                                                              \
     if (!a_mn && b_mn) {                                                                           \
-      if (epi == EPI_BF16) B2C_LAUNCH(BN_, false, true, EPI_BF16);                                 \
-      if (epi == EPI_SILU_BWD) B2C_LAUNCH(BN_, false, true, EPI_SILU_BWD);                         \
-      B2C_LAUNCH(BN_, false, true, EPI_GENERIC);                                                   \
+      if (epi == EPI_BF16) B2C_LAUNCH(BN_, false, true, EPI_BF16, C2);                             \
+      if (epi == EPI_SILU_BWD) B2C_LAUNCH(BN_, false, true, EPI_SILU_BWD, C2);                     \
+      B2C_LAUNCH(BN_, false, true, EPI_GENERIC, C2);                                               \
     }                                                                                              \
     if (a_mn && b_mn) {                                                                            \
-      if (epi == EPI_ACCUM) B2C_LAUNCH(BN_, true, true, EPI_ACCUM);                                \
-      B2C_LAUNCH(BN_, true, true, EPI_GENERIC);                                                    \
+      if (epi == EPI_ACCUM) B2C_LAUNCH(BN_, true, true, EPI_ACCUM, C2);                            \
+      B2C_LAUNCH(BN_, true, true, EPI_GENERIC, C2);                                                \
     }                                                                                              \
-    B2C_LAUNCH(BN_, true, false, EPI_GENERIC);                                                     \
+    B2C_LAUNCH(BN_, true, false, EPI_GENERIC, C2);                                                 \
   }
-  B2C_DISPATCH(64)
-  B2C_DISPATCH(128)
-  B2C_DISPATCH(256)
+  B2C_DISPATCH(64, false)
+  B2C_DISPATCH(128, false)
+  B2C_DISPATCH(256, false)
+  B2C_DISPATCH(128, true)
+  B2C_DISPATCH(256, true)
 #undef B2C_LAUNCH
 #undef B2C_DISPATCH
   return -1;

@@ -190,20 +190,54 @@ __global__ void multi_cast_kernel(const CastEntry* __restrict__ table) {
   }
 }
 
-__global__ void scale_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n,
-                                  float alpha, DropCfg drop) {
-  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
-  if (i >= n) return;                       // n % 4 == 0 enforced by the host
-  float4 a = *reinterpret_cast<const float4*>(src + i);
-  float f[4] = {a.x * alpha, a.y * alpha, a.z * alpha, a.w * alpha};
-  if (drop.thresh16) {
-    drop = drop_resolve(drop);
-    float s0, s1, s2, s3;
-    drop_scale2(drop, static_cast<uint64_t>(i), s0, s1);
-    drop_scale2(drop, static_cast<uint64_t>(i) + 2, s2, s3);
-    f[0] *= s0; f[1] *= s1; f[2] *= s2; f[3] *= s3;
+// dst = bf16(alpha * dropout(src)); optionally colsum[c] += sum_r dst[r, c].  2-D mapping: a thread owns 4 adjacent
+// columns and walks rows (coalesced 16 B loads across the row), so column partials live in registers; one shared-memory
+// reduction and one atomic per column per CTA.
+__global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                        int64_t rows, int cols, float alpha, DropCfg drop,
+                                                        float* __restrict__ colsum, int rows_per_block) {
+  extern __shared__ float cs_red[];                    // [cols] column partials of this CTA
+  const int c4 = cols >> 2;                            // float4 groups per row
+  const int tpr = c4 < 256 ? c4 : 256;                 // threads per row
+  const int rstep = 256 / tpr;                         // rows per pass
+  const int tc = threadIdx.x % tpr, tr = threadIdx.x / tpr;
+  if (colsum) {
+    for (int i = threadIdx.x; i < cols; i += 256) cs_red[i] = 0.f;
+    __syncthreads();
   }
-  *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+  if (drop.thresh16) drop = drop_resolve(drop);
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  if (tr < rstep) {
+    for (int cg = tc; cg < c4; cg += tpr) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int64_t r = r0 + tr; r < r1; r += rstep) {
+        const int64_t i = r * cols + cg * 4;
+        const float4 a = *reinterpret_cast<const float4*>(src + i);
+        float f[4] = {a.x * alpha, a.y * alpha, a.z * alpha, a.w * alpha};
+        if (drop.thresh16) {
+          float s0, s1, s2, s3;
+          drop_scale2(drop, static_cast<uint64_t>(i), s0, s1);
+          drop_scale2(drop, static_cast<uint64_t>(i) + 2, s2, s3);
+          f[0] *= s0; f[1] *= s1; f[2] *= s2; f[3] *= s3;
+        }
+        const uint2 packed = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+        *reinterpret_cast<uint2*>(dst + i) = packed;
+        if (colsum) {                                  // sums of the ROUNDED values: exactly what the wgrad GEMM will see
+          const float2 p0 = unpack_bf16(packed.x), p1 = unpack_bf16(packed.y);
+          a0 += p0.x; a1 += p0.y; a2 += p1.x; a3 += p1.y;
+        }
+      }
+      if (colsum) {
+        atomicAdd(&cs_red[cg * 4 + 0], a0); atomicAdd(&cs_red[cg * 4 + 1], a1);
+        atomicAdd(&cs_red[cg * 4 + 2], a2); atomicAdd(&cs_red[cg * 4 + 3], a3);
+      }
+    }
+  }
+  if (colsum) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < cols; i += 256) atomicAdd(colsum + i, cs_red[i]);
+  }
 }
 
 // column sums of a bf16 matrix: block = 32 x 8 threads, each thread owns 2 adjacent columns over a row slab
@@ -310,14 +344,17 @@ extern "C" int b2c_multi_cast_f32_bf16(const void* table_dev, int n_tensors, int
 }
 
 extern "C" int b2c_scale_cast(const float* src, void* dst, int64_t rows, int64_t cols, float alpha, float drop_p,
-                              uint64_t drop_seed, void* stream) {
+                              uint64_t drop_seed, float* colsum, void* stream) {
   B2C_REQUIRE(src && dst, "b2c_scale_cast: null pointer");
-  const int64_t n = rows * cols;
-  if (n <= 0) return 0;
-  B2C_REQUIRE(n % 4 == 0, "b2c_scale_cast: element count must be a multiple of 4");
-  const int64_t threads = n / 4;
-  scale_cast_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(dst), n, alpha, make_drop(drop_p, drop_seed));
+  if (rows <= 0 || cols <= 0) return 0;
+  B2C_REQUIRE(cols % 4 == 0 && cols <= 8192, "b2c_scale_cast: cols must be a multiple of 4 (<= 8192)");
+  const int64_t want_blocks = static_cast<int64_t>(num_sms()) * 4;
+  int rows_per_block = static_cast<int>((rows + want_blocks - 1) / want_blocks);
+  if (rows_per_block < 4) rows_per_block = 4;
+  const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
+  scale_cast_kernel<<<grid, 256, colsum ? cols * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), rows, static_cast<int>(cols), alpha, make_drop(drop_p, drop_seed), colsum,
+      rows_per_block);
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

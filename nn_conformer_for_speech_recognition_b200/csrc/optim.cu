@@ -97,23 +97,31 @@ __global__ void adafactor_tick_kernel(int64_t* __restrict__ step, float* __restr
   *beta2t = 1.f - powf(static_cast<float>(s), decay_rate);          // HF: 1 - step^decay_rate
 }
 
-// one block per (tensor, slab-range): updates the factored second moments and the per-slab mean of the row factor
+// grid = (blocks, tensors): updates the factored second moments and the per-slab mean of the row factor.
+// A warp owns whole slabs (it updates the R row entries of slab p and reduces their mean itself), columns are a
+// plain grid-stride loop -- no cross-block dependency, so large stacks of small slabs (conv kernels: 65k slabs of 3x3)
+// spread over the whole chip instead of crawling through one CTA.
 __global__ void __launch_bounds__(AF_THREADS) adafactor_factors_kernel(const AfTensor* __restrict__ tensors, int n_tensors,
                                                                       const float* __restrict__ beta2t_ptr) {
   const float beta2t = *beta2t_ptr;
-  const AfTensor T = tensors[blockIdx.x];
+  const AfTensor T = tensors[blockIdx.y];
   if (!T.factored) return;
   const int C = T.C, R = T.R, P = T.P;
   const float om = 1.f - beta2t;
-  for (int64_t i = threadIdx.x; i < static_cast<int64_t>(P) * C; i += AF_THREADS)
+  const int64_t gtid = static_cast<int64_t>(blockIdx.x) * AF_THREADS + threadIdx.x;
+  const int64_t gstride = static_cast<int64_t>(gridDim.x) * AF_THREADS;
+  for (int64_t i = gtid; i < static_cast<int64_t>(P) * C; i += gstride)
     T.col[i] = beta2t * T.col[i] + om * (T.colsum[i] / R);
-  for (int64_t i = threadIdx.x; i < static_cast<int64_t>(P) * R; i += AF_THREADS)
-    T.row[i] = beta2t * T.row[i] + om * (T.rowsum[i] / C);
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int pslab = warp; pslab < P; pslab += AF_THREADS / 32) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gwarp = gtid >> 5, nwarps = gstride >> 5;
+  for (int64_t pslab = gwarp; pslab < P; pslab += nwarps) {
     float acc = 0.f;
-    for (int r = lane; r < R; r += 32) acc += T.row[static_cast<int64_t>(pslab) * R + r];
+    for (int r = lane; r < R; r += 32) {
+      const int64_t i = pslab * R + r;
+      const float v = beta2t * T.row[i] + om * (T.rowsum[i] / C);
+      T.row[i] = v;
+      acc += v;
+    }
     acc = warp_sum(acc);
     if (lane == 0) T.rmean[pslab] = acc / R;
   }
@@ -196,7 +204,7 @@ extern "C" int b2c_adafactor_step(const void* tensors_dev, int n_tensors, const 
   const AfChunk* Cc = static_cast<const AfChunk*>(chunks_dev);
   adafactor_tick_kernel<<<1, 1, 0, st>>>(step_dev, beta2t_dev, decay_rate);
   adafactor_stats_kernel<<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, eps1);
-  adafactor_factors_kernel<<<n_tensors, AF_THREADS, 0, st>>>(T, n_tensors, beta2t_dev);
+  adafactor_factors_kernel<<<dim3(32, n_tensors), AF_THREADS, 0, st>>>(T, n_tensors, beta2t_dev);
   adafactor_update_kernel<false><<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, beta2t_dev, eps1, lr, beta1, clip);
   adafactor_update_kernel<true><<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, beta2t_dev, eps1, lr, beta1, clip);
   B2C_CUDA(cudaGetLastError());

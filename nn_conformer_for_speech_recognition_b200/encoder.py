@@ -38,12 +38,11 @@ class _BridgeFn(torch.autograd.Function):
     def backward(ctx, dy):
         a, w_bf16 = ctx.saved_tensors
         M, K, N = ctx.shapes
-        dyb = ops.scale_cast(dy.contiguous().view(M, N), 1.0)
-        dW = torch.zeros((N, K), device=dy.device, dtype=torch.float32)
         db = torch.zeros(N, device=dy.device, dtype=torch.float32)
+        dyb = ops.scale_cast(dy.contiguous().view(M, N), 1.0, colsum=db)
+        dW = torch.zeros((N, K), device=dy.device, dtype=torch.float32)
         ops.gemm(dyb, a, M=N, N=K, K=M, a_mn=True, b_mn=True, out=dW, accumulate=True,
                  split_k=max(1, min(16, ((M + 63) // 64) // 4)))
-        ops.colsum(dyb, db)
         da = ops.gemm(dyb, w_bf16, M=M, N=K, K=N, b_mn=True) if ctx.needs_input_grad[0] else None
         return da, dW, db, None
 

@@ -30,7 +30,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_mn: bool
          bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, aux: Optional[torch.Tensor] = None,
          resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
          out_dtype: torch.dtype = torch.bfloat16, alpha: float = 1.0, drop_p: float = 0.0, drop_seed: int = 0,
-         accumulate: bool = False, split_k: int = 1, block_n: int = 0) -> torch.Tensor:
+         accumulate: bool = False, split_k: int = 1, block_n: int = 0,
+         colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D[M,N] = epilogue(A * B^T) -- see b2c_gemm_bf16.  a/b are 2-D bf16 tensors whose last dim is contiguous;
     with a_mn/b_mn the tensor is the [K, rows] storage."""
     _lib.require_device()
@@ -55,6 +56,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_mn: bool
     ep.act = act
     ep.out_dtype = BF16 if out.dtype == torch.bfloat16 else F32
     ep.accumulate = int(accumulate)
+    ep.colsum = ptr(colsum)
     call("b2c_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), M, N, K, split_k, block_n,
          ctypes.byref(ep), stream_ptr(), flops=2.0 * M * N * K)
     return out
@@ -195,10 +197,10 @@ def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None):
     return dst
 
 
-def scale_cast(src, alpha: float, drop_p: float = 0.0, drop_seed: int = 0):
+def scale_cast(src, alpha: float, drop_p: float = 0.0, drop_seed: int = 0, colsum: Optional[torch.Tensor] = None):
     rows, cols = src.shape
     dst = torch.empty((rows, cols), device=src.device, dtype=torch.bfloat16)
-    call("b2c_scale_cast", ptr(src), ptr(dst), rows, cols, alpha, drop_p, drop_seed, stream_ptr())
+    call("b2c_scale_cast", ptr(src), ptr(dst), rows, cols, alpha, drop_p, drop_seed, ptr(colsum), stream_ptr())
     return dst
 
 

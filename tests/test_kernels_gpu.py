@@ -305,3 +305,67 @@ def test_fused_adafactor_matches_hf():
             _close(o1.views[i]["col"].view(st["exp_avg_sq_col"].shape), st["exp_avg_sq_col"], rel=1e-3, abs_=1e-12, name="col")
         else:
             _close(o1.views[i]["row"], st["exp_avg_sq"], rel=1e-3, abs_=1e-12, name="sq")
+
+
+# ----------------------------------------------------------------------------------------------- GEMM, CTA pairs
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, -256), (512, 512, 256, -256), (1000, 1024, 256, -256),
+                                      (777, 768, 320, -256), (300, 144, 144, -128), (23872, 256, 1024, -256),
+                                      (2049, 384, 576, -128)])
+def test_gemm_cta_pair_forward(ops, M, N, K, bn):
+    """tcgen05.mma.cta_group::2 path (256 x |bn| tile per CTA pair), forward layout, all fused epilogues."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().T + bias
+    _close(ops.gemm(a, w, M=M, N=N, K=K, bias=bias, block_n=bn), ref, name="pair bias")
+    out2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    h = ops.gemm(a, w, M=M, N=N, K=K, bias=bias, act=ops.ACT_SILU, out2=out2, block_n=bn)
+    _close(out2, ref, name="pair pre-act")
+    _close(h, torch.nn.functional.silu(ref), name="pair silu")
+    x = torch.randn(M, N, device="cuda", generator=g)
+    want = x + 0.5 * ref
+    ops.gemm(a, w, M=M, N=N, K=K, bias=bias, resid=x, out=x, alpha=0.5, block_n=bn)
+    _close(x, want, rel=5e-3, name="pair resid")
+
+
+@pytest.mark.parametrize("bn", [-256, -128])
+def test_gemm_cta_pair_dgrad_wgrad(ops, bn):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 1000, 512, 256
+    dy = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(K, N, device="cuda", generator=g) / math.sqrt(K))
+    _close(ops.gemm(dy, w, M=M, N=N, K=K, b_mn=True, block_n=bn), dy.float() @ w.float(), name="pair dgrad")
+    u = _bf(torch.randn(M, N, device="cuda", generator=g))
+    s = torch.sigmoid(u.float())
+    out = ops.gemm(dy, w, M=M, N=N, K=K, b_mn=True, act=ops.ACT_SILU_BWD, aux=u, block_n=bn)
+    _close(out, (dy.float() @ w.float()) * (s * (1 + u.float() * (1 - s))), name="pair silu bwd")
+    Mo, No, Kt = 256, 1024, 5000
+    dyt = _bf(torch.randn(Kt, Mo, device="cuda", generator=g))
+    xt = _bf(torch.randn(Kt, No, device="cuda", generator=g))
+    dw = ops.gemm(dyt, xt, M=Mo, N=No, K=Kt, a_mn=True, b_mn=True, out_dtype=torch.float32, accumulate=True, split_k=7,
+                  block_n=bn)
+    _close(dw, dyt.float().T @ xt.float(), rel=2e-3, name="pair wgrad")
+
+
+def test_fused_column_sums(ops):
+    """bias gradients are produced by the kernels that write the tensor (scale_cast, GEMM epilogue)."""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(5000, 256, device="cuda", generator=g)
+    cs = torch.zeros(256, device="cuda")
+    y = ops.scale_cast(x, 0.5, 0.5, 77, colsum=cs)
+    _close(cs, y.float().sum(0), rel=1e-4, abs_=1e-2, name="scale_cast colsum")
+    assert torch.equal(y, ops.scale_cast(x, 0.5, 0.5, 77))
+    x2 = torch.randn(333, 144, device="cuda", generator=g)
+    cs2 = torch.zeros(144, device="cuda")
+    y2 = ops.scale_cast(x2, 1.0, colsum=cs2)
+    assert torch.equal(y2, x2.to(torch.bfloat16))
+    _close(cs2, y2.float().sum(0), rel=1e-4, abs_=1e-2, name="scale_cast colsum 144")
+    M, N, K = 3000, 1024, 256
+    dy = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(K, N, device="cuda", generator=g) / 16)
+    u = _bf(torch.randn(M, N, device="cuda", generator=g))
+    for bn in (128, -256, 64):
+        cs3 = torch.zeros(N, device="cuda")
+        out = ops.gemm(dy, w, M=M, N=N, K=K, b_mn=True, act=ops.ACT_SILU_BWD, aux=u, colsum=cs3, block_n=bn)
+        _close(cs3, out.float().sum(0), rel=1e-3, abs_=5e-2, name=f"gemm colsum bn{bn}")

@@ -53,7 +53,7 @@ def main():
                          gbs=round(nbytes / us / 1e3, 1) if nbytes else None)
         print(f"{name:44s} {us:9.2f} us  {res[name]['tflops'] or '':>8} TF/s  {res[name]['gbs'] or '':>8} GB/s", flush=True)
 
-    for bn in (128, 256):
+    for bn in (128, 256, -256):
         rec(f"gemm ffn1 M{M} N{f} K{d} silu bn{bn}", timeit(lambda: ops.gemm(a_d, w_fd, M=M, N=f, K=d, bias=bias_f, act=ops.ACT_SILU, out=out_f, block_n=bn)),
             2 * M * f * d, M * d * 2 + M * f * 2)
         rec(f"gemm ffn2 M{M} N{d} K{f} resid bn{bn}", timeit(lambda: ops.gemm(a_f, w_df, M=M, N=d, K=f, bias=bias_d, resid=x, out=x, alpha=0.5, block_n=bn)),
@@ -67,8 +67,8 @@ def main():
         rec(f"gemm dgrad M{M} N{d} K{f} bn{bn}", timeit(lambda: ops.gemm(a_f, w_fd, M=M, N=d, K=f, b_mn=True, out=out_d, block_n=bn)),
             2 * M * f * d, M * f * 2 + M * d * 2)
     dW = torch.zeros(d, f, device=dev)
-    for split in (8, 18, 37):
-        rec(f"gemm wgrad M{d} N{f} K{M} split{split}", timeit(lambda: ops.gemm(a_d, a_f, M=d, N=f, K=M, a_mn=True, b_mn=True, out=dW, accumulate=True, split_k=split)),
+    for split, bn in ((18, 128), (18, -256), (37, -256)):
+        rec(f"gemm wgrad M{d} N{f} K{M} split{split} bn{bn}", timeit(lambda: ops.gemm(a_d, a_f, M=d, N=f, K=M, a_mn=True, b_mn=True, out=dW, accumulate=True, split_k=split, block_n=bn)),
             2 * M * f * d, M * d * 2 + M * f * 2)
     g, be = torch.ones(d, device=dev), torch.zeros(d, device=dev)
     rec("layernorm fwd bf16", timeit(lambda: ops.layernorm_fwd(x, g, be, out=out_d)), 0, M * d * 6)
