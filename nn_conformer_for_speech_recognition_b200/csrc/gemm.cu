@@ -78,7 +78,9 @@ enum : int {
 // CTA2 = true: launched as clusters of two CTAs; tile = 256 x BN per pair (tcgen05.mma.cta_group::2, M = 256).  CTA r of
 // the pair owns rows [128 r, 128 r + 128) of the tile (A slab, accumulator, epilogue) and loads B rows
 // [r BN/2, (r+1) BN/2); the leader (r = 0) issues every MMA and its commits fan out to both CTAs' barriers.
-template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2>
+// EXTRA = false compiles the training-only extras (saved pre-activation, dropout, fused column sums) out of the
+// specialised epilogues; the generic epilogue always keeps them (run-time switched).
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmB,
                                                                        const GemmParams p) {
@@ -237,8 +239,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const bool do_silu = G ? (ep.act == B2C_ACT_SILU) : (EPI == EPI_SILU);
       const bool out_bf16 = G ? (ep.out_dtype == B2C_BF16) : (EPI == EPI_BF16 || EPI == EPI_SILU || EPI == EPI_SILU_BWD);
       const bool do_accum = G ? (ep.accumulate != 0) : (EPI == EPI_ACCUM);
-      const bool do_out2 = (G || EPI == EPI_SILU) && ep.out2 != nullptr;
-      const bool do_drop = (EPI != EPI_BF16 && EPI != EPI_ACCUM) && p.drop.thresh16 != 0;
+      const bool do_out2 = (G || (EXTRA && EPI == EPI_SILU)) && ep.out2 != nullptr;
+      const bool do_drop = (G || (EXTRA && EPI != EPI_BF16 && EPI != EPI_ACCUM)) && p.drop.thresh16 != 0;
       const bool do_alpha = (G || EPI == EPI_RESID || EPI == EPI_ACCUM) && ep.alpha != 1.f;
 #pragma unroll 1
       for (int ch = 0; ch < Cfg::CHUNKS; ++ch) {
@@ -292,24 +294,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           *reinterpret_cast<uint4*>(stg + lane * CW + ((c ^ (lane & SWZ)) << 2)) =
               make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         __syncwarp();
-        const bool do_colsum = (EPI != EPI_RESID && EPI != EPI_ACCUM) && ep.colsum != nullptr && out_bf16;
+        const bool do_colsum = (G || (EXTRA && EPI != EPI_RESID && EPI != EPI_ACCUM)) && ep.colsum != nullptr && out_bf16;
         float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
         if (col_ok) {
-          const uint64_t drop_base = static_cast<uint64_t>(row0) * p.N + col;
+          // loop-carried pointers / indices: one 64-bit add per stream per row step instead of re-deriving
+          // base + i*stride (IMAD.WIDE chains) in every unrolled iteration -- the epilogue is issue-bound
+          uint64_t di = static_cast<uint64_t>(row0) * p.N + col;            // dropout element index (even)
+          const uint64_t di_step = static_cast<uint64_t>(RPI) * p.N;
           __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(ep.out) + row0 * ep.ld_out + col;
           float* of = static_cast<float*>(ep.out) + row0 * ep.ld_out + col;
           __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(ep.out2) + row0 * ep.ld_out2 + col;
+          const int64_t o_step = static_cast<int64_t>(RPI) * ep.ld_out, o2_step = static_cast<int64_t>(RPI) * ep.ld_out2;
+          // transpose-buffer read offsets: (r & SWZ) cycles with period PC rows steps, so PC precomputed offsets suffice
+          constexpr int PC = (SWZ + 1) / RPI > 0 ? (SWZ + 1) / RPI : 1;
+          int rd_off[PC];
+#pragma unroll
+          for (int pc = 0; pc < PC; ++pc) {
+            const int r = pc * RPI + r_lane;
+            rd_off[pc] = r * CW + ((c_lane ^ (r & SWZ)) << 2);
+          }
           // variants that index the prefetch registers need the full unroll; the others stay compact (I-cache)
           constexpr int UNR = (EPI == EPI_RESID || EPI == EPI_SILU_BWD || EPI == EPI_GENERIC) ? NIT : (NIT < 4 ? NIT : 4);
 #pragma unroll UNR
           for (int i = 0; i < NIT; ++i) {
             if (i * RPI >= rows_left) break;
-            const int r = i * RPI + r_lane;
-            const float4 a4 = *reinterpret_cast<const float4*>(stg + r * CW + ((c_lane ^ (r & SWZ)) << 2));
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + rd_off[i % PC] + (i / PC) * (PC * RPI * CW));
             float f[4] = {a4.x + bv.x, a4.y + bv.y, a4.z + bv.z, a4.w + bv.w};
-            if (do_out2)                               // pre-activation copy (saved for the backward pass)
-              *reinterpret_cast<uint2*>(o2 + static_cast<int64_t>(i) * RPI * ep.ld_out2) =
-                  make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+            if (do_out2) {                             // pre-activation copy (saved for the backward pass)
+              *reinterpret_cast<uint2*>(o2) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+              o2 += o2_step;
+            }
             if (do_silu) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) f[j] *= sigmoid_fast(f[j]);
@@ -324,10 +338,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             }
             if (do_drop) {
               float s0, s1, s2, s3;
-              const uint64_t di = drop_base + static_cast<uint64_t>(i) * RPI * p.N;   // N % 8 == 0, col % 4 == 0: even
               drop_scale2(drop, di, s0, s1);
               drop_scale2(drop, di + 2, s2, s3);
               f[0] *= s0; f[1] *= s1; f[2] *= s2; f[3] *= s3;
+              di += di_step;
             }
             if (do_alpha) {
 #pragma unroll
@@ -335,23 +349,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             }
             if (out_bf16) {
               const uint2 packed = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
-              *reinterpret_cast<uint2*>(ob + static_cast<int64_t>(i) * RPI * ep.ld_out) = packed;
+              *reinterpret_cast<uint2*>(ob) = packed;
+              ob += o_step;
               if (do_colsum) {                         // column sums of the ROUNDED values (what the next GEMM consumes)
                 const float2 p0 = unpack_bf16(packed.x), p1 = unpack_bf16(packed.y);
                 cs0 += p0.x; cs1 += p0.y; cs2 += p1.x; cs3 += p1.y;
               }
             } else {
-              float* o = of + static_cast<int64_t>(i) * RPI * ep.ld_out;
               if (do_accum) {                          // split-K / gradient accumulation: fp32 reductions in L2
-                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3])
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(of), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3])
                              : "memory");
               } else {
                 if (want_resid) {
                   f[0] += __uint_as_float(pre[i].x); f[1] += __uint_as_float(pre[i].y);
                   f[2] += __uint_as_float(pre[i].z); f[3] += __uint_as_float(pre[i].w);
                 }
-                *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(of) = make_float4(f[0], f[1], f[2], f[3]);
               }
+              of += o_step;
             }
           }
         }
@@ -378,10 +393,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTA2>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CTA2>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CTA2, EXTRA>;
   static bool configured = false;
   if (!configured) {
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -467,36 +482,43 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   // pick the specialised epilogue when the request matches one of the hot-path patterns, else the generic kernel
   int epi = EPI_GENERIC;
   const bool plain = !ep->out2 && !ep->aux && !ep->resid && !ep->accumulate && ep->act == B2C_ACT_NONE && ep->alpha == 1.f;
-  if (ep->out_dtype == B2C_BF16 && plain && ep->drop_p == 0.f) epi = EPI_BF16;
+  if (ep->out_dtype == B2C_BF16 && plain && ep->drop_p == 0.f && !ep->colsum) epi = EPI_BF16;
   else if (ep->out_dtype == B2C_BF16 && ep->act == B2C_ACT_SILU && !ep->resid && ep->alpha == 1.f) epi = EPI_SILU;
   else if (ep->out_dtype == B2C_F32 && ep->resid && !ep->accumulate && ep->act == B2C_ACT_NONE && !ep->out2) epi = EPI_RESID;
   else if (ep->out_dtype == B2C_BF16 && ep->act == B2C_ACT_SILU_BWD && !ep->out2 && !ep->bias && ep->alpha == 1.f) epi = EPI_SILU_BWD;
   else if (ep->out_dtype == B2C_F32 && ep->accumulate && ep->act == B2C_ACT_NONE && !ep->out2 && !ep->bias && ep->drop_p == 0.f) epi = EPI_ACCUM;
-#define B2C_LAUNCH(BN_, AM, BMN, E, C2) return launch_gemm<BN_, AM, BMN, E, C2>(ta, tb, p, st)
+  const bool extra = ep->out2 || ep->colsum || ep->drop_p > 0.f;
+#define B2C_LAUNCH(BN_, AM, BMN, E, C2)                                                           \
+  do {                                                                                             \
+    if (extra) return launch_gemm<BN_, AM, BMN, E, C2, true>(ta, tb, p, st);                       \
+    return launch_gemm<BN_, AM, BMN, E, C2, false>(ta, tb, p, st);                                 \
+  } while (0)
+#define B2C_LAUNCH1(BN_, AM, BMN, E, C2) return launch_gemm<BN_, AM, BMN, E, C2, true>(ta, tb, p, st)
 #define B2C_DISPATCH(BN_, C2)                                                                      \
   if (bn == BN_ && cta2 == C2) {                                                                   \
     if (!a_mn && !b_mn) {                                                                          \
       if (epi == EPI_BF16) B2C_LAUNCH(BN_, false, false, EPI_BF16, C2);                            \
       if (epi == EPI_SILU) B2C_LAUNCH(BN_, false, false, EPI_SILU, C2);                            \
       if (epi == EPI_RESID) B2C_LAUNCH(BN_, false, false, EPI_RESID, C2);                          \
-      B2C_LAUNCH(BN_, false, false, EPI_GENERIC, C2);                                              \
+      B2C_LAUNCH1(BN_, false, false, EPI_GENERIC, C2);                                             \
     }                                                                                              \
     if (!a_mn && b_mn) {                                                                           \
       if (epi == EPI_BF16) B2C_LAUNCH(BN_, false, true, EPI_BF16, C2);                             \
       if (epi == EPI_SILU_BWD) B2C_LAUNCH(BN_, false, true, EPI_SILU_BWD, C2);                     \
-      B2C_LAUNCH(BN_, false, true, EPI_GENERIC, C2);                                               \
+      B2C_LAUNCH1(BN_, false, true, EPI_GENERIC, C2);                                              \
     }                                                                                              \
     if (a_mn && b_mn) {                                                                            \
-      if (epi == EPI_ACCUM) B2C_LAUNCH(BN_, true, true, EPI_ACCUM, C2);                            \
-      B2C_LAUNCH(BN_, true, true, EPI_GENERIC, C2);                                                \
+      if (epi == EPI_ACCUM) B2C_LAUNCH1(BN_, true, true, EPI_ACCUM, C2);                           \
+      B2C_LAUNCH1(BN_, true, true, EPI_GENERIC, C2);                                               \
     }                                                                                              \
-    B2C_LAUNCH(BN_, true, false, EPI_GENERIC, C2);                                                 \
+    B2C_LAUNCH1(BN_, true, false, EPI_GENERIC, C2);                                                \
   }
   B2C_DISPATCH(64, false)
   B2C_DISPATCH(128, false)
   B2C_DISPATCH(256, false)
   B2C_DISPATCH(128, true)
   B2C_DISPATCH(256, true)
+#undef B2C_LAUNCH1
 #undef B2C_LAUNCH
 #undef B2C_DISPATCH
   return -1;
