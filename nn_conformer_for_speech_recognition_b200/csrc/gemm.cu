@@ -449,8 +449,12 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   int bn = block_n;
   bool cta2 = false;
   if (bn == 0) {
+    // measured on B200 at the Conformer-M shapes (tools/kernel_bench.py): deep-K weight gradients gain from CTA pairs
+    // (half the operand bytes per output), wide forward GEMMs from 128x256 tiles, the rest from 128x128
     static const bool allow2 = [] { const char* e = getenv("B2C_GEMM_2SM"); return !(e && e[0] == '0'); }();
-    if (allow2 && N >= 256 && M >= 256) { bn = 256; cta2 = true; }
+    if (allow2 && a_mn && b_mn && N >= 256 && M >= 256) { bn = 256; cta2 = true; }
+    else if (ep->act == B2C_ACT_SILU_BWD) bn = (N >= 128) ? 128 : 64;
+    else if (N >= 512 || (N >= 256 && K >= 512)) bn = 256;
     else bn = (N >= 128) ? 128 : 64;
   } else if (bn < 0) {
     bn = -bn;
