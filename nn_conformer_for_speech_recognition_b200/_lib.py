@@ -114,7 +114,7 @@ def call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0) -> None:
         raise kind(f"{name} failed (rc={rc}): {last_error()}")
     if _profile is not None:
         e1.record()
-        _profile.append((name, e0, e1, flops, nbytes))
+        _profile.append((name, e0, e1, flops, nbytes, args))
     LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
 
 
@@ -126,11 +126,33 @@ def profile_begin():
 
 
 def profile_end(prof):
-    """-> [(entry point, milliseconds, flops, bytes)]"""
+    """-> [(entry point, milliseconds, flops, bytes, args)]"""
     global _profile
     _profile = None
     torch.cuda.synchronize()
-    return [(n, a.elapsed_time(b), fl, nb) for n, a, b, fl, nb in prof]
+    return [(n, a.elapsed_time(b), fl, nb, args) for n, a, b, fl, nb, args in prof]
+
+
+def replay(rows, name: str, reps: int = 3):
+    """Re-issue, back to back and without any Python work in between, every recorded launch of entry point `name`
+    (same pointers, shapes and epilogues as in the instrumented step) and time the whole train with ONE CUDA-event pair
+    on the launching stream.  Returns (launches per repetition, average microseconds per launch, flops, bytes)."""
+    calls = [(r[4], r[2], r[3]) for r in rows if r[0] == name]
+    if not calls:
+        return 0, 0.0, 0.0, 0.0
+    fn = getattr(load(), name)
+    for args, _, _ in calls:
+        fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        for args, _, _ in calls:
+            fn(*args)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * len(calls))
+    return len(calls), us, sum(c[1] for c in calls), sum(c[2] for c in calls)
 
 
 _checked = False

@@ -5,7 +5,7 @@
 // called by torchaudio ConformerLayer (conformer.py:152,194-200): softmax(Q K^T / sqrt(dh) + key mask) V where
 // keys t >= lengths[b] are masked and padded QUERY rows are still computed.
 //
-// Forward, one CTA = (128-query tile, head, utterance), 128 threads, thread r <-> query row r <-> TMEM lane r:
+// Forward, one CTA = (128-query tile, head, utterance), 256 threads, two threads per query row / TMEM lane:
 //   TMA   Q tile once, then per 128-key block K_j, V_j                       (128B-swizzled smem)
 //   UMMA  S = Q K_j^T          (M128 N128 K16 x4, both operands K-major)      -> TMEM cols [0,128)
 //   regs  online softmax on the thread's row (tcgen05.ld), P -> smem as bf16 in the K-major SW128 UMMA layout
@@ -47,21 +47,24 @@ struct AttnParams {
   DropCfg drop;
 };
 
-__global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+// 256 threads: thread (row = tid & 127, half = tid >> 7) owns query row `row` and 64 of the 128 keys of every key block
+// (and 32 of the 64 output columns).  K is double-buffered and V is fetched one step ahead by TMA, so the only exposed
+// waits are the two MMAs of the current block; 96 KB smem + 256 TMEM columns -> 2 CTAs per SM.
+__global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* sQ = smem;                 // 16 KB  [128 q][64]
-  uint8_t* sK = smem + 16384;         // 16 KB  [128 keys][64]
-  uint8_t* sV = smem + 32768;         // 16 KB  [128 keys][64]
-  uint8_t* sP = smem + 49152;         // 32 KB  2 x [128 q][64 keys]
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + 81920);
-  uint64_t* bar_kv = bar_q + 1;
-  uint64_t* bar_s = bar_q + 2;
-  uint64_t* bar_o = bar_q + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 4);
+  constexpr uint32_t OFF_Q = 0, OFF_K = 16384 /*2 bufs*/, OFF_V = 49152, OFF_P = 65536, OFF_X = 98304, OFF_BAR = 99328;
+  float* sx = reinterpret_cast<float*>(smem + OFF_X);          // [2][128] row-max / row-sum exchange between halves
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* bar_k = bar_q + 1;                                 // [2]
+  uint64_t* bar_v = bar_q + 3;
+  uint64_t* bar_s = bar_q + 4;
+  uint64_t* bar_o = bar_q + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, half = tid >> 7;
   const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
   const int len = min(p.lengths[b], p.T);
   const int nkb = (len + AT_BK - 1) / AT_BK;
@@ -69,7 +72,8 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
-    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    mbar_init(bar_q, 1); mbar_init(&bar_k[0], 1); mbar_init(&bar_k[1], 1); mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     fence_barrier_init();
   }
   if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 256); }
@@ -77,63 +81,71 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 
-  if (tid == 0) {
+  if (tid == 0 && nkb > 0) {
     mbar_expect_tx(bar_q, 16384);
-    tma_load_2d(sQ, &tmQKV, bar_q, p.q_col + h * AT_DH, row_base + q0);
+    tma_load_2d(smem + OFF_Q, &tmQKV, bar_q, p.q_col + h * AT_DH, row_base + q0);
+    mbar_expect_tx(&bar_k[0], 16384);
+    tma_load_2d(smem + OFF_K, &tmQKV, &bar_k[0], p.k_col + h * AT_DH, row_base);
+    mbar_expect_tx(bar_v, 16384);
+    tma_load_2d(smem + OFF_V, &tmQKV, bar_v, p.v_col + h * AT_DH, row_base);
   }
 
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
 
-  float o[AT_DH];
+  float o[32];
 #pragma unroll
-  for (int i = 0; i < AT_DH; ++i) o[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
+  for (int i = 0; i < 32; ++i) o[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;                 // l_run: this thread's half of the row sum
   const DropCfg drop = drop_resolve(p.drop);
-  const int q_idx = q0 + tid;                           // query position inside the utterance
+  const int q_idx = q0 + row;                           // query position inside the utterance
   const uint64_t drop_row = (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad;
 
   for (int j = 0; j < nkb; ++j) {
-    const uint32_t ph = j & 1;
+    const uint32_t ph = j & 1, kb = j & 1;
     if (tid == 0) {
-      mbar_expect_tx(bar_kv, 32768);
-      tma_load_2d(sK, &tmQKV, bar_kv, p.k_col + h * AT_DH, row_base + j * AT_BK);
-      tma_load_2d(sV, &tmQKV, bar_kv, p.v_col + h * AT_DH, row_base + j * AT_BK);
+      if (j + 1 < nkb) {                                // K_{j+1} into the other buffer (its last reader, S_{j-1}, is done)
+        mbar_expect_tx(&bar_k[kb ^ 1], 16384);
+        tma_load_2d(smem + OFF_K + (kb ^ 1) * 16384, &tmQKV, &bar_k[kb ^ 1], p.k_col + h * AT_DH, row_base + (j + 1) * AT_BK);
+      }
       if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_kv, ph);
+      mbar_wait(&bar_k[kb], (j >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < AT_DH / 16; ++k)
-        umma_bf16(tmem_base, umma_desc_sw128(base + k * 32, 16, 1024), umma_desc_sw128(base + 16384 + k * 32, 16, 1024),
-                  idesc_s, k > 0 ? 1u : 0u);
+        umma_bf16(tmem_base, umma_desc_sw128(base + OFF_Q + k * 32, 16, 1024),
+                  umma_desc_sw128(base + OFF_K + kb * 16384 + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
       tc_commit(bar_s);
     }
     mbar_wait(bar_s, ph);
     tc_fence_after();
 
-    // ---- online softmax on this thread's row ----
-    const int key0 = j * AT_BK;
-    float m_blk = -INFINITY;
+    // ---- online softmax: this thread's 64 keys of its row ----
+    const int key0 = j * AT_BK + half * 64;
+    float m_loc = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < AT_BK; c += 32) {
+    for (int c = 0; c < 64; c += 32) {
       uint32_t v[32];
       __syncwarp();
-      tmem_ld32(tm_lane + c, v);
+      tmem_ld32(tm_lane + half * 64 + c, v);
       tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (key0 + c + i < len) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+        if (key0 + c + i < len) m_loc = fmaxf(m_loc, __uint_as_float(v[i]));
     }
+    sx[half * 128 + row] = m_loc;
+    __syncthreads();
+    const float m_blk = fmaxf(m_loc, sx[(half ^ 1) * 128 + row]);
     const float m_new = fmaxf(m_run, m_blk * p.scale_log2);
     const float alpha = exp2f(m_run - m_new);           // first block: exp2(-inf) = 0
     float l_blk = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < AT_BK; c += 32) {
+    for (int c = 0; c < 64; c += 32) {
       uint32_t v[32];
       __syncwarp();
-      tmem_ld32(tm_lane + c, v);
+      tmem_ld32(tm_lane + half * 64 + c, v);
       tmem_wait_ld();
       float pr[32];
 #pragma unroll
@@ -142,7 +154,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
         l_blk += e;
         pr[i] = e;
       }
-      if (p.drop.thresh16) {
+      if (drop.thresh16) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float s0, s1;
@@ -154,53 +166,60 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
       for (int g = 0; g < 4; ++g) {
         const uint4 u = make_uint4(pack_bf16(pr[g * 8], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
                                    pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
-        *reinterpret_cast<uint4*>(sP + sw128_offset(tid, c + g * 8, 128)) = u;
+        *reinterpret_cast<uint4*>(smem + OFF_P + sw128_offset(row, half * 64 + c + g * 8, 128)) = u;
       }
     }
     l_run = l_run * alpha + l_blk;
     m_run = m_new;
 #pragma unroll
-    for (int i = 0; i < AT_DH; ++i) o[i] *= alpha;
+    for (int i = 0; i < 32; ++i) o[i] *= alpha;
 
     fence_proxy_async();          // P (generic-proxy stores) -> visible to the UMMA async proxy
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
+      mbar_wait(bar_v, ph);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < AT_BK / 16; ++k)
-        umma_bf16(tmem_base + 128, umma_desc_sw128(base + 49152 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                  umma_desc_sw128(base + 32768 + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+        umma_bf16(tmem_base + 128, umma_desc_sw128(base + OFF_P + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                  umma_desc_sw128(base + OFF_V + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
       tc_commit(bar_o);
     }
     mbar_wait(bar_o, ph);
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < AT_DH; c += 32) {
+    if (tid == 0 && j + 1 < nkb) {                      // V_{j+1}: the PV product that read V_j has retired
+      mbar_expect_tx(bar_v, 16384);
+      tma_load_2d(smem + OFF_V, &tmQKV, bar_v, p.v_col + h * AT_DH, row_base + (j + 1) * AT_BK);
+    }
+    {
       uint32_t v[32];
       __syncwarp();
-      tmem_ld32(tm_lane + 128 + c, v);
+      tmem_ld32(tm_lane + 128 + half * 32, v);
       tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(v[i]);
+      for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v[i]);
     }
     tc_fence_before();
-    __syncthreads();              // sK/sV/sP and both TMEM regions are free for the next block
+    __syncthreads();              // sP and both TMEM regions are free for the next block
   }
 
-  // len == 0 -> l_run == 0 -> 0/0 = NaN, the same value torch's softmax over an all-masked row gives
+  // combine the two halves' row sums.  len == 0 -> l == 0 -> 0/0 = NaN, what torch's softmax gives for an all-masked row
+  sx[half * 128 + row] = l_run;
+  __syncthreads();
+  const float l_tot = l_run + sx[(half ^ 1) * 128 + row];
   if (q_idx < p.T) {
-    const float inv_l = 1.f / l_run;
-    __nv_bfloat16* dst = p.out + static_cast<int64_t>(row_base + q_idx) * p.ld_out + h * AT_DH;
+    const float inv_l = 1.f / l_tot;
+    __nv_bfloat16* dst = p.out + static_cast<int64_t>(row_base + q_idx) * p.ld_out + h * AT_DH + half * 32;
 #pragma unroll
-    for (int g = 0; g < AT_DH / 8; ++g) {
+    for (int g = 0; g < 4; ++g) {
       const uint4 u = make_uint4(pack_bf16(o[g * 8] * inv_l, o[g * 8 + 1] * inv_l),
                                  pack_bf16(o[g * 8 + 2] * inv_l, o[g * 8 + 3] * inv_l),
                                  pack_bf16(o[g * 8 + 4] * inv_l, o[g * 8 + 5] * inv_l),
                                  pack_bf16(o[g * 8 + 6] * inv_l, o[g * 8 + 7] * inv_l));
       *reinterpret_cast<uint4*>(dst + g * 8) = u;
     }
-    if (p.lse) p.lse[static_cast<int64_t>(b * p.H + h) * p.T + q_idx] = m_run + log2f(l_run);
+    if (p.lse && half == 0) p.lse[static_cast<int64_t>(b * p.H + h) * p.T + q_idx] = m_run + log2f(l_tot);
   }
   __syncthreads();
   if (warp == 0) {
@@ -210,7 +229,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   }
 }
 
-constexpr uint32_t ATTN_FWD_SMEM = 81920 + 64 + 1024;
+constexpr uint32_t ATTN_FWD_SMEM = 99328 + 64 + 1024;
 // ================================================================================================
 // backward
 // ================================================================================================
@@ -300,7 +319,7 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
 //   UMMA  S = Q_i K_j^T, dP = dO_i V_j^T                  -> TMEM [0,128) and [128,256)
 //   regs  P = exp2(S*scale - lse), dS = P o (dP - delta)   -> smem (bf16, K-major SW128), dropout regenerated
 //   UMMA  dV += P^T dO_i, dK += dS^T Q_i  (accumulate over i in TMEM), dQp = dS K_j (fresh)
-//   regs  dQ[i] += dQp  as fp32 red.global.add.v4 (each (i,j) pair contributes once; a cast kernel makes it bf16)
+//   regs  dQp -> this key block's fp32 partial slab (plain 128 B stores); attn_dq_cast_kernel sums the slabs -> bf16
 // S and dP are recomputed here from the saved log-sum-exp, so no T x T tensor ever reaches HBM.
 __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                           const __grid_constant__ CUtensorMap tmDO,
@@ -324,7 +343,15 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
   // this thread stores 32 of the 64 head-dim columns of its key row
   __nv_bfloat16* dk_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.k_col + h * AT_DH + chalf * 32 : nullptr;
   __nv_bfloat16* dv_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.v_col + h * AT_DH + chalf * 32 : nullptr;
-  if (key0 >= len) {                       // every key of this block is masked: P = 0 -> dK = dV = 0, no dQ contribution
+  if (key0 >= len) {                       // every key of this block is masked: P = 0 -> dK = dV = 0, dQ partial = 0
+    for (int i = 0; i < (p.T + AT_BQ - 1) / AT_BQ; ++i) {
+      const int q_idx = i * AT_BQ + row;
+      if (q_idx < p.T) {
+        float* dst = dq_f32 + (static_cast<int64_t>(j) * p.B * p.T + row_base + q_idx) * (p.H * AT_DH) + h * AT_DH + chalf * 32;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(dst + g * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     if (dk_dst) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -414,13 +441,13 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
       tmem_ld32(tm_lane + TM_DQ + chalf * 32, v);
       tmem_wait_ld();
       if (q_idx < p.T) {
-        float* dst = dq_f32 + static_cast<int64_t>(row_base + q_idx) * (p.H * AT_DH) + h * AT_DH + chalf * 32;
+        // plain 128-byte stores into THIS key block's partial-dQ slab (summed by attn_dq_cast_kernel): fp32 atomics
+        // on 75 MB per layer were the bottleneck of the first version
+        float* dst = dq_f32 + (static_cast<int64_t>(j) * p.B * p.T + row_base + q_idx) * (p.H * AT_DH) + h * AT_DH + chalf * 32;
 #pragma unroll
         for (int g = 0; g < 8; ++g)
-          asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + g * 4), "f"(__uint_as_float(v[g * 4])),
-                       "f"(__uint_as_float(v[g * 4 + 1])), "f"(__uint_as_float(v[g * 4 + 2])),
-                       "f"(__uint_as_float(v[g * 4 + 3]))
-                       : "memory");
+          *reinterpret_cast<float4*>(dst + g * 4) = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
+                                                                __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
       }
     }
     tc_fence_before();
@@ -463,14 +490,20 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
   }
 }
 
-// dq fp32 [rows, H*64] -> the Q slab of dqkv (bf16, pitch ld)
+// dQ = sum over key blocks of the fp32 partial slabs [nkb][rows, H*64] -> the Q slab of dqkv (bf16, pitch ld)
 __global__ void __launch_bounds__(256) attn_dq_cast_kernel(const float* __restrict__ dq, __nv_bfloat16* __restrict__ dqkv,
-                                                          int64_t rows, int cols, int64_t ld, int q_col) {
+                                                          int64_t rows, int cols, int64_t ld, int q_col, int nkb) {
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
-  if (i >= rows * cols) return;
+  const int64_t n = rows * cols;
+  if (i >= n) return;
   const int64_t r = i / cols;
   const int c = static_cast<int>(i % cols);
-  const float4 a = *reinterpret_cast<const float4*>(dq + i), b4 = *reinterpret_cast<const float4*>(dq + i + 4);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
+  for (int k = 0; k < nkb; ++k) {
+    const float4 x = *reinterpret_cast<const float4*>(dq + k * n + i), y = *reinterpret_cast<const float4*>(dq + k * n + i + 4);
+    a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+    b4.x += y.x; b4.y += y.y; b4.z += y.z; b4.w += y.w;
+  }
   *reinterpret_cast<uint4*>(dqkv + r * ld + q_col + c) =
       make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b4.x, b4.y), pack_bf16(b4.z, b4.w));
 }
@@ -505,7 +538,7 @@ extern "C" int b2c_attention_fwd(const void* qkv, int64_t ld, int64_t k_off, int
   p.Tpad = (T + 1) & ~1;
   p.drop = make_drop(drop_p, drop_seed);
   dim3 grid((T + AT_BQ - 1) / AT_BQ, H, B);
-  attn_fwd_kernel<<<grid, 128, ATTN_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
+  attn_fwd_kernel<<<grid, 256, ATTN_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -531,7 +564,6 @@ extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int
   const int64_t n = rows * H;
   attn_delta_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), ld_out, delta, B, T, H);
-  B2C_CUDA(cudaMemsetAsync(dq_f32, 0, static_cast<size_t>(rows) * H * AT_DH * sizeof(float), st));
   AttnBwdParams p;
   p.lengths = lengths; p.lse = lse; p.delta = delta; p.dqkv = static_cast<__nv_bfloat16*>(dqkv); p.ld = ld;
   p.B = B; p.T = T; p.H = H;
@@ -543,7 +575,7 @@ extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int
   attn_bwd_kernel<<<grid, 256, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
   const int64_t n8 = rows * H * AT_DH / 8;
   attn_dq_cast_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, st>>>(dq_f32, static_cast<__nv_bfloat16*>(dqkv),
-                                                                               rows, H * AT_DH, ld, 0);
+                                                                               rows, H * AT_DH, ld, 0, (T + AT_BK - 1) / AT_BK);
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
