@@ -288,12 +288,12 @@ def main():
     tgt_lens = torch.full((B,), TGT_LEN, device=dev)
     x_dev = x_host.to(dev)
     params = list(enc.parameters()) + list(head.parameters())
-    sync = dp.GradSync(enc, head, world) if world > 1 else None
+    sync = dp.GradSync(enc, head, world=world) if world > 1 else None
     if sync is not None:
         sync.broadcast_parameters()
 
     from nn_conformer_for_speech_recognition_b200.specaugment import SpecAugPlan
-    use_graph = not args.no_graph and world == 1
+    use_graph = not args.no_graph          # per-rank graphs: the gradient all-reduce runs between backward and optimizer, outside them
     plan = SpecAugPlan(hp, B, dev, mode="paper")
     tgt_lens_host = [TGT_LEN] * B
     out_lens_host = [Tp] * B
