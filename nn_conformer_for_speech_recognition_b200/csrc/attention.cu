@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
   for (int i = 0; i < 32; ++i) o[i] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;                 // l_run: this thread's half of the row sum
   const DropCfg drop = drop_resolve(p.drop);
+  const float inv_keep8 = 256.f / (256.f - static_cast<float>(drop.thresh16 >> 8));
   const int q_idx = q0 + row;                           // query position inside the utterance
-  const uint64_t drop_row = (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad;
+  const uint64_t drop_row = (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad;   // Tpad % 4 == 0
 
   for (int j = 0; j < nkb; ++j) {
     const uint32_t ph = j & 1, kb = j & 1;
@@ -123,6 +124,8 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
     tc_fence_after();
 
     // ---- online softmax: this thread's 64 keys of its row ----
+    // chunks that lie entirely below `len` (all but the utterance's last one) take a predicate-free path: the softmax
+    // is issue-bound, every instruction per score counts
     const int key0 = j * AT_BK + half * 64;
     float m_loc = -INFINITY;
 #pragma unroll 1
@@ -131,15 +134,20 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
       __syncwarp();
       tmem_ld32(tm_lane + half * 64 + c, v);
       tmem_wait_ld();
+      if (key0 + c + 32 <= len) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (key0 + c + i < len) m_loc = fmaxf(m_loc, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) m_loc = fmaxf(m_loc, __uint_as_float(v[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (key0 + c + i < len) m_loc = fmaxf(m_loc, __uint_as_float(v[i]));
+      }
     }
     sx[half * 128 + row] = m_loc;
     __syncthreads();
     const float m_blk = fmaxf(m_loc, sx[(half ^ 1) * 128 + row]);
     const float m_new = fmaxf(m_run, m_blk * p.scale_log2);
-    const float alpha = exp2f(m_run - m_new);           // first block: exp2(-inf) = 0
+    const float alpha = ex2_approx(m_run - m_new);      // first block: 2^(-inf) = 0
     float l_blk = 0.f;
 #pragma unroll 1
     for (int c = 0; c < 64; c += 32) {
@@ -148,18 +156,25 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
       tmem_ld32(tm_lane + half * 64 + c, v);
       tmem_wait_ld();
       float pr[32];
+      if (key0 + c + 32 <= len) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float e = (key0 + c + i < len) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new) : 0.f;
-        l_blk += e;
-        pr[i] = e;
+        for (int i = 0; i < 32; ++i) {
+          pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+          l_blk += pr[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          pr[i] = (key0 + c + i < len) ? ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new)) : 0.f;
+          l_blk += pr[i];
+        }
       }
       if (drop.thresh16) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float s0, s1;
-          drop_scale2(drop, drop_row + key0 + c + i, s0, s1);
-          pr[i] *= s0; pr[i + 1] *= s1;
+        for (int i = 0; i < 32; i += 4) {
+          float sc[4];
+          drop_scale4(drop, drop_row + key0 + c + i, inv_keep8, sc);
+          pr[i] *= sc[0]; pr[i + 1] *= sc[1]; pr[i + 2] *= sc[2]; pr[i + 3] *= sc[3];
         }
       }
 #pragma unroll
@@ -278,8 +293,10 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint32_t tm_s, uint32_t tm_dp, uint8_t* sP,
                                                    uint8_t* sdS, int row, int chalf, int q_idx, int key0, int len,
                                                    float lse_r, float delta_r, uint64_t drop_row) {
-  const bool q_ok = q_idx < p.T;
+  // rows past the utterance end contribute nothing: with lse = +inf their probabilities are exactly 2^(-inf) = 0,
+  // no per-element predicate needed (lse_r is set by the caller)
   const DropCfg drop = drop_resolve(p.drop);
+  const float inv_keep8 = 256.f / (256.f - static_cast<float>(drop.thresh16 >> 8));
 #pragma unroll 1
   for (int cc = 0; cc < 64; cc += 32) {
     const int c = chalf * 64 + cc;
@@ -289,16 +306,17 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
     tmem_ld32(tm_dp + c, vd);
     tmem_wait_ld();
     float pr[32], ds[32];
+    const bool full = key0 + c + 32 <= len;
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float dsc[2] = {1.f, 1.f};
-      if (drop.thresh16) drop_scale2(drop, drop_row + key0 + c + i, dsc[0], dsc[1]);
+    for (int i = 0; i < 32; i += 4) {
+      float dsc[4] = {1.f, 1.f, 1.f, 1.f};
+      if (drop.thresh16) drop_scale4(drop, drop_row + key0 + c + i, inv_keep8, dsc);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const bool ok = q_ok && (key0 + c + i + e < len);
-        const float pv = ok ? exp2f(__uint_as_float(vs[i + e]) * p.scale_log2 - lse_r) : 0.f;
+      for (int e = 0; e < 4; ++e) {
+        float pv = ex2_approx(fmaf(__uint_as_float(vs[i + e]), p.scale_log2, -lse_r));
+        if (!full && key0 + c + i + e >= len) pv = 0.f;
         pr[i + e] = pv * dsc[e];
-        ds[i + e] = pv * (__uint_as_float(vd[i + e]) * dsc[e] - delta_r) * p.scale;
+        ds[i + e] = (pv * p.scale) * fmaf(__uint_as_float(vd[i + e]), dsc[e], -delta_r);
       }
     }
 #pragma unroll
@@ -409,7 +427,7 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
       tc_commit(bar_s);
     }
     const int64_t stat = static_cast<int64_t>(b * p.H + h) * p.T + min(q_idx, p.T - 1);
-    const float lse_r = p.lse[stat], delta_r = p.delta[stat];
+    const float lse_r = q_idx < p.T ? p.lse[stat] : INFINITY, delta_r = q_idx < p.T ? p.delta[stat] : 0.f;
     mbar_wait(bar_s, ph);
     tc_fence_after();
     attn_bwd_tile_math(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P, smem + OFF_DS, row, chalf, q_idx, key0, len,
@@ -535,7 +553,7 @@ extern "C" int b2c_attention_fwd(const void* qkv, int64_t ld, int64_t k_off, int
   p.B = B; p.T = T; p.H = H;
   p.q_col = 0; p.k_col = static_cast<int>(k_off); p.v_col = static_cast<int>(v_off);
   p.scale_log2 = scale * LOG2E;
-  p.Tpad = (T + 1) & ~1;
+  p.Tpad = (T + 3) & ~3;
   p.drop = make_drop(drop_p, drop_seed);
   dim3 grid((T + AT_BQ - 1) / AT_BQ, H, B);
   attn_fwd_kernel<<<grid, 256, ATTN_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
@@ -569,7 +587,7 @@ extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int
   p.B = B; p.T = T; p.H = H;
   p.q_col = 0; p.k_col = static_cast<int>(k_off); p.v_col = static_cast<int>(v_off);
   p.scale = scale; p.scale_log2 = scale * LOG2E;
-  p.Tpad = (T + 1) & ~1;
+  p.Tpad = (T + 3) & ~3;
   p.drop = make_drop(drop_p, drop_seed);
   dim3 grid((T + AT_BK - 1) / AT_BK, H, B);
   attn_bwd_kernel<<<grid, 256, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);

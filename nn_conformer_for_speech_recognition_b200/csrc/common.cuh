@@ -104,6 +104,21 @@ __device__ __forceinline__ DropCfg drop_resolve(DropCfg d) {
   if (d.thresh16 && d.epoch) d.seed += (*d.epoch) * 0x9E3779B97F4A7C15ull;
   return d;
 }
+// single-instruction 2^x (MUFU.EX2, flush-to-zero): exp2f() adds range fix-ups the softmax does not need
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// scales for elements idx (multiple of 4) .. idx+3 from ONE hash, 8 bits per decision (attention probabilities: the
+// per-element budget there is a handful of instructions).  thresh8 = thresh16 >> 8; exact for p = 0.5, and
+// inv_keep8 = 256 / (256 - thresh8) keeps the mask unbiased for any p.
+__device__ __forceinline__ void drop_scale4(const DropCfg& d, uint64_t idx4, float inv_keep8, float* s) {
+  const uint32_t h = drop_hash32(d.seed ^ 0x5851F42D4C957F2Dull, idx4 >> 2);
+  const uint32_t t8 = d.thresh16 >> 8;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s[j] = ((h >> (8 * j)) & 0xFFu) >= t8 ? inv_keep8 : 0.f;
+}
 // scales for elements idx (even) and idx+1
 __device__ __forceinline__ void drop_scale2(const DropCfg& d, uint64_t idx_even, float& s0, float& s1) {
   const uint32_t h = drop_hash32(d.seed, idx_even >> 1);
