@@ -287,59 +287,54 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
   delta[(static_cast<int64_t>(b_) * H + h) * T + t] = acc;
 }
 
-// Thread (row = tid & 127, column half = tid >> 7) turns 64 columns of its S row and dP row (TMEM) into
+// Thread (row = tid & 127, column quarter cq = tid >> 7) turns 32 columns of its S row and dP row (TMEM) into
 // P (optionally dropped, feeds dV) and dS = P o (dP*drop - delta) * scale, both written as bf16 [q][key] K-major
-// SW128 tiles (2 x [128][64]; column half h is exactly 64-column block h).
+// SW128 tiles (2 x [128][64]).  Rows past the utterance end contribute nothing: with lse = +inf their probabilities
+// are exactly 2^(-inf) = 0, no per-element predicate needed (lse_r is set by the caller).
 __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint32_t tm_s, uint32_t tm_dp, uint8_t* sP,
-                                                   uint8_t* sdS, int row, int chalf, int q_idx, int key0, int len,
-                                                   float lse_r, float delta_r, uint64_t drop_row) {
-  // rows past the utterance end contribute nothing: with lse = +inf their probabilities are exactly 2^(-inf) = 0,
-  // no per-element predicate needed (lse_r is set by the caller)
+                                                   uint8_t* sdS, int row, int cq, int key0, int len, float lse_r,
+                                                   float delta_r, uint64_t drop_row) {
   const DropCfg drop = drop_resolve(p.drop);
   const float inv_keep8 = 256.f / (256.f - static_cast<float>(drop.thresh16 >> 8));
-#pragma unroll 1
-  for (int cc = 0; cc < 64; cc += 32) {
-    const int c = chalf * 64 + cc;
-    uint32_t vs[32], vd[32];
-    __syncwarp();
-    tmem_ld32(tm_s + c, vs);
-    tmem_ld32(tm_dp + c, vd);
-    tmem_wait_ld();
-    float pr[32], ds[32];
-    const bool full = key0 + c + 32 <= len;
+  const int c = cq * 32;
+  uint32_t vs[32], vd[32];
+  __syncwarp();
+  tmem_ld32(tm_s + c, vs);
+  tmem_ld32(tm_dp + c, vd);
+  tmem_wait_ld();
+  const bool full = key0 + c + 32 <= len;
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
+  for (int g = 0; g < 4; ++g) {
+    float pr[8], ds[8];
+#pragma unroll
+    for (int i4 = 0; i4 < 8; i4 += 4) {
+      const int i = g * 8 + i4;
       float dsc[4] = {1.f, 1.f, 1.f, 1.f};
       if (drop.thresh16) drop_scale4(drop, drop_row + key0 + c + i, inv_keep8, dsc);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float pv = ex2_approx(fmaf(__uint_as_float(vs[i + e]), p.scale_log2, -lse_r));
         if (!full && key0 + c + i + e >= len) pv = 0.f;
-        pr[i + e] = pv * dsc[e];
-        ds[i + e] = (pv * p.scale) * fmaf(__uint_as_float(vd[i + e]), dsc[e], -delta_r);
+        pr[i4 + e] = pv * dsc[e];
+        ds[i4 + e] = (pv * p.scale) * fmaf(__uint_as_float(vd[i + e]), dsc[e], -delta_r);
       }
     }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const uint32_t off = sw128_offset(row, c + g * 8, 128);
-      *reinterpret_cast<uint4*>(sP + off) =
-          make_uint4(pack_bf16(pr[g * 8], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
-                     pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
-      *reinterpret_cast<uint4*>(sdS + off) =
-          make_uint4(pack_bf16(ds[g * 8], ds[g * 8 + 1]), pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]),
-                     pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]), pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]));
-    }
+    const uint32_t off = sw128_offset(row, c + g * 8, 128);
+    *reinterpret_cast<uint4*>(sP + off) = make_uint4(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]),
+                                                     pack_bf16(pr[4], pr[5]), pack_bf16(pr[6], pr[7]));
+    *reinterpret_cast<uint4*>(sdS + off) = make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]),
+                                                      pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
   }
 }
 
-// One kernel for dQ, dK, dV.  CTA = (128-key block j, head, utterance), 256 threads (two per tile row, 64 columns
-// each), loops over the utterance's query blocks i with Q_i / dO_i double-buffered by TMA:
+// One kernel for dQ, dK, dV.  CTA = (128-key block j, head, utterance), 512 threads (four per tile row, 32 columns
+// each: the tile math is latency bound, 4 warps per scheduler hide it), loops over the utterance's query blocks i with Q_i / dO_i double-buffered by TMA:
 //   UMMA  S = Q_i K_j^T, dP = dO_i V_j^T                  -> TMEM [0,128) and [128,256)
 //   regs  P = exp2(S*scale - lse), dS = P o (dP - delta)   -> smem (bf16, K-major SW128), dropout regenerated
 //   UMMA  dV += P^T dO_i, dK += dS^T Q_i  (accumulate over i in TMEM), dQp = dS K_j (fresh)
 //   regs  dQp -> this key block's fp32 partial slab (plain 128 B stores); attn_dq_cast_kernel sums the slabs -> bf16
 // S and dP are recomputed here from the saved log-sum-exp, so no T x T tensor ever reaches HBM.
-__global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
+__global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                           const __grid_constant__ CUtensorMap tmDO,
                                                           const AttnBwdParams p, float* __restrict__ dq_f32) {
   extern __shared__ uint8_t smem_raw[];
@@ -353,26 +348,26 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
   uint64_t* bar_acc = bar_kv + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 5);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int row = tid & 127, chalf = tid >> 7;
+  const int row = tid & 127, cq = tid >> 7;          // cq: which 32 tile columns / 16 head-dim columns this thread owns
   const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int len = min(p.lengths[b], p.T);
   const int key0 = j * AT_BK, row_base = b * p.T;
   const int key_idx = key0 + row;
-  // this thread stores 32 of the 64 head-dim columns of its key row
-  __nv_bfloat16* dk_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.k_col + h * AT_DH + chalf * 32 : nullptr;
-  __nv_bfloat16* dv_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.v_col + h * AT_DH + chalf * 32 : nullptr;
+  // this thread stores 16 of the 64 head-dim columns of its key row
+  __nv_bfloat16* dk_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.k_col + h * AT_DH + cq * 16 : nullptr;
+  __nv_bfloat16* dv_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.v_col + h * AT_DH + cq * 16 : nullptr;
   if (key0 >= len) {                       // every key of this block is masked: P = 0 -> dK = dV = 0, dQ partial = 0
     for (int i = 0; i < (p.T + AT_BQ - 1) / AT_BQ; ++i) {
       const int q_idx = i * AT_BQ + row;
       if (q_idx < p.T) {
-        float* dst = dq_f32 + (static_cast<int64_t>(j) * p.B * p.T + row_base + q_idx) * (p.H * AT_DH) + h * AT_DH + chalf * 32;
+        float* dst = dq_f32 + (static_cast<int64_t>(j) * p.B * p.T + row_base + q_idx) * (p.H * AT_DH) + h * AT_DH + cq * 16;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(dst + g * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(dst + g * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     if (dk_dst) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < 2; ++g) {
         reinterpret_cast<uint4*>(dk_dst)[g] = make_uint4(0, 0, 0, 0);
         reinterpret_cast<uint4*>(dv_dst)[g] = make_uint4(0, 0, 0, 0);
       }
@@ -430,7 +425,7 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
     const float lse_r = q_idx < p.T ? p.lse[stat] : INFINITY, delta_r = q_idx < p.T ? p.delta[stat] : 0.f;
     mbar_wait(bar_s, ph);
     tc_fence_after();
-    attn_bwd_tile_math(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P, smem + OFF_DS, row, chalf, q_idx, key0, len,
+    attn_bwd_tile_math(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P, smem + OFF_DS, row, cq, key0, len,
                        lse_r, delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad);
     fence_proxy_async();
     tc_fence_before();
@@ -454,16 +449,16 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
     mbar_wait(bar_acc, ph);                // all three products done: smem tiles and S/dP are free again
     tc_fence_after();
     {
-      uint32_t v[32];
+      uint32_t v[16];
       __syncwarp();
-      tmem_ld32(tm_lane + TM_DQ + chalf * 32, v);
+      tmem_ld16(tm_lane + TM_DQ + cq * 16, v);
       tmem_wait_ld();
       if (q_idx < p.T) {
-        // plain 128-byte stores into THIS key block's partial-dQ slab (summed by attn_dq_cast_kernel): fp32 atomics
-        // on 75 MB per layer were the bottleneck of the first version
-        float* dst = dq_f32 + (static_cast<int64_t>(j) * p.B * p.T + row_base + q_idx) * (p.H * AT_DH) + h * AT_DH + chalf * 32;
+        // plain stores into THIS key block's partial-dQ slab (summed by attn_dq_cast_kernel): fp32 atomics on 75 MB per
+        // layer were the bottleneck of the first version
+        float* dst = dq_f32 + (static_cast<int64_t>(j) * p.B * p.T + row_base + q_idx) * (p.H * AT_DH) + h * AT_DH + cq * 16;
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
+        for (int g = 0; g < 4; ++g)
           *reinterpret_cast<float4*>(dst + g * 4) = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
                                                                 __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
       }
@@ -473,13 +468,13 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
   }
   tc_fence_after();
   {
-    uint32_t v[32];
+    uint32_t v[16];
     __syncwarp();
-    tmem_ld32(tm_lane + TM_DV + chalf * 32, v);
+    tmem_ld16(tm_lane + TM_DV + cq * 16, v);
     tmem_wait_ld();
     if (dv_dst) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+      for (int g = 0; g < 2; ++g)
         reinterpret_cast<uint4*>(dv_dst)[g] =
             make_uint4(pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
                        pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
@@ -487,11 +482,11 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
                        pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
     }
     __syncwarp();
-    tmem_ld32(tm_lane + TM_DK + chalf * 32, v);
+    tmem_ld16(tm_lane + TM_DK + cq * 16, v);
     tmem_wait_ld();
     if (dk_dst) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+      for (int g = 0; g < 2; ++g)
         reinterpret_cast<uint4*>(dk_dst)[g] =
             make_uint4(pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
                        pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
@@ -590,7 +585,7 @@ extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int
   p.Tpad = (T + 3) & ~3;
   p.drop = make_drop(drop_p, drop_seed);
   dim3 grid((T + AT_BK - 1) / AT_BK, H, B);
-  attn_bwd_kernel<<<grid, 256, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
+  attn_bwd_kernel<<<grid, 512, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
   const int64_t n8 = rows * H * AT_DH / 8;
   attn_dq_cast_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, st>>>(dq_f32, static_cast<__nv_bfloat16*>(dqkv),
                                                                                rows, H * AT_DH, ld, 0, (T + AT_BK - 1) / AT_BK);
