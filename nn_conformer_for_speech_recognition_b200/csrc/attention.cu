@@ -259,6 +259,7 @@ struct AttnBwdParams {
   float scale, scale_log2;
   int Tpad;
   DropCfg drop;
+  void* delta_dbg;         // only used by -DB2C_ATTN_TIMING builds (cycle stamps of one CTA)
 };
 
 // delta[b,h,t] = sum_c dO[row, h*64+c] * O[row, h*64+c]
@@ -327,6 +328,12 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
   }
 }
 
+#ifdef B2C_ATTN_TIMING
+#define B2C_TS(slot) if ((tid == 0 || tid == 300) && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 1) \
+    reinterpret_cast<long long*>(p.delta_dbg)[(tid ? 64 : 0) + i * 8 + (slot)] = clock64();
+#else
+#define B2C_TS(slot)
+#endif
 // One kernel for dQ, dK, dV.  CTA = (128-key block j, head, utterance), 512 threads (four per tile row, 32 columns
 // each: the tile math is latency bound, 4 warps per scheduler hide it), loops over the utterance's query blocks i with Q_i / dO_i double-buffered by TMA:
 //   UMMA  S = Q_i K_j^T, dP = dO_i V_j^T                  -> TMEM [0,128) and [128,256)
@@ -402,34 +409,45 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant_
   constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, false, false);
   constexpr uint32_t idesc_mm = umma_idesc_bf16(128, 64, true, true);
   constexpr uint32_t idesc_km = umma_idesc_bf16(128, 64, false, true);
+  // S = Q K^T and dP = dO V^T of query block i (one elected thread); their accumulators are free as soon as the tile
+  // math of block i-1 has read them, so they are issued one block AHEAD, right behind the dV/dK/dQ products
+  auto issue_s_dp = [&](int i) {
+    const uint32_t bf = i & 1;
+    const uint32_t q_addr = base + OFF_Q + bf * 16384, do_addr = base + OFF_DO + bf * 16384;
+    mbar_wait(&bar_q[bf], (i >> 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem_base + TM_S, umma_desc_sw128(q_addr + k * 32, 16, 1024),
+                umma_desc_sw128(base + OFF_K + k * 32, 16, 1024), idesc_kk, k > 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem_base + TM_DP, umma_desc_sw128(do_addr + k * 32, 16, 1024),
+                umma_desc_sw128(base + OFF_V + k * 32, 16, 1024), idesc_kk, k > 0);
+    tc_commit(bar_s);
+  };
+  if (tid == 0) {
+    if (nqb > 1) load_q(1);
+    mbar_wait(bar_kv, 0);
+    issue_s_dp(0);
+  }
   for (int i = 0; i < nqb; ++i) {
     const uint32_t ph = i & 1, bf = i & 1;
+    B2C_TS(0)
     const uint32_t q_addr = base + OFF_Q + bf * 16384, do_addr = base + OFF_DO + bf * 16384;
     const int q_idx = i * AT_BQ + row;
-    if (tid == 0) {
-      if (i + 1 < nqb) load_q(i + 1);      // buffer (i+1)&1 was released by iteration i-1's bar_acc wait
-      if (i == 0) mbar_wait(bar_kv, 0);
-      mbar_wait(&bar_q[bf], (i >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 4; ++k)          // S = Q K^T
-        umma_bf16(tmem_base + TM_S, umma_desc_sw128(q_addr + k * 32, 16, 1024),
-                  umma_desc_sw128(base + OFF_K + k * 32, 16, 1024), idesc_kk, k > 0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)          // dP = dO V^T
-        umma_bf16(tmem_base + TM_DP, umma_desc_sw128(do_addr + k * 32, 16, 1024),
-                  umma_desc_sw128(base + OFF_V + k * 32, 16, 1024), idesc_kk, k > 0);
-      tc_commit(bar_s);
-    }
     const int64_t stat = static_cast<int64_t>(b * p.H + h) * p.T + min(q_idx, p.T - 1);
     const float lse_r = q_idx < p.T ? p.lse[stat] : INFINITY, delta_r = q_idx < p.T ? p.delta[stat] : 0.f;
     mbar_wait(bar_s, ph);
     tc_fence_after();
+    B2C_TS(1)
     attn_bwd_tile_math(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P, smem + OFF_DS, row, cq, key0, len,
                        lse_r, delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad);
+    B2C_TS(2)
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    B2C_TS(3)
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
@@ -445,9 +463,13 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant_
         umma_bf16(tmem_base + TM_DQ, umma_desc_sw128(base + OFF_DS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
                   umma_desc_sw128(base + OFF_K + k * 2048, 8192, 1024), idesc_km, k > 0);
       tc_commit(bar_acc);
+      if (i + 1 < nqb) issue_s_dp(i + 1);  // queued behind the three products: runs while the CTA drains dQ below
     }
-    mbar_wait(bar_acc, ph);                // all three products done: smem tiles and S/dP are free again
+    B2C_TS(4)
+    mbar_wait(bar_acc, ph);                // all three products done: P/dS and this block's Q/dO buffer are free again
     tc_fence_after();
+    if (tid == 0 && i + 2 < nqb) load_q(i + 2);
+    B2C_TS(5)
     {
       uint32_t v[16];
       __syncwarp();
@@ -463,8 +485,10 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant_
                                                                 __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
       }
     }
+    B2C_TS(6)
     tc_fence_before();
     __syncthreads();
+    B2C_TS(7)
   }
   tc_fence_after();
   {
@@ -584,6 +608,7 @@ extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int
   p.scale = scale; p.scale_log2 = scale * LOG2E;
   p.Tpad = (T + 3) & ~3;
   p.drop = make_drop(drop_p, drop_seed);
+  p.delta_dbg = dq_f32;     // timing builds scribble cycle stamps over the head of the dQ workspace
   dim3 grid((T + AT_BK - 1) / AT_BK, H, B);
   attn_bwd_kernel<<<grid, 512, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
   const int64_t n8 = rows * H * AT_DH / 8;
