@@ -355,6 +355,13 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant_
   uint64_t* bar_acc = bar_kv + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 5);
   const int tid = threadIdx.x, warp = tid >> 5;
+#ifdef B2C_ATTN_TIMING
+#define B2C_TK(slot) if (tid == 0 && blockIdx.x == 1 && blockIdx.y == 1 && (blockIdx.z == 1 || blockIdx.z == 40)) \
+    reinterpret_cast<long long*>(p.delta_dbg)[128 + (blockIdx.z == 40 ? 16 : 0) + (slot)] = clock64();
+#else
+#define B2C_TK(slot)
+#endif
+  B2C_TK(0)
   const int row = tid & 127, cq = tid >> 7;          // cq: which 32 tile columns / 16 head-dim columns this thread owns
   const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int len = min(p.lengths[b], p.T);
@@ -391,6 +398,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  B2C_TK(1)
   const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
   const int nqb = (p.T + AT_BQ - 1) / AT_BQ;
@@ -429,6 +437,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant_
   if (tid == 0) {
     if (nqb > 1) load_q(1);
     mbar_wait(bar_kv, 0);
+    B2C_TK(2)
     issue_s_dp(0);
   }
   for (int i = 0; i < nqb; ++i) {
@@ -491,6 +500,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant_
     B2C_TS(7)
   }
   tc_fence_after();
+  B2C_TK(3)
   {
     uint32_t v[16];
     __syncwarp();
@@ -520,11 +530,13 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  B2C_TK(4)
   if (warp == 0) {
     tc_fence_after();
     __syncwarp();
     tmem_dealloc(tmem_base, 512);
   }
+  B2C_TK(5)
 }
 
 // dQ = sum over key blocks of the fp32 partial slabs [nkb][rows, H*64] -> the Q slab of dqkv (bf16, pitch ld)

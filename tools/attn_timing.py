@@ -15,7 +15,10 @@ for _ in range(2):
     call("b2c_attention_bwd", ptr(qkv), qkv.stride(0), H * 64, 2 * H * 64, ptr(lens), ptr(att), ptr(datt), att.stride(0),
          ptr(lse), ptr(delta), ptr(dq32), ptr(dqkv), B, T, H, 0.125, 0.5, 1, stream_ptr())
 torch.cuda.synchronize()
-st = dq32.view(-1)[:256].view(torch.int64).cpu().tolist()
+st = dq32.view(-1)[:512].view(torch.int64).cpu().tolist()
+for nm, o in (("cta z=1", 128), ("cta z=40", 144)):
+    t = st[o:o + 6]
+    print(nm, "start->alloc", t[1] - t[0], "alloc->kv", t[2] - t[1], "kv->loop end", t[3] - t[2], "final stores", t[4] - t[3], "dealloc", t[5] - t[4], "total", t[5] - t[0])
 for who, off in (("tid0", 0), ("tid300", 64)):
     for i in range(3):
         t = st[off // 1 + i * 8: off + i * 8 + 8] if False else st[(off + i * 8):(off + i * 8 + 8)]
