@@ -129,6 +129,29 @@ int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off,
                       void* dqkv, int B, int T, int H, float scale, float drop_p, uint64_t drop_seed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Relative-positional variant (north_star / SURVEY section 8 row a7).  The reference only ships the sinusoid table
+ * (/root/reference/unused_lib/relativepositionalembeddings.py:13-32, used additively at unused_lib/conformer.py:101-103)
+ * and imports -- never calls -- the HF module whose arithmetic this follows:
+ * Wav2Vec2ConformerSelfAttention._apply_relative_embeddings (transformers modeling_wav2vec2_conformer.py:528-565):
+ *     score[i,j] = ( (q_i + u) . k_j  +  BD[i, T-1-i+j] ) * scale,      BD = (q + v) Pw^T,   Pw = linear_pos(PE)
+ * Parity for this entry point is pinned to HF (tests/golden/relpos_hf.npz), not to the reference.
+ *   qkv  bf16 [B*T, ld]: q+u at column h*64, k at k_off + h*64, v at v_off + h*64, q+v at qv_off + h*64 (the host
+ *        side runs the in-projection with augmented weights, so no extra elementwise pass exists)
+ *   pw   bf16 [pw_rows >= 2T-1, ld_pw]: row r = projected embedding of relative position (T-1-r), head h at h*64
+ * _fwd fuses the BD product into the flash kernel (one extra M128xN256 UMMA per tile, rel_shift as index math).
+ * _bwd takes BD materialised by the caller (bd fp32 [B*T, H, Rp], column r, produced with b2c_gemm_bf16 from the same
+ * operands) and writes dS at the shifted index into dbd (bf16 [B*T, H, Rp], ZEROED by the caller); the caller then gets
+ * d(q+v) = dbd Pw and dPw = dbd^T (q+v) from b2c_gemm_bf16.  dqkv receives d(q+u), dk, dv.
+ * ------------------------------------------------------------------------------------------------------- */
+int b2c_attention_rel_fwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, int64_t qv_off, const void* pw,
+                          int64_t ld_pw, int64_t pw_rows, const int32_t* lengths, void* out, int64_t ld_out, float* lse,
+                          int B, int T, int H, float scale, float drop_p, uint64_t drop_seed, void* stream);
+int b2c_attention_rel_bwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
+                          const void* out, const void* dout, int64_t ld_out, const float* lse, float* delta,
+                          float* dq_f32, void* dqkv, const float* bd, void* dbd, int64_t Rp, int B, int T, int H,
+                          float scale, float drop_p, uint64_t drop_seed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * ConvSubSampling (/root/reference/lib/convsubsampling.py:16-45): conv_sub_2(conv_sub_1(x)), no activation
  * between, valid padding.  Executed as the exact composition Conv2d(1->C2, kc x kc, stride s1*s2) with
  * kc = k1 + (k2-1)*s1: _compose builds Wc (bf16 [C2, KP], KP = kc*kc rounded up to 64)

@@ -15,12 +15,12 @@ from typing import List
 import torch
 
 from . import _lib, ops
-from .conformer import _LAYER_PARAMS, HEAD_PAD, Conformer, _get, run_layers
+from .conformer import HEAD_PAD, Conformer, _get, run_layers
 
 
 def conformer_apply(model: Conformer, inp: torch.Tensor, lengths_i32: torch.Tensor) -> torch.Tensor:
     B, T, d = inp.shape
-    params = [_get(layer, n) for layer in model.conformer_layers for n in _LAYER_PARAMS]
+    params = [_get(layer, n) for layer in model.conformer_layers for n in model.layer_params]
     need_grad = torch.is_grad_enabled() and (inp.requires_grad or any(p.requires_grad for p in params))
     drop_p = model.dropout_p if model.training else 0.0
     if drop_p > 0.0:            # one device-side tick per training forward: fresh masks even when a CUDA graph replays
@@ -72,17 +72,22 @@ class _ConformerFn(torch.autograd.Function):
             dx = dx.clone()
 
         # one zeroed fp32 arena holds every parameter gradient of the stack (atomics accumulate into it)
-        padded = dh != HEAD_PAD
+        rel = model.rel_att
+        nq = 4 if rel else 3                  # rel_att: the in-projection carries a 4th slab (q + pos_bias_v)
+        padded = dh != HEAD_PAD or rel
+        _LAYER_PARAMS = model.layer_params
         sizes = []
         for layer in model.conformer_layers:
             for n in _LAYER_PARAMS:
                 p = _get(layer, n)
                 if padded and n == "self_attn.in_proj_weight":
-                    sizes.append(3 * Hd * d)
+                    sizes.append(nq * Hd * d)
                 elif padded and n == "self_attn.in_proj_bias":
-                    sizes.append(3 * Hd)
-                elif padded and n == "self_attn.out_proj.weight":
+                    sizes.append(nq * Hd)
+                elif padded and n in ("self_attn.out_proj.weight", "self_attn.linear_pos.weight"):
                     sizes.append(d * Hd)
+                elif n in ("self_attn.pos_bias_u", "self_attn.pos_bias_v"):
+                    sizes.append(4)           # filled from the in-projection bias gradient below
                 else:
                     sizes.append(p.numel())
         offs = [0]
@@ -152,10 +157,18 @@ class _ConformerFn(torch.autograd.Function):
             dyb = ops.scale_cast(dx, 1.0, drop_p, sd + 5, colsum=G(li, "self_attn.out_proj.bias"))
             wgrad(dyb, s["att"], d, Hd, G(li, "self_attn.out_proj.weight"))
             datt = ops.gemm(dyb, w["self_attn.out_proj.weight"], M=M, N=Hd, K=d, b_mn=True)
-            dqkv = ops.attention_bwd(s["qkv"], ctx.lengths, s["att"], datt, s["lse"], B, T, H, scale, drop_p, sd + 4)
+            if rel:
+                dqkv, dpw = ops.attention_rel_bwd(s["qkv"], s["pw"], ctx.lengths, s["att"], datt, s["lse"], B, T, H, scale,
+                                                  drop_p, sd + 4)
+                pe = model.rel_table(T, dev)
+                # Pw = PE W_pos^T  =>  dW_pos[Hd, d] = dPw^T PE
+                ops.gemm(ops.cast_bf16(dpw), pe, M=Hd, N=d, K=pe.shape[0], a_mn=True, b_mn=True,
+                         out=G(li, "self_attn.linear_pos.weight").view(Hd, d), accumulate=True)
+            else:
+                dqkv = ops.attention_bwd(s["qkv"], ctx.lengths, s["att"], datt, s["lse"], B, T, H, scale, drop_p, sd + 4)
             ops.colsum(dqkv, G(li, "self_attn.in_proj_bias"))
-            wgrad(dqkv, s["a"], 3 * Hd, d, G(li, "self_attn.in_proj_weight"))
-            da = ops.gemm(dqkv, w["self_attn.in_proj_weight"], M=M, N=d, K=3 * Hd, b_mn=True)
+            wgrad(dqkv, s["a"], nq * Hd, d, G(li, "self_attn.in_proj_weight"))
+            da = ops.gemm(dqkv, w["self_attn.in_proj_weight"], M=M, N=d, K=nq * Hd, b_mn=True)
             ops.layernorm_bwd(da, s["x"], P("self_attn_layer_norm.weight"), s["mean"], s["rstd"], dx, True,
                               G(li, "self_attn_layer_norm.weight"), G(li, "self_attn_layer_norm.bias"))
 
@@ -169,9 +182,23 @@ class _ConformerFn(torch.autograd.Function):
                 p = _get(layer, n)
                 g = G(li, n)
                 if padded and n == "self_attn.in_proj_weight":
-                    g = g.view(3, H, HEAD_PAD, d)[:, :, :dh].reshape(3 * d, d)
+                    g4 = g.view(nq, H, HEAD_PAD, d)[:, :, :dh]
+                    g = g4[:3].clone() if rel else g4
+                    if rel:
+                        g[0] += g4[3]             # W_q feeds both q+u and q+v
+                    g = g.reshape(3 * d, d)
                 elif padded and n == "self_attn.in_proj_bias":
-                    g = g.view(3, H, HEAD_PAD)[:, :, :dh].reshape(3 * d)
+                    g4 = g.view(nq, H, HEAD_PAD)[:, :, :dh]
+                    g = g4[:3].clone() if rel else g4
+                    if rel:
+                        g[0] += g4[3]
+                    g = g.reshape(3 * d)
+                elif n == "self_attn.pos_bias_u":      # d(q+u) summed over tokens = slab 0 of the in-projection bias gradient
+                    g = G(li, "self_attn.in_proj_bias").view(nq, H, HEAD_PAD)[0, :, :dh].clone()
+                elif n == "self_attn.pos_bias_v":
+                    g = G(li, "self_attn.in_proj_bias").view(nq, H, HEAD_PAD)[3, :, :dh].clone()
+                elif padded and n == "self_attn.linear_pos.weight":
+                    g = g.view(H, HEAD_PAD, d)[:, :dh].reshape(d, d)
                 elif padded and n == "self_attn.out_proj.weight":
                     g = g.view(d, H, HEAD_PAD)[:, :, :dh].reshape(d, d)
                 else:

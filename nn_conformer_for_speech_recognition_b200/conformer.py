@@ -73,13 +73,23 @@ class ConformerLayer(nn.Module):
     """Parameter holder mirroring torchaudio `ConformerLayer` (conformer.py:122-212)."""
 
     def __init__(self, input_dim: int, ffn_dim: int, num_attention_heads: int, depthwise_conv_kernel_size: int,
-                 dropout: float = 0.0, use_group_norm: bool = False, convolution_first: bool = False) -> None:
+                 dropout: float = 0.0, use_group_norm: bool = False, convolution_first: bool = False,
+                 rel_att: bool = False) -> None:
         super().__init__()
         if convolution_first:
             raise NotImplementedError("convolution_first=True is not on the reference's path (asrnn.py:29)")
         self.ffn1 = _FeedForwardModule(input_dim, ffn_dim, dropout=dropout)
         self.self_attn_layer_norm = nn.LayerNorm(input_dim)
         self.self_attn = nn.MultiheadAttention(input_dim, num_attention_heads, dropout=dropout)
+        if rel_att:
+            # additive extension (SURVEY 8b): HF Wav2Vec2ConformerSelfAttention's names and initialisation
+            # (modeling_wav2vec2_conformer.py:441-445, 866-868) hung on the same `self_attn` module
+            dh = input_dim // num_attention_heads
+            self.self_attn.linear_pos = nn.Linear(input_dim, input_dim, bias=False)
+            self.self_attn.pos_bias_u = nn.Parameter(torch.zeros(num_attention_heads, dh))
+            self.self_attn.pos_bias_v = nn.Parameter(torch.zeros(num_attention_heads, dh))
+            nn.init.xavier_uniform_(self.self_attn.pos_bias_u)
+            nn.init.xavier_uniform_(self.self_attn.pos_bias_v)
         self.self_attn_dropout = nn.Dropout(dropout)
         self.conv_module = _ConvolutionModule(input_dim=input_dim, num_channels=input_dim,
                                               depthwise_kernel_size=depthwise_conv_kernel_size, dropout=dropout,
@@ -103,6 +113,7 @@ _LAYER_PARAMS = [
     "ffn2.sequential.4.weight", "ffn2.sequential.4.bias",
     "final_layer_norm.weight", "final_layer_norm.bias",
 ]
+_REL_PARAMS = ["self_attn.linear_pos.weight", "self_attn.pos_bias_u", "self_attn.pos_bias_v"]
 # GEMM weights that need a bf16 copy (everything else is consumed as fp32 straight from the Parameter)
 _BF16_WEIGHTS = ["ffn1.sequential.1.weight", "ffn1.sequential.4.weight", "self_attn.in_proj_weight",
                  "self_attn.out_proj.weight", "conv_module.sequential.0.weight", "conv_module.sequential.5.weight",
@@ -129,7 +140,7 @@ class _WeightCache:
     def _signature(self):
         sig = []
         for layer in self.owner.conformer_layers:
-            for name in _BF16_WEIGHTS + ["self_attn.in_proj_bias"]:
+            for name in _BF16_WEIGHTS + ["self_attn.in_proj_bias"] + (_REL_PARAMS if self.owner.rel_att else []):
                 p = _get(layer, name)
                 sig.append((p.data_ptr(), p._version))
         return tuple(sig)
@@ -140,7 +151,7 @@ class _WeightCache:
             return self.bf16
         o = self.owner
         dev = next(o.parameters()).device
-        if o.head_dim != HEAD_PAD:
+        if o.head_dim != HEAD_PAD or o.rel_att:
             self._build_padded(dev)
         else:
             rebuild = self.table is None or [s[0] for s in sig] != [s[0] for s in (self.key or ())]
@@ -174,9 +185,13 @@ class _WeightCache:
             for name in _BF16_WEIGHTS:
                 p = _get(layer, name).detach()
                 if name == "self_attn.in_proj_weight":
-                    w = torch.zeros(3, H, HEAD_PAD, d, device=dev, dtype=torch.float32)
-                    w[:, :, :dh] = p.view(3, H, dh, d)
-                    p = w.view(3 * H * HEAD_PAD, d)
+                    # rel_att: a 4th slab repeats W_q -- the GEMM then emits [q+u | k | v | q+v] through the bias below
+                    nslab = 4 if o.rel_att else 3
+                    w = torch.zeros(nslab, H, HEAD_PAD, d, device=dev, dtype=torch.float32)
+                    w[:3, :, :dh] = p.view(3, H, dh, d)
+                    if o.rel_att:
+                        w[3] = w[0]
+                    p = w.view(nslab * H * HEAD_PAD, d)
                 elif name == "self_attn.out_proj.weight":
                     w = torch.zeros(d, H, HEAD_PAD, device=dev, dtype=torch.float32)
                     w[:, :, :dh] = p.view(d, H, dh)
@@ -184,8 +199,15 @@ class _WeightCache:
                 elif p.dim() == 3:
                     p = p[:, :, 0]
                 out[name] = ops.cast_bf16(p.contiguous())
-            b = torch.zeros(3, H, HEAD_PAD, device=dev, dtype=torch.float32)
-            b[:, :, :dh] = _get(layer, "self_attn.in_proj_bias").detach().view(3, H, dh)
+            b = torch.zeros(4 if o.rel_att else 3, H, HEAD_PAD, device=dev, dtype=torch.float32)
+            b[:3, :, :dh] = _get(layer, "self_attn.in_proj_bias").detach().view(3, H, dh)
+            if o.rel_att:
+                b[3] = b[0]
+                b[0, :, :dh] += _get(layer, "self_attn.pos_bias_u").detach()
+                b[3, :, :dh] += _get(layer, "self_attn.pos_bias_v").detach()
+                wp = torch.zeros(H, HEAD_PAD, d, device=dev, dtype=torch.float32)
+                wp[:, :dh] = _get(layer, "self_attn.linear_pos.weight").detach().view(H, dh, d)
+                out["self_attn.linear_pos.weight"] = ops.cast_bf16(wp.view(H * HEAD_PAD, d))
             out["in_bias"] = b.view(-1)
             self.bf16.append(out)
 
@@ -200,15 +222,20 @@ class Conformer(nn.Module):
 
     def __init__(self, input_dim: int, num_heads: int, ffn_dim: int, num_layers: int,
                  depthwise_conv_kernel_size: int, dropout: float = 0.0, use_group_norm: bool = False,
-                 convolution_first: bool = False):
+                 convolution_first: bool = False, rel_att: bool = False):
         super().__init__()
         if input_dim % num_heads != 0:
             raise AssertionError("embed_dim must be divisible by num_heads")
         self.conformer_layers = nn.ModuleList([
             ConformerLayer(input_dim, ffn_dim, num_heads, depthwise_conv_kernel_size, dropout=dropout,
-                           use_group_norm=use_group_norm, convolution_first=convolution_first)
+                           use_group_norm=use_group_norm, convolution_first=convolution_first, rel_att=rel_att)
             for _ in range(num_layers)
         ])
+        # rel_att (`hp.rel_att`, lib/hparams.py:102): Transformer-XL style relative-positional attention with HF's
+        # rel_shift; adds self_attn.linear_pos.weight / pos_bias_u / pos_bias_v per layer.  Default off = torchaudio.
+        self.rel_att = bool(rel_att)
+        self.layer_params = _LAYER_PARAMS + (_REL_PARAMS if rel_att else [])
+        self._pe_cache = {}
         self.input_dim, self.num_heads, self.ffn_dim = input_dim, num_heads, ffn_dim
         self.num_layers, self.kernel_size, self.dropout_p = num_layers, depthwise_conv_kernel_size, float(dropout)
         self.head_dim = input_dim // num_heads
@@ -237,6 +264,25 @@ class Conformer(nn.Module):
         return y, lengths
 
     # ------------------------------------------------------------------------------------------------
+    def rel_table(self, T: int, device) -> torch.Tensor:
+        """HF Wav2Vec2ConformerRelPositionalEmbedding.extend_pe (modeling_wav2vec2_conformer.py:168-196): fp32 table,
+        interleaved sin/cos, row r = relative position T-1-r.  Returned as bf16 [Rp, d] with Rp = 2T-1 rounded up to 8
+        (zero rows), cached per T -- a constant, like a weight."""
+        key = (T, str(device))
+        if key not in self._pe_cache:
+            d = self.input_dim
+            pos = torch.arange(0, T, dtype=torch.int64).float().unsqueeze(1)
+            div = torch.exp(torch.arange(0, d, 2, dtype=torch.int64).float() * -(math.log(10000.0) / d))
+            pe_pos, pe_neg = torch.zeros(T, d), torch.zeros(T, d)
+            pe_pos[:, 0::2], pe_pos[:, 1::2] = torch.sin(pos * div), torch.cos(pos * div)
+            pe_neg[:, 0::2], pe_neg[:, 1::2] = torch.sin(-1 * pos * div), torch.cos(-1 * pos * div)
+            pe = torch.cat([torch.flip(pe_pos, [0]), pe_neg[1:]], 0)
+            Rp = (2 * T - 1 + 7) // 8 * 8
+            full = torch.zeros(Rp, d)
+            full[:2 * T - 1] = pe
+            self._pe_cache[key] = full.to(device=device, dtype=torch.bfloat16)
+        return self._pe_cache[key]
+
     def next_seed(self) -> int:
         """Dropout seeds: torch's CPU generator picks the stream (so torch.manual_seed controls it), the counter
         keeps successive forward passes distinct."""
@@ -264,10 +310,13 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
     dev = x.device
     save = train_state is not None
     bf = torch.bfloat16
+    rel = model.rel_att
+    nq = 4 if rel else 3                               # rel_att: the in-projection also emits q + pos_bias_v
+    pe = model.rel_table(T, dev) if rel else None
     if not save:       # inference workspaces, reused by every layer (stay L2-resident between kernels)
         a_buf = torch.empty((M, d), device=dev, dtype=bf)
         h_buf = torch.empty((M, f), device=dev, dtype=bf)
-        qkv_buf = torch.empty((M, 3 * Hd), device=dev, dtype=bf)
+        qkv_buf = torch.empty((M, nq * Hd), device=dev, dtype=bf)
         u_buf = torch.empty((M, 2 * d), device=dev, dtype=bf)
 
     for li, layer in enumerate(model.conformer_layers):
@@ -299,18 +348,26 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
 
         # ---- 2. x += out_proj(Attn(in_proj(LN(x))))                                  conformer.py:192-202
         ln_w, ln_b = P("self_attn_layer_norm.weight"), P("self_attn_layer_norm.bias")
+        pw = None
+        if rel:            # Pw = linear_pos(PE): [Rp, H*64] projected relative embeddings of this layer
+            pw = ops.gemm(pe, w["self_attn.linear_pos.weight"], M=pe.shape[0], N=Hd, K=d)
         if save:
             a, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, save_stats=True)
-            qkv = ops.gemm(a, w["self_attn.in_proj_weight"], M=M, N=3 * Hd, K=d, bias=w["in_bias"])
-            att, lse = ops.attention_fwd(qkv, lengths_i32, B, T, H, scale, save_lse=True, drop_p=drop_p, drop_seed=sd + 4)
+            qkv = ops.gemm(a, w["self_attn.in_proj_weight"], M=M, N=nq * Hd, K=d, bias=w["in_bias"])
+            if rel:
+                att, lse = ops.attention_rel_fwd(qkv, pw, lengths_i32, B, T, H, scale, save_lse=True, drop_p=drop_p,
+                                                 drop_seed=sd + 4)
+            else:
+                att, lse = ops.attention_fwd(qkv, lengths_i32, B, T, H, scale, save_lse=True, drop_p=drop_p, drop_seed=sd + 4)
             x_out = ops.gemm(att, w["self_attn.out_proj.weight"], M=M, N=d, K=Hd, bias=P("self_attn.out_proj.bias"),
                              resid=x, out_dtype=torch.float32, drop_p=drop_p, drop_seed=sd + 5)
-            st["attn"] = dict(x=x, a=a, mean=mean, rstd=rstd, qkv=qkv, att=att, lse=lse)
+            st["attn"] = dict(x=x, a=a, mean=mean, rstd=rstd, qkv=qkv, att=att, lse=lse, pw=pw)
             x = x_out
         else:
             ops.layernorm_fwd(x, ln_w, ln_b, out=a_buf)
-            ops.gemm(a_buf, w["self_attn.in_proj_weight"], M=M, N=3 * Hd, K=d, bias=w["in_bias"], out=qkv_buf)
-            att = ops.attention_fwd(qkv_buf, lengths_i32, B, T, H, scale)
+            ops.gemm(a_buf, w["self_attn.in_proj_weight"], M=M, N=nq * Hd, K=d, bias=w["in_bias"], out=qkv_buf)
+            att = (ops.attention_rel_fwd(qkv_buf, pw, lengths_i32, B, T, H, scale) if rel
+                   else ops.attention_fwd(qkv_buf, lengths_i32, B, T, H, scale))
             ops.gemm(att, w["self_attn.out_proj.weight"], M=M, N=d, K=Hd, bias=P("self_attn.out_proj.bias"),
                      resid=x, out=x)
 

@@ -45,23 +45,57 @@ struct AttnParams {
   float scale_log2;            // scale * log2(e)
   int Tpad;                    // even row pitch of the dropout index space
   DropCfg drop;
+  int qv_col;                  // REL: column of head 0 of (q + pos_bias_v) inside a qkv row
 };
+
+// Per-lane barrel shifter for the rel_shift: out[t] = in[t + s], s in [0, 32), all register resident (190 selects
+// per 32 outputs).  tcgen05.ld hands every lane of a warp the SAME columns; the shift needs lane-dependent ones.
+__device__ __forceinline__ void skew_select(const uint32_t (&in)[64], int s, uint32_t (&out)[32]) {
+  uint32_t a[48], b[40], c[36], d[34];
+  const bool s16 = s & 16, s8 = s & 8, s4 = s & 4, s2 = s & 2, s1 = s & 1;
+#pragma unroll
+  for (int t = 0; t < 48; ++t) a[t] = s16 ? in[t + 16] : in[t];
+#pragma unroll
+  for (int t = 0; t < 40; ++t) b[t] = s8 ? a[t + 8] : a[t];
+#pragma unroll
+  for (int t = 0; t < 36; ++t) c[t] = s4 ? b[t + 4] : b[t];
+#pragma unroll
+  for (int t = 0; t < 34; ++t) d[t] = s2 ? c[t + 2] : c[t];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) out[t] = s1 ? d[t + 1] : d[t];
+}
 
 // 256 threads: thread (row = tid & 127, half = tid >> 7) owns query row `row` and 64 of the 128 keys of every key block
 // (and 32 of the 64 output columns).  K is double-buffered and V is fetched one step ahead by TMA, so the only exposed
 // waits are the two MMAs of the current block; 96 KB smem + 256 TMEM columns -> 2 CTAs per SM.
-__global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+//
+// REL = true adds the Transformer-XL relative-position term of HF Wav2Vec2ConformerSelfAttention._apply_relative_embeddings
+// (modeling_wav2vec2_conformer.py:528-565; the reference only imports it):
+//   score[i,j] = (q_i + u) . k_j + shift(BD)[i,j],   BD = (q + v) Pw^T,   shift(BD)[i,j] = BD[i, T-1-i+j]
+// Q (column 0) already holds q + u and column qv_col holds q + v (the in-projection is run with augmented weights).
+// For a (128-query, 128-key) tile only the 256 relative positions r in [r_lo, r_lo + 256), r_lo = T-128-q0+k0, occur:
+// ONE extra UMMA  BD_win = Qv Pw[r_lo..]^T  (M128 N256) lands in TMEM cols [256,512) and row ii reads its scores from
+// window columns 127-ii+jj -- the rel_shift is pure index math: a warp-uniform column base plus a per-lane barrel
+// shift.  The combined score is written back over S (tcgen05.st) so the softmax below is shared.  512 TMEM columns
+// -> one CTA per SM in this mode.
+template <bool REL>
+__global__ void __launch_bounds__(256, REL ? 1 : 2) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                   const __grid_constant__ CUtensorMap tmPW,
+                                                                   const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   constexpr uint32_t OFF_Q = 0, OFF_K = 16384 /*2 bufs*/, OFF_V = 49152, OFF_P = 65536, OFF_X = 98304, OFF_BAR = 99328;
+  constexpr uint32_t OFF_QV = 100352, OFF_PW = 116736 /*[256][64] window*/;     // REL only
+  constexpr uint32_t TM_COLS = REL ? 512 : 256, TM_BD = 256;
   float* sx = reinterpret_cast<float*>(smem + OFF_X);          // [2][128] row-max / row-sum exchange between halves
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* bar_k = bar_q + 1;                                 // [2]
   uint64_t* bar_v = bar_q + 3;
   uint64_t* bar_s = bar_q + 4;
   uint64_t* bar_o = bar_q + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 6);
+  uint64_t* bar_pw = bar_q + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 7);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid & 127, half = tid >> 7;
@@ -73,19 +107,31 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(bar_q, 1); mbar_init(&bar_k[0], 1); mbar_init(&bar_k[1], 1); mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_pw, 1);
     fence_barrier_init();
   }
-  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 256); }
+  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, TM_COLS); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 
+  // REL: relative positions of key block j start at r_lo = T-128-q0 + 128 j (negative / past-the-end rows: TMA zero fill)
+  auto load_pw = [&](int j) {
+    const int r_lo = p.T - AT_BQ - q0 + j * AT_BK;
+    mbar_expect_tx(bar_pw, 32768);
+    tma_load_2d(smem + OFF_PW, &tmPW, bar_pw, h * AT_DH, r_lo);
+    tma_load_2d(smem + OFF_PW + 16384, &tmPW, bar_pw, h * AT_DH, r_lo + 128);
+  };
   if (tid == 0 && nkb > 0) {
-    mbar_expect_tx(bar_q, 16384);
+    if constexpr (REL) tma_prefetch_desc(&tmPW);
+    mbar_expect_tx(bar_q, REL ? 32768 : 16384);
     tma_load_2d(smem + OFF_Q, &tmQKV, bar_q, p.q_col + h * AT_DH, row_base + q0);
+    if constexpr (REL) {
+      tma_load_2d(smem + OFF_QV, &tmQKV, bar_q, p.qv_col + h * AT_DH, row_base + q0);
+      load_pw(0);
+    }
     mbar_expect_tx(&bar_k[0], 16384);
     tma_load_2d(smem + OFF_K, &tmQKV, &bar_k[0], p.k_col + h * AT_DH, row_base);
     mbar_expect_tx(bar_v, 16384);
@@ -94,6 +140,9 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
 
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
+  constexpr uint32_t idesc_bd = umma_idesc_bf16(128, 256, false, false);
+  // REL: first BD-window column this warp's lanes read for key 0 of the thread's half; lane l adds 31-l
+  const uint32_t bd_col0 = TM_BD + 96 - 32 * (warp & 3) + 64 * half;
 
   float o[32];
 #pragma unroll
@@ -118,10 +167,21 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
       for (int k = 0; k < AT_DH / 16; ++k)
         umma_bf16(tmem_base, umma_desc_sw128(base + OFF_Q + k * 32, 16, 1024),
                   umma_desc_sw128(base + OFF_K + kb * 16384 + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+      if constexpr (REL) {
+        mbar_wait(bar_pw, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < AT_DH / 16; ++k)
+          umma_bf16(tmem_base + TM_BD, umma_desc_sw128(base + OFF_QV + k * 32, 16, 1024),
+                    umma_desc_sw128(base + OFF_PW + k * 32, 16, 1024), idesc_bd, k > 0 ? 1u : 0u);
+      }
       tc_commit(bar_s);
     }
     mbar_wait(bar_s, ph);
     tc_fence_after();
+    if constexpr (REL) {
+      if (tid == 0 && j + 1 < nkb) load_pw(j + 1);      // the product that read this window has retired
+    }
 
     // ---- online softmax: this thread's 64 keys of its row ----
     // chunks that lie entirely below `len` (all but the utterance's last one) take a predicate-free path: the softmax
@@ -133,7 +193,18 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
       uint32_t v[32];
       __syncwarp();
       tmem_ld32(tm_lane + half * 64 + c, v);
-      tmem_wait_ld();
+      if constexpr (REL) {
+        uint32_t w[64], sh[32];
+        tmem_ld32(tm_lane + bd_col0 + c, w);
+        tmem_ld32(tm_lane + bd_col0 + c + 32, w + 32);
+        tmem_wait_ld();
+        skew_select(w, 31 - (tid & 31), sh);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(sh[i]));
+        tmem_st32(tm_lane + half * 64 + c, v);          // combined score back over S: the exp pass below re-reads it
+      } else {
+        tmem_wait_ld();
+      }
       if (key0 + c + 32 <= len) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) m_loc = fmaxf(m_loc, __uint_as_float(v[i]));
@@ -143,6 +214,7 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
           if (key0 + c + i < len) m_loc = fmaxf(m_loc, __uint_as_float(v[i]));
       }
     }
+    if constexpr (REL) tmem_wait_st();
     sx[half * 128 + row] = m_loc;
     __syncthreads();
     const float m_blk = fmaxf(m_loc, sx[(half ^ 1) * 128 + row]);
@@ -240,11 +312,12 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
   if (warp == 0) {
     tc_fence_after();
     __syncwarp();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, TM_COLS);
   }
 }
 
 constexpr uint32_t ATTN_FWD_SMEM = 99328 + 64 + 1024;
+constexpr uint32_t ATTN_FWD_REL_SMEM = 116736 + 32768 + 1024;
 // ================================================================================================
 // backward
 // ================================================================================================
@@ -260,6 +333,11 @@ struct AttnBwdParams {
   int Tpad;
   DropCfg drop;
   void* delta_dbg;         // only used by -DB2C_ATTN_TIMING builds (cycle stamps of one CTA)
+  // REL (relative-position scores): bd = (q+v) Pw^T fp32 [B*T, H, Rp] (un-shifted, column r = relative row index);
+  // dbd receives dS at the shifted position (bf16, same layout, zeroed by the caller) -- see b2c_attention_rel_bwd
+  const float* bd;
+  __nv_bfloat16* dbd;
+  int64_t Rp;
 };
 
 // delta[b,h,t] = sum_c dO[row, h*64+c] * O[row, h*64+c]
@@ -292,9 +370,12 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 // P (optionally dropped, feeds dV) and dS = P o (dP*drop - delta) * scale, both written as bf16 [q][key] K-major
 // SW128 tiles (2 x [128][64]).  Rows past the utterance end contribute nothing: with lse = +inf their probabilities
 // are exactly 2^(-inf) = 0, no per-element predicate needed (lse_r is set by the caller).
+// REL: the relative-position score term is read from the materialised BD at the rel_shift index r = T-1-q+key and dS
+// is stored to dBD at the same index (the two products that consume dBD are plain GEMMs, see b2c_attention_rel_bwd).
+template <bool REL>
 __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint32_t tm_s, uint32_t tm_dp, uint8_t* sP,
                                                    uint8_t* sdS, int row, int cq, int key0, int len, float lse_r,
-                                                   float delta_r, uint64_t drop_row) {
+                                                   float delta_r, uint64_t drop_row, int64_t rel_row, int q_idx) {
   const DropCfg drop = drop_resolve(p.drop);
   const float inv_keep8 = 256.f / (256.f - static_cast<float>(drop.thresh16 >> 8));
   const int c = cq * 32;
@@ -307,6 +388,13 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float pr[8], ds[8];
+    float bb[8];
+    // rel_row >= 0 only for real query rows; keys past T have no relative position (and no probability mass)
+    const int64_t rel_at = rel_row + (p.T - 1 - q_idx) + key0 + c + g * 8;
+    if constexpr (REL) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bb[e] = (rel_row >= 0 && key0 + c + g * 8 + e < p.T) ? __ldg(p.bd + rel_at + e) : 0.f;
+    }
 #pragma unroll
     for (int i4 = 0; i4 < 8; i4 += 4) {
       const int i = g * 8 + i4;
@@ -314,6 +402,7 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
       if (drop.thresh16) drop_scale4(drop, drop_row + key0 + c + i, inv_keep8, dsc);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
+        if constexpr (REL) vs[i + e] = __float_as_uint(__uint_as_float(vs[i + e]) + bb[i4 + e]);
         float pv = ex2_approx(fmaf(__uint_as_float(vs[i + e]), p.scale_log2, -lse_r));
         if (!full && key0 + c + i + e >= len) pv = 0.f;
         pr[i4 + e] = pv * dsc[e];
@@ -325,6 +414,13 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
                                                      pack_bf16(pr[4], pr[5]), pack_bf16(pr[6], pr[7]));
     *reinterpret_cast<uint4*>(sdS + off) = make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]),
                                                       pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+    if constexpr (REL) {
+      if (rel_row >= 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (key0 + c + g * 8 + e < p.T) p.dbd[rel_at + e] = __float2bfloat16_rn(ds[e]);
+      }
+    }
   }
 }
 
@@ -341,6 +437,7 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
 //   UMMA  dV += P^T dO_i, dK += dS^T Q_i  (accumulate over i in TMEM), dQp = dS K_j (fresh)
 //   regs  dQp -> this key block's fp32 partial slab (plain 128 B stores); attn_dq_cast_kernel sums the slabs -> bf16
 // S and dP are recomputed here from the saved log-sum-exp, so no T x T tensor ever reaches HBM.
+template <bool REL>
 __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                           const __grid_constant__ CUtensorMap tmDO,
                                                           const AttnBwdParams p, float* __restrict__ dq_f32) {
@@ -450,8 +547,9 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant_
     mbar_wait(bar_s, ph);
     tc_fence_after();
     B2C_TS(1)
-    attn_bwd_tile_math(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P, smem + OFF_DS, row, cq, key0, len,
-                       lse_r, delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad);
+    attn_bwd_tile_math<REL>(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P, smem + OFF_DS, row, cq, key0, len,
+                            lse_r, delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad,
+                            (REL && q_idx < p.T) ? (static_cast<int64_t>(row_base + q_idx) * p.H + h) * p.Rp : -1, q_idx);
     B2C_TS(2)
     fence_proxy_async();
     tc_fence_before();
@@ -563,50 +661,81 @@ constexpr uint32_t ATTN_BWD_SMEM = 163840 + 64 + 1024;
 
 using namespace b2c;
 
-extern "C" int b2c_attention_fwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
-                                 void* out, int64_t ld_out, float* lse, int B, int T, int H, float scale, float drop_p,
-                                 uint64_t drop_seed, void* stream) {
+static int attention_fwd_launch(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, int64_t qv_off, const void* pw,
+                                int64_t ld_pw, int64_t pw_rows, const int32_t* lengths, void* out, int64_t ld_out,
+                                float* lse, int B, int T, int H, float scale, float drop_p, uint64_t drop_seed,
+                                void* stream) {
+  const bool rel = pw != nullptr;
   B2C_REQUIRE(qkv && lengths && out, "b2c_attention_fwd: null pointer");
   B2C_REQUIRE(B > 0 && T > 0 && H > 0, "b2c_attention_fwd: empty problem");
-  B2C_REQUIRE(ld % 8 == 0 && ld_out % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
+  B2C_REQUIRE(ld % 8 == 0 && ld_out % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0 && qv_off % 8 == 0,
               "b2c_attention_fwd: pitches/offsets must be multiples of 8 elements");
   B2C_REQUIRE(static_cast<int64_t>(B) * T < (1ll << 31), "b2c_attention_fwd: B*T too large");
-  CUtensorMap tm;
+  CUtensorMap tm, tp;
   int rc = get_tensor_map_2d(&tm, qkv, 2, static_cast<uint64_t>(ld), static_cast<uint64_t>(B) * T, ld * 2, 64, 128, true);
   if (rc) return rc;
+  if (rel) {
+    B2C_REQUIRE(ld_pw % 8 == 0 && ld_pw >= static_cast<int64_t>(H) * AT_DH && pw_rows >= 2ll * T - 1,
+                "b2c_attention_rel_fwd: pw must be bf16 [>= 2T-1, ld_pw >= H*64], ld_pw a multiple of 8");
+    rc = get_tensor_map_2d(&tp, pw, 2, static_cast<uint64_t>(H) * AT_DH, static_cast<uint64_t>(pw_rows), ld_pw * 2, 64, 128, true);
+    if (rc) return rc;
+  } else {
+    tp = tm;
+  }
   static bool configured = false;
   if (!configured) {
-    B2C_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_FWD_SMEM));
+    B2C_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_FWD_SMEM));
+    B2C_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_FWD_REL_SMEM));
     configured = true;
   }
   AttnParams p;
   p.lengths = lengths; p.out = static_cast<__nv_bfloat16*>(out); p.lse = lse; p.ld_out = ld_out;
   p.B = B; p.T = T; p.H = H;
-  p.q_col = 0; p.k_col = static_cast<int>(k_off); p.v_col = static_cast<int>(v_off);
+  p.q_col = 0; p.k_col = static_cast<int>(k_off); p.v_col = static_cast<int>(v_off); p.qv_col = static_cast<int>(qv_off);
   p.scale_log2 = scale * LOG2E;
   p.Tpad = (T + 3) & ~3;
   p.drop = make_drop(drop_p, drop_seed);
   dim3 grid((T + AT_BQ - 1) / AT_BQ, H, B);
-  attn_fwd_kernel<<<grid, 256, ATTN_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
+  if (rel) attn_fwd_kernel<true><<<grid, 256, ATTN_FWD_REL_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, tp, p);
+  else attn_fwd_kernel<false><<<grid, 256, ATTN_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, tp, p);
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
-                                 const void* out, const void* dout, int64_t ld_out, const float* lse, float* delta,
-                                 float* dq_f32, void* dqkv, int B, int T, int H, float scale, float drop_p,
+extern "C" int b2c_attention_fwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
+                                 void* out, int64_t ld_out, float* lse, int B, int T, int H, float scale, float drop_p,
                                  uint64_t drop_seed, void* stream) {
+  return attention_fwd_launch(qkv, ld, k_off, v_off, 0, nullptr, 0, 0, lengths, out, ld_out, lse, B, T, H, scale, drop_p,
+                              drop_seed, stream);
+}
+
+extern "C" int b2c_attention_rel_fwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, int64_t qv_off,
+                                     const void* pw, int64_t ld_pw, int64_t pw_rows, const int32_t* lengths, void* out,
+                                     int64_t ld_out, float* lse, int B, int T, int H, float scale, float drop_p,
+                                     uint64_t drop_seed, void* stream) {
+  B2C_REQUIRE(pw, "b2c_attention_rel_fwd: null pw");
+  return attention_fwd_launch(qkv, ld, k_off, v_off, qv_off, pw, ld_pw, pw_rows, lengths, out, ld_out, lse, B, T, H, scale,
+                              drop_p, drop_seed, stream);
+}
+
+static int attention_bwd_launch(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
+                                const void* out, const void* dout, int64_t ld_out, const float* lse, float* delta,
+                                float* dq_f32, void* dqkv, const float* bd, void* dbd, int64_t Rp, int B, int T, int H,
+                                float scale, float drop_p, uint64_t drop_seed, void* stream) {
   B2C_REQUIRE(qkv && lengths && out && dout && lse && delta && dq_f32 && dqkv, "b2c_attention_bwd: null pointer");
   B2C_REQUIRE(B > 0 && T > 0 && H > 0, "b2c_attention_bwd: empty problem");
   B2C_REQUIRE(ld % 8 == 0 && ld_out % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
               "b2c_attention_bwd: pitches/offsets must be multiples of 8 elements");
+  const bool rel = bd != nullptr;
+  B2C_REQUIRE(!rel || (dbd && Rp >= 2ll * T - 1), "b2c_attention_rel_bwd: dbd missing or Rp < 2T-1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tq, td;
   if (int rc = get_tensor_map_2d(&tq, qkv, 2, static_cast<uint64_t>(ld), static_cast<uint64_t>(B) * T, ld * 2, 64, 128, true)) return rc;
   if (int rc = get_tensor_map_2d(&td, dout, 2, static_cast<uint64_t>(H) * AT_DH, static_cast<uint64_t>(B) * T, ld_out * 2, 64, 128, true)) return rc;
   static bool configured = false;
   if (!configured) {
-    B2C_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_BWD_SMEM));
+    B2C_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_BWD_SMEM));
+    B2C_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_BWD_SMEM));
     configured = true;
   }
   const int64_t rows = static_cast<int64_t>(B) * T;
@@ -621,11 +750,30 @@ extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int
   p.Tpad = (T + 3) & ~3;
   p.drop = make_drop(drop_p, drop_seed);
   p.delta_dbg = dq_f32;     // timing builds scribble cycle stamps over the head of the dQ workspace
+  p.bd = bd; p.dbd = static_cast<__nv_bfloat16*>(dbd); p.Rp = Rp;
   dim3 grid((T + AT_BK - 1) / AT_BK, H, B);
-  attn_bwd_kernel<<<grid, 512, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
+  if (rel) attn_bwd_kernel<true><<<grid, 512, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
+  else attn_bwd_kernel<false><<<grid, 512, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
   const int64_t n8 = rows * H * AT_DH / 8;
   attn_dq_cast_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, st>>>(dq_f32, static_cast<__nv_bfloat16*>(dqkv),
                                                                                rows, H * AT_DH, ld, 0, (T + AT_BK - 1) / AT_BK);
   B2C_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
+                                 const void* out, const void* dout, int64_t ld_out, const float* lse, float* delta,
+                                 float* dq_f32, void* dqkv, int B, int T, int H, float scale, float drop_p,
+                                 uint64_t drop_seed, void* stream) {
+  return attention_bwd_launch(qkv, ld, k_off, v_off, lengths, out, dout, ld_out, lse, delta, dq_f32, dqkv, nullptr,
+                              nullptr, 0, B, T, H, scale, drop_p, drop_seed, stream);
+}
+
+extern "C" int b2c_attention_rel_bwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
+                                     const void* out, const void* dout, int64_t ld_out, const float* lse, float* delta,
+                                     float* dq_f32, void* dqkv, const float* bd, void* dbd, int64_t Rp, int B, int T,
+                                     int H, float scale, float drop_p, uint64_t drop_seed, void* stream) {
+  B2C_REQUIRE(bd && dbd, "b2c_attention_rel_bwd: null bd / dbd");
+  return attention_bwd_launch(qkv, ld, k_off, v_off, lengths, out, dout, ld_out, lse, delta, dq_f32, dqkv, bd, dbd, Rp, B,
+                              T, H, scale, drop_p, drop_seed, stream);
 }

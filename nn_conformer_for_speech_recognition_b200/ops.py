@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import ACT_NONE, ACT_SILU, ACT_SILU_BWD, BF16, F32, Epilogue, call, ptr, stream_ptr
 
 __all__ = ["gemm", "layernorm_fwd", "layernorm_bwd", "convmod_eval", "convmod_dw_fwd", "convmod_bn_finalize",
-           "convmod_bn_apply", "attention_fwd", "convsub_compose", "convsub_fwd", "convsub_wgrad",
+           "convmod_bn_apply", "attention_fwd", "attention_rel_fwd", "attention_rel_bwd", "convsub_compose", "convsub_fwd", "convsub_wgrad",
            "convsub_compose_bwd", "specaug_apply", "cast_bf16", "scale_cast", "colsum", "repack_heads",
            "ACT_NONE", "ACT_SILU", "ACT_SILU_BWD"]
 
@@ -133,6 +133,56 @@ def attention_fwd(qkv: torch.Tensor, lengths_i32: torch.Tensor, B: int, T: int, 
     call("b2c_attention_fwd", ptr(qkv), qkv.stride(0), H * 64, 2 * H * 64, ptr(lengths_i32), ptr(out), out.stride(0),
          ptr(lse), B, T, H, scale, drop_p, drop_seed, stream_ptr(), flops=4.0 * B * H * T * T * 64)
     return (out, lse) if save_lse else out
+
+
+def attention_rel_fwd(qkv: torch.Tensor, pw: torch.Tensor, lengths_i32: torch.Tensor, B: int, T: int, H: int,
+                      scale: float, *, save_lse: bool = False, drop_p: float = 0.0, drop_seed: int = 0):
+    """Relative-positional attention (HF `_apply_relative_embeddings`).  qkv bf16 [B*T, 4*H*64] = [q+u | k | v | q+v];
+    pw bf16 [>= 2T-1, H*64] projected relative embeddings, row r = relative position T-1-r."""
+    _lib.require_device()
+    _check(qkv, torch.bfloat16, "qkv")
+    _check(pw, torch.bfloat16, "pw")
+    _check(lengths_i32, torch.int32, "lengths")
+    out = torch.empty((B * T, H * 64), device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32) if save_lse else None
+    call("b2c_attention_rel_fwd", ptr(qkv), qkv.stride(0), H * 64, 2 * H * 64, 3 * H * 64, ptr(pw), pw.stride(0),
+         pw.shape[0], ptr(lengths_i32), ptr(out), out.stride(0), ptr(lse), B, T, H, scale, drop_p, drop_seed, stream_ptr(),
+         flops=4.0 * B * H * T * T * 64 + 2.0 * B * H * T * (2 * T) * 64)
+    return (out, lse) if save_lse else out
+
+
+def attention_rel_bwd(qkv, pw, lengths_i32, att, datt, lse, B: int, T: int, H: int, scale: float, drop_p: float = 0.0,
+                      drop_seed: int = 0):
+    """-> (dqkv bf16 [B*T, 4*H*64] = [d(q+u) | dk | dv | d(q+v)], dpw fp32 [Rp, H*64]).  BD is re-materialised with the
+    GEMM kernel (one launch per head), the attention kernel scatters dS to the shifted index, and the two products that
+    consume it are GEMMs again (dgrad / split-K wgrad form)."""
+    Hd = H * 64
+    M = B * T
+    Rp = pw.shape[0]
+    dev = qkv.device
+    bd = torch.empty((M, H, Rp), device=dev, dtype=torch.float32)
+    for h in range(H):
+        gemm(qkv[:, 3 * Hd + h * 64:3 * Hd + (h + 1) * 64], pw[:, h * 64:(h + 1) * 64], M=M, N=Rp, K=64, out=bd[:, h, :])
+    dbd = torch.zeros((M, H, Rp), device=dev, dtype=torch.bfloat16)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, H, T), device=dev, dtype=torch.float32)
+    dq32 = torch.empty(((T + 127) // 128, M, Hd), device=dev, dtype=torch.float32)
+    call("b2c_attention_rel_bwd", ptr(qkv), qkv.stride(0), Hd, 2 * Hd, ptr(lengths_i32), ptr(att), ptr(datt),
+         att.stride(0), ptr(lse), ptr(delta), ptr(dq32), ptr(dqkv), ptr(bd), ptr(dbd), Rp, B, T, H, scale, drop_p,
+         drop_seed, stream_ptr(), flops=14.0 * B * H * T * T * 64)
+    dpw = torch.zeros((Rp, Hd), device=dev, dtype=torch.float32)
+    tiles = (Rp + 127) // 128
+    kb = (M + 63) // 64
+    split = max(1, min(kb // 4 if kb >= 4 else 1, (296 + tiles - 1) // tiles))
+    for h in range(H):
+        dbd_h = dbd[:, h, :]
+        qv_h = qkv[:, 3 * Hd + h * 64:3 * Hd + (h + 1) * 64]
+        # d(q+v)[M,64] = dBD_h[M,Rp] Pw_h[Rp,64]
+        gemm(dbd_h, pw[:, h * 64:(h + 1) * 64], M=M, N=64, K=Rp, b_mn=True, out=dqkv[:, 3 * Hd + h * 64:3 * Hd + (h + 1) * 64])
+        # dPw_h[Rp,64] = dBD_h^T (q+v)_h
+        gemm(dbd_h, qv_h, M=Rp, N=64, K=M, a_mn=True, b_mn=True, out=dpw[:, h * 64:(h + 1) * 64], accumulate=True,
+             split_k=split)
+    return dqkv, dpw
 
 
 def convsub_compose(W1, b1, W2, b2, s1: int, KP: int, want_f32: bool = False):

@@ -13,13 +13,15 @@ from .conformer import Conformer
 from .convsubsampling import ConvSubSampling
 
 
-def conformer_from_torchaudio(ref) -> Conformer:
-    """Build our Conformer with the constructor arguments of a torchaudio.models.Conformer and copy its weights."""
+def conformer_from_torchaudio(ref, rel_att: bool = False) -> Conformer:
+    """Build our Conformer with the constructor arguments of a torchaudio.models.Conformer and copy its weights.
+    rel_att=True (`hp.rel_att`, lib/hparams.py:102) adds the relative-positional parameters (fresh initialisation
+    unless `ref` already carries `self_attn.linear_pos.weight` / `pos_bias_u` / `pos_bias_v`)."""
     layer = ref.conformer_layers[0]
     lin = layer.ffn1.sequential[1]
     new = Conformer(lin.in_features, layer.self_attn.num_heads, lin.out_features, len(ref.conformer_layers),
-                    layer.conv_module.sequential[2].kernel_size[0], layer.self_attn_dropout.p)
-    new.load_state_dict(ref.state_dict())
+                    layer.conv_module.sequential[2].kernel_size[0], layer.self_attn_dropout.p, rel_att=rel_att)
+    new.load_state_dict(ref.state_dict(), strict=not rel_att)
     p = next(ref.parameters())
     return new.to(device=p.device, dtype=p.dtype).train(ref.training)
 
@@ -35,7 +37,7 @@ def patch_asrnn(model, specaug_mode: str = "reference"):
     if specaug_mode not in ("reference", "paper"):
         raise ValueError("specaug_mode must be 'reference' or 'paper'")
     model.conv_sub_sampling = convsub_from_reference(model.conv_sub_sampling)
-    model.conformers = conformer_from_torchaudio(model.conformers)
+    model.conformers = conformer_from_torchaudio(model.conformers, bool(getattr(getattr(model, "hp", None), "rel_att", False)))
     model._b2c_specaug_mode = specaug_mode
     for name in ("SpecAugment", "time_warping", "frequency_masking", "time_masking"):
         setattr(model, name, types.MethodType(getattr(specaugment, name), model))

@@ -6,7 +6,12 @@ fp32-stored results with a tighter bound.  Integer / index work (SpecAugment) is
 """
 import math
 
+import os
+import sys
+
 import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 
 pytestmark = pytest.mark.gpu
@@ -197,6 +202,36 @@ def test_attention_fwd(ops, B, T, H, lens):
     out, lse = ops.attention_fwd(qkv, lengths, B, T, H, 1 / 8.0, save_lse=True)
     _close(out, ref, rel=2e-2, name="attention out")
     _close(lse * math.log(2.0), lse_ref, rel=1e-3, abs_=1e-2, name="attention lse")
+
+
+# rel_att: relative-positional scores (HF rel_shift).  Reference = tests/_rel_reference.py, pinned to the HF golden.
+@pytest.mark.parametrize("B,T,H,lens", [(2, 10, 2, [10, 6]), (1, 128, 1, [128]), (2, 300, 2, [300, 131]),
+                                        (2, 373, 4, [373, 200]), (1, 520, 1, [515])])
+def test_attention_rel_fwd_bwd(ops, B, T, H, lens):
+    from _rel_reference import rel_attention_core
+    g = torch.Generator(device="cuda").manual_seed(T + 1)
+    Hd, M, Rp = H * 64, B * T, (2 * T - 1 + 7) // 8 * 8
+    qkv = _bf(0.7 * torch.randn(M, 4 * Hd, device="cuda", generator=g))
+    pw = _bf(0.7 * torch.randn(Rp, Hd, device="cuda", generator=g))
+    pw[2 * T - 1:] = 0
+    lengths = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    dout = _bf(torch.randn(M, Hd, device="cuda", generator=g))
+    qf = qkv.float().requires_grad_(True)
+    pf = pw.float().requires_grad_(True)
+    qu, k, v, qv = (qf.view(B, T, 4, H, 64)[:, :, i].transpose(1, 2) for i in range(4))
+    o = rel_attention_core(qu, k, v, qv, pf[:2 * T - 1].view(2 * T - 1, H, 64).transpose(0, 1), lengths, 1 / 8.0)
+    ref = o.transpose(1, 2).reshape(M, Hd)
+    (ref * dout.float()).sum().backward()
+    out, lse = ops.attention_rel_fwd(qkv, pw, lengths, B, T, H, 1 / 8.0, save_lse=True)
+    _close(out, ref.detach(), rel=2e-2, name="rel attention out")
+    dqkv, dpw = ops.attention_rel_bwd(qkv, pw, lengths, out, dout, lse, B, T, H, 1 / 8.0)
+    valid = (torch.arange(T, device="cuda")[None, :] < lengths[:, None]).reshape(M, 1).float()
+    for i, nm in enumerate(["d(q+u)", "dk", "dv", "d(q+v)"]):
+        got, want = dqkv[:, i * Hd:(i + 1) * Hd].float(), qf.grad[:, i * Hd:(i + 1) * Hd]
+        if i in (1, 2):       # keys/values past the utterance end receive no gradient
+            assert float((got * (1 - valid)).abs().max()) == 0.0, nm
+        _close(got, want, rel=3e-2, name="rel " + nm)
+    _close(dpw, pf.grad, rel=3e-2, name="rel dPw")
 
 
 def test_attention_zero_length_row_is_nan_like_torch(ops):
