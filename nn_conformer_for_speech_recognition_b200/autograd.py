@@ -10,6 +10,7 @@ matrix product is the tcgen05 GEMM in one of its three operand-major modes:
 from __future__ import annotations
 
 import math
+import os
 from typing import List
 
 import torch
@@ -30,6 +31,17 @@ def conformer_apply(model: Conformer, inp: torch.Tensor, lengths_i32: torch.Tens
         y = run_layers(model, x, lengths_i32, B, T, None, model.training, drop_p, model.next_seed())
         return y.view(B, T, d)
     return _ConformerFn.apply(inp, lengths_i32, model, *params)
+
+
+_WGRAD_SIDE_STREAM = os.environ.get("B2C_WGRAD_STREAM", "1") != "0"
+_SIDE = {}
+
+
+def _side_stream(dev) -> torch.cuda.Stream:
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
 
 
 def _split_k(tokens: int, out_tiles: int, sms: int = 148) -> int:
@@ -100,11 +112,25 @@ class _ConformerFn(torch.autograd.Function):
             i = li * np_ + _LAYER_PARAMS.index(name)
             return arena[offs[i]:offs[i] + sizes[i]]
 
+        # Weight-gradient GEMMs have no consumer inside the backward pass: they go to a side stream, where their CTAs
+        # fill the SMs the dependent chain (dgrad GEMM -> LayerNorm backward -> cast ...) leaves idle in its tail waves
+        # and run next to the memory-bound kernels.  Operands stay referenced until the streams are joined again.
+        main = torch.cuda.current_stream()
+        side = _side_stream(dev) if _WGRAD_SIDE_STREAM else None
+        keep = []
+
         def wgrad(dyb, act, Mo, No, out):
             """out[Mo,No] += dyb[tokens,Mo]^T act[tokens,No]"""
             tiles = ((Mo + 127) // 128) * ((No + 127) // 128)
-            ops.gemm(dyb, act, M=Mo, N=No, K=M, a_mn=True, b_mn=True, out=out.view(Mo, No), accumulate=True,
-                     split_k=_split_k(M, tiles))
+            if side is None:
+                ops.gemm(dyb, act, M=Mo, N=No, K=M, a_mn=True, b_mn=True, out=out.view(Mo, No), accumulate=True,
+                         split_k=_split_k(M, tiles))
+                return
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ops.gemm(dyb, act, M=Mo, N=No, K=M, a_mn=True, b_mn=True, out=out.view(Mo, No), accumulate=True,
+                         split_k=_split_k(M, tiles))
+            keep.append((dyb, act))
 
         for li in reversed(range(model.num_layers)):
             layer = model.conformer_layers[li]
@@ -176,6 +202,9 @@ class _ConformerFn(torch.autograd.Function):
             ffn_bwd("ffn1", 0)
             ctx.state[li] = None                  # free this layer's saved activations
 
+        if side is not None:
+            main.wait_stream(side)
+            keep.clear()
         grads = []
         for li, layer in enumerate(model.conformer_layers):
             for n in _LAYER_PARAMS:

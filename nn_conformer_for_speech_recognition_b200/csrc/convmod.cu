@@ -20,35 +20,41 @@ namespace b2c {
 constexpr int CM_TT = 128;     // output frames per CTA
 constexpr int CM_CH = 64;      // channels per CTA
 constexpr int CM_MAXK = 33;    // taps (repo default k=33, Conformer S/M/L k=31)
-constexpr int CM_G = 8;        // outputs per register window
+constexpr int CM_G = 8;        // outputs per register window (backward)
+constexpr int CM_GF = 16;      // outputs per register window (forward: one window per warp)
 
-// stage GLU(u) for frames [t_lo, t_lo + nrow) of utterance b into smem (zero outside [0,T)).
-// Rows are taken 4 at a time per warp with all 8 global loads issued before any is consumed (memory-level
-// parallelism: the un-batched version exposed one DRAM round trip per row and dominated the kernel).
+// stage GLU(u) for frames [t_lo, t_lo + nrow) of utterance b into smem (zero outside [0,T)) as fp32 [row][64].
+// A half-warp takes one row (lane = 4 adjacent channels: one 8-byte load from each GLU half, one conflict-free
+// 16-byte smem store), so a warp instruction covers two rows and the CTA 16; loads are issued UN row-pairs deep before
+// the first is consumed (memory-level parallelism: the un-batched version exposed one DRAM round trip per row).
 __device__ __forceinline__ void stage_glu(const __nv_bfloat16* __restrict__ u, float2* __restrict__ sG, int b, int T,
                                           int d, int c0, int t_lo, int nrow) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ch = c0 + lane * 2;
-  const bool ch_ok = ch < d;
-  constexpr int UN = 4;
-  for (int r0 = warp; r0 < nrow; r0 += 8 * UN) {
-    uint32_t av[UN], gv[UN];
+  const int hl = lane & 15, rsel = lane >> 4;
+  const int ch = c0 + hl * 4;
+  const bool ch_ok = ch < d;                       // d % 8 == 0 and c0 % 64 == 0: a 4-channel group is all in or all out
+  constexpr int UN = 5;
+  float4* sG4 = reinterpret_cast<float4*>(sG);
+  for (int r0 = warp * 2 + rsel; r0 < nrow; r0 += 16 * UN) {
+    uint2 av[UN], gv[UN];
 #pragma unroll
     for (int q = 0; q < UN; ++q) {
-      const int r = r0 + q * 8, t = t_lo + r;
-      av[q] = gv[q] = 0u;
+      const int r = r0 + q * 16, t = t_lo + r;
+      av[q] = gv[q] = make_uint2(0u, 0u);
       if (r < nrow && t >= 0 && t < T && ch_ok) {
         const __nv_bfloat16* row = u + (static_cast<int64_t>(b) * T + t) * (2 * d);
-        av[q] = *reinterpret_cast<const uint32_t*>(row + ch);
-        gv[q] = *reinterpret_cast<const uint32_t*>(row + d + ch);
+        av[q] = *reinterpret_cast<const uint2*>(row + ch);
+        gv[q] = *reinterpret_cast<const uint2*>(row + d + ch);
       }
     }
 #pragma unroll
     for (int q = 0; q < UN; ++q) {
-      const int r = r0 + q * 8;
+      const int r = r0 + q * 16;
       if (r < nrow) {
-        const float2 a = unpack_bf16(av[q]), gt = unpack_bf16(gv[q]);
-        sG[r * 32 + lane] = make_float2(a.x * sigmoid_f(gt.x), a.y * sigmoid_f(gt.y));   // zero rows: 0 * 0.5 = 0
+        const float2 a0 = unpack_bf16(av[q].x), a1 = unpack_bf16(av[q].y);
+        const float2 g0 = unpack_bf16(gv[q].x), g1 = unpack_bf16(gv[q].y);
+        sG4[r * 16 + hl] = make_float4(a0.x * sigmoid_f(g0.x), a0.y * sigmoid_f(g0.y), a1.x * sigmoid_f(g1.x),
+                                       a1.y * sigmoid_f(g1.y));                          // zero rows: 0 * 0.5 = 0
       }
     }
   }
@@ -65,7 +71,7 @@ __device__ __forceinline__ void stage_taps(const float* __restrict__ wdw, float*
 // MODE 1: train -> y (bf16) + per-channel sum / sumsq   (stats fp64 [2][d], atomics once per CTA per channel)
 // KT = compile-time tap count (31, 33) or 0 = run-time k: with KT known the window loop has no branches and no dead taps
 template <int MODE, int KT>
-__global__ void __launch_bounds__(256) convmod_fwd_kernel(const __nv_bfloat16* __restrict__ u,
+__global__ void __launch_bounds__(256, 2) convmod_fwd_kernel(const __nv_bfloat16* __restrict__ u,
                                                           const float* __restrict__ wdw, const float* __restrict__ bdw,
                                                           const float* __restrict__ bn_w, const float* __restrict__ bn_b,
                                                           const float* __restrict__ bn_mean,
@@ -87,13 +93,12 @@ __global__ void __launch_bounds__(256) convmod_fwd_kernel(const __nv_bfloat16* _
   stage_glu(u, sG, b, T, d, c0, t0 - half, CM_TT + k - 1);
   __syncthreads();
 
-  float w0[NTAP], w1[NTAP];
+  float2 w[NTAP];                                  // taps of this lane's channel pair (FFMA2 operands)
 #pragma unroll
-  for (int j = 0; j < NTAP; ++j) {
-    const float2 wv = j < k ? *reinterpret_cast<const float2*>(sWt + j * CM_CH + lane * 2) : make_float2(0.f, 0.f);
-    w0[j] = wv.x; w1[j] = wv.y;
-  }
-  const float bias0 = ch_ok ? __ldg(bdw + ch) : 0.f, bias1 = ch_ok ? __ldg(bdw + ch + 1) : 0.f;
+  for (int j = 0; j < NTAP; ++j)
+    w[j] = j < k ? *reinterpret_cast<const float2*>(sWt + j * CM_CH + lane * 2) : make_float2(0.f, 0.f);
+  float2 bias = make_float2(0.f, 0.f);
+  if (ch_ok) bias = *reinterpret_cast<const float2*>(bdw + ch);
   float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
   if (MODE == 0 && ch_ok) {
     sc0 = __ldg(bn_w + ch) * rsqrtf(__ldg(bn_var + ch) + eps);
@@ -103,40 +108,40 @@ __global__ void __launch_bounds__(256) convmod_fwd_kernel(const __nv_bfloat16* _
   }
 
   float s_sum0 = 0.f, s_sum1 = 0.f, s_sq0 = 0.f, s_sq1 = 0.f;
-#pragma unroll 1
-  for (int grp = 0; grp < (CM_TT / 8) / CM_G; ++grp) {          // 16 frames per warp = 2 groups of 8
-    const int tl = warp * (CM_TT / 8) + grp * CM_G;             // first local output frame of the group
-    float a0[CM_G], a1[CM_G];
+  static_assert(CM_TT / 8 == CM_GF, "one register window per warp");
+  {
+    const int tl = warp * CM_GF;                                // first local output frame of this warp
+    float2 a[CM_GF];
 #pragma unroll
-    for (int i = 0; i < CM_G; ++i) { a0[i] = bias0; a1[i] = bias1; }
-    // window rows tl .. tl + CM_G + k - 2 ; output i uses rows tl+i .. tl+i+k-1 with taps 0..k-1
+    for (int i = 0; i < CM_GF; ++i) a[i] = bias;
+    // window rows tl .. tl + CM_GF + k - 2 ; output i uses rows tl+i .. tl+i+k-1 with taps 0..k-1
 #pragma unroll
-    for (int r = 0; r < CM_G + NTAP - 1; ++r) {
-      if (KT || r < CM_G + k - 1) {
+    for (int r = 0; r < CM_GF + NTAP - 1; ++r) {
+      if (KT || r < CM_GF + k - 1) {
         const float2 g = sG[(tl + r) * 32 + lane];
 #pragma unroll
-        for (int i = 0; i < CM_G; ++i) {
+        for (int i = 0; i < CM_GF; ++i) {
           const int j = r - i;
-          if (j >= 0 && j < NTAP) { a0[i] = fmaf(g.x, w0[j], a0[i]); a1[i] = fmaf(g.y, w1[j], a1[i]); }
+          if (j >= 0 && j < NTAP) a[i] = ffma2(g, w[j], a[i]);
         }
       }
     }
+    __nv_bfloat16* orow = out + (static_cast<int64_t>(b) * T + t0 + tl) * d + ch;
 #pragma unroll
-    for (int i = 0; i < CM_G; ++i) {
-      const int t = t0 + tl + i;
-      if (t < T && ch_ok) {
-        float y0 = a0[i], y1 = a1[i];
+    for (int i = 0; i < CM_GF; ++i) {
+      if (t0 + tl + i < T && ch_ok) {
+        float y0 = a[i].x, y1 = a[i].y;
         if (MODE == 1) {
           // statistics of the STORED (bf16-rounded) tensor: BatchNorm and its backward then see exactly the y they
           // normalise, so sum(yhat) = 0 and the analytically-zero gradients (depthwise bias) stay ~0
-          const float2 yr = unpack_bf16(pack_bf16(y0, y1));
-          y0 = yr.x; y1 = yr.y;
-          s_sum0 += y0; s_sum1 += y1; s_sq0 += y0 * y0; s_sq1 += y1 * y1;
+          const uint32_t pk = pack_bf16(y0, y1);
+          const float2 yr = unpack_bf16(pk);
+          s_sum0 += yr.x; s_sum1 += yr.y; s_sq0 = fmaf(yr.x, yr.x, s_sq0); s_sq1 = fmaf(yr.y, yr.y, s_sq1);
+          *reinterpret_cast<uint32_t*>(orow + static_cast<int64_t>(i) * d) = pk;
         } else {
-          y0 = silu_f(y0 * sc0 + sh0);
-          y1 = silu_f(y1 * sc1 + sh1);
+          *reinterpret_cast<uint32_t*>(orow + static_cast<int64_t>(i) * d) =
+              pack_bf16(silu_f(fmaf(y0, sc0, sh0)), silu_f(fmaf(y1, sc1, sh1)));
         }
-        *reinterpret_cast<uint32_t*>(out + (static_cast<int64_t>(b) * T + t) * d + ch) = pack_bf16(y0, y1);
       }
     }
   }
@@ -171,25 +176,45 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
   }
 }
 
+// Thread = one fixed group of 8 channels (folded scale/shift live in registers) walking down the rows: one 16-byte load
+// and store per 8 elements, four rows in flight per thread.
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                                       const float* __restrict__ rstd, const float* __restrict__ bn_w,
                                                       const float* __restrict__ bn_b, __nv_bfloat16* __restrict__ out,
-                                                      int64_t n8, int d) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // index of an 8-element chunk
-  if (i >= n8) return;
-  const int c = static_cast<int>((i * 8) % d);
-  const uint4 v = reinterpret_cast<const uint4*>(y)[i];
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  uint32_t o[4];
+                                                      int64_t rows, int d, int rows_per_block) {
+  const int cg = d >> 3, rpi = 256 / cg;                 // channel groups per row, rows per CTA step
+  const int tr = threadIdx.x / cg, tg = threadIdx.x - tr * cg;
+  if (tr >= rpi) return;
+  float sc[8], sh[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 f = unpack_bf16(w[j]);
-    const int cc = c + 2 * j;
-    const float z0 = (f.x - __ldg(mean + cc)) * __ldg(rstd + cc) * __ldg(bn_w + cc) + __ldg(bn_b + cc);
-    const float z1 = (f.y - __ldg(mean + cc + 1)) * __ldg(rstd + cc + 1) * __ldg(bn_w + cc + 1) + __ldg(bn_b + cc + 1);
-    o[j] = pack_bf16(silu_f(z0), silu_f(z1));
+  for (int j = 0; j < 8; ++j) {
+    const int c = tg * 8 + j;
+    sc[j] = __ldg(rstd + c) * __ldg(bn_w + c);
+    sh[j] = __ldg(bn_b + c) - __ldg(mean + c) * sc[j];
   }
-  reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  const int64_t r_end = min(rows, (static_cast<int64_t>(blockIdx.x) + 1) * rows_per_block);
+  constexpr int UN = 4;
+  for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + tr; r0 < r_end; r0 += static_cast<int64_t>(UN) * rpi) {
+    uint4 v[UN];
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const int64_t r = r0 + static_cast<int64_t>(q) * rpi;
+      if (r < r_end) v[q] = *reinterpret_cast<const uint4*>(y + r * d + tg * 8);
+    }
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const int64_t r = r0 + static_cast<int64_t>(q) * rpi;
+      if (r >= r_end) break;
+      const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(w[j]);
+        o[j] = pack_bf16(silu_f(fmaf(f.x, sc[2 * j], sh[2 * j])), silu_f(fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1])));
+      }
+      *reinterpret_cast<uint4*>(out + r * d + tg * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
 }
 
 
@@ -208,33 +233,57 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
                                                            const float* __restrict__ bn_w, const float* __restrict__ bn_b,
                                                            double* __restrict__ sums, int64_t rows, int d,
                                                            int rows_per_block) {
-  __shared__ float red[2][8][64];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int ch = blockIdx.x * 64 + tx * 2;
-  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
-  const int64_t r1 = min(rows, r0 + rows_per_block);
-  float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-  if (ch < d) {
-    const float m0 = mean[ch], m1 = mean[ch + 1], q0 = rstd[ch], q1 = rstd[ch + 1];
-    const float g0 = bn_w[ch], g1 = bn_w[ch + 1], b0 = bn_b[ch], b1 = bn_b[ch + 1];
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
-      const float2 dcv = unpack_bf16(*reinterpret_cast<const uint32_t*>(dc + r * d + ch));
-      const float2 yv = unpack_bf16(*reinterpret_cast<const uint32_t*>(y + r * d + ch));
-      const float yh0 = (yv.x - m0) * q0, yh1 = (yv.y - m1) * q1;
-      const float dz0 = dcv.x * silu_grad_f(yh0 * g0 + b0), dz1 = dcv.y * silu_grad_f(yh1 * g1 + b1);
-      s1a += dz0; s1b += dz1; s2a += dz0 * yh0; s2b += dz1 * yh1;
+  // thread = fixed group of 8 channels walking down this CTA's rows (16-byte loads, 2 x 4 rows in flight); the CTA's
+  // partial sums meet in shared memory and leave as one fp64 atomic per channel
+  extern __shared__ float red_dyn[];                     // [2][d]
+  const int cg = d >> 3, rpi = 256 / cg;
+  const int tr = threadIdx.x / cg, tg = threadIdx.x - tr * cg;
+  for (int i = threadIdx.x; i < 2 * d; i += 256) red_dyn[i] = 0.f;
+  __syncthreads();
+  if (tr < rpi) {
+    float m[8], q[8], g[8], bb[8], s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = tg * 8 + j;
+      m[j] = __ldg(mean + c); q[j] = __ldg(rstd + c); g[j] = __ldg(bn_w + c); bb[j] = __ldg(bn_b + c);
+      s1[j] = s2[j] = 0.f;
+    }
+    const int64_t r_end = min(rows, (static_cast<int64_t>(blockIdx.x) + 1) * rows_per_block);
+    constexpr int UN = 4;
+    for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + tr; r0 < r_end; r0 += static_cast<int64_t>(UN) * rpi) {
+      uint4 vd[UN], vy[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int64_t r = r0 + static_cast<int64_t>(u) * rpi;
+        if (r < r_end) {
+          vd[u] = *reinterpret_cast<const uint4*>(dc + r * d + tg * 8);
+          vy[u] = *reinterpret_cast<const uint4*>(y + r * d + tg * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int64_t r = r0 + static_cast<int64_t>(u) * rpi;
+        if (r >= r_end) break;
+        const uint32_t wd[4] = {vd[u].x, vd[u].y, vd[u].z, vd[u].w}, wy[4] = {vy[u].x, vy[u].y, vy[u].z, vy[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 dcv = unpack_bf16(wd[j]), yv = unpack_bf16(wy[j]);
+          const float yh0 = (yv.x - m[2 * j]) * q[2 * j], yh1 = (yv.y - m[2 * j + 1]) * q[2 * j + 1];
+          const float dz0 = dcv.x * silu_grad_f(fmaf(yh0, g[2 * j], bb[2 * j]));
+          const float dz1 = dcv.y * silu_grad_f(fmaf(yh1, g[2 * j + 1], bb[2 * j + 1]));
+          s1[2 * j] += dz0; s1[2 * j + 1] += dz1;
+          s2[2 * j] = fmaf(dz0, yh0, s2[2 * j]); s2[2 * j + 1] = fmaf(dz1, yh1, s2[2 * j + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red_dyn[tg * 8 + j], s1[j]);
+      atomicAdd(&red_dyn[d + tg * 8 + j], s2[j]);
     }
   }
-  red[0][ty][tx * 2] = s1a; red[0][ty][tx * 2 + 1] = s1b;
-  red[1][ty][tx * 2] = s2a; red[1][ty][tx * 2 + 1] = s2b;
   __syncthreads();
-  if (threadIdx.x < 128) {
-    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
-    float sum = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) sum += red[which][w][c];
-    if (blockIdx.x * 64 + c < d) atomicAdd(sums + static_cast<int64_t>(which) * d + blockIdx.x * 64 + c, static_cast<double>(sum));
-  }
+  for (int i = threadIdx.x; i < 2 * d; i += 256) atomicAdd(sums + i, static_cast<double>(red_dyn[i]));
 }
 
 // pass 2: dy on the fly -> du (through depthwise conv + GLU), dwdw, dbdw (fp32 atomics), dbn_w/dbn_b (from sums)
@@ -265,47 +314,60 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
   stage_taps(wdw, sWt, c0, d, k);
   stage_glu(u, sG, b, T, d, c0, t0 - half, nrow);
   {
-    float m0 = 0, m1 = 0, q0 = 0, q1 = 0, g0 = 0, g1 = 0, b0 = 0, b1 = 0, a10 = 0, a11 = 0, a20 = 0, a21 = 0;
-    if (ch_ok) {
-      m0 = mean[ch]; m1 = mean[ch + 1]; q0 = rstd[ch]; q1 = rstd[ch + 1];
-      g0 = bn_w[ch]; g1 = bn_w[ch + 1]; b0 = bn_b[ch]; b1 = bn_b[ch + 1];
-      if (BN_TRAIN) {
-        a10 = static_cast<float>(sums[ch] * inv_count); a11 = static_cast<float>(sums[ch + 1] * inv_count);
-        a20 = static_cast<float>(sums[d + ch] * inv_count); a21 = static_cast<float>(sums[d + ch + 1] * inv_count);
-      }
-      if (blockIdx.x == 0 && blockIdx.z == 0 && warp == 0) {     // parameter grads of BN = the two sums
-        atomicAdd(dbn_b + ch, static_cast<float>(sums[ch])); atomicAdd(dbn_b + ch + 1, static_cast<float>(sums[ch + 1]));
-        atomicAdd(dbn_w + ch, static_cast<float>(sums[d + ch])); atomicAdd(dbn_w + ch + 1, static_cast<float>(sums[d + ch + 1]));
+    if (ch_ok && blockIdx.x == 0 && blockIdx.z == 0 && warp == 0) {     // parameter grads of BN = the two sums
+      atomicAdd(dbn_b + ch, static_cast<float>(sums[ch])); atomicAdd(dbn_b + ch + 1, static_cast<float>(sums[ch + 1]));
+      atomicAdd(dbn_w + ch, static_cast<float>(sums[d + ch])); atomicAdd(dbn_w + ch + 1, static_cast<float>(sums[d + ch + 1]));
+    }
+    // same half-warp-per-row / 4-channels-per-lane scheme as stage_glu (the lane's channel quad differs from its
+    // compute pair, so the per-channel constants are re-read here through the read-only path)
+    const int hl = lane & 15, rsel = lane >> 4;
+    const int ch4 = c0 + hl * 4;
+    const bool ch4_ok = ch4 < d;
+    float pm[4], pq[4], pg[4], pb[4], pa1[4], pa2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pm[j] = pq[j] = pg[j] = pb[j] = pa1[j] = pa2[j] = 0.f;
+      if (ch4_ok) {
+        pm[j] = __ldg(mean + ch4 + j); pq[j] = __ldg(rstd + ch4 + j); pg[j] = __ldg(bn_w + ch4 + j); pb[j] = __ldg(bn_b + ch4 + j);
+        if (BN_TRAIN) {
+          pa1[j] = static_cast<float>(sums[ch4 + j] * inv_count);
+          pa2[j] = static_cast<float>(sums[d + ch4 + j] * inv_count);
+        }
       }
     }
-    constexpr int UN = 4;
-    for (int r0 = warp; r0 < nrow; r0 += 8 * UN) {
-      uint32_t dcr[UN], yr[UN];
+    float4* sDY4 = reinterpret_cast<float4*>(sDY);
+    constexpr int UN = 5;
+    for (int r0 = warp * 2 + rsel; r0 < nrow; r0 += 16 * UN) {
+      uint2 dcr[UN], yr[UN];
       bool ok[UN];
 #pragma unroll
       for (int q = 0; q < UN; ++q) {
-        const int r = r0 + q * 8, t = t0 - half + r;
-        ok[q] = r < nrow && t >= 0 && t < T && ch_ok;
-        dcr[q] = yr[q] = 0u;
+        const int r = r0 + q * 16, t = t0 - half + r;
+        ok[q] = r < nrow && t >= 0 && t < T && ch4_ok;
+        dcr[q] = yr[q] = make_uint2(0u, 0u);
         if (ok[q]) {
           const int64_t row = static_cast<int64_t>(b) * T + t;
-          dcr[q] = *reinterpret_cast<const uint32_t*>(dc + row * d + ch);
-          yr[q] = *reinterpret_cast<const uint32_t*>(y + row * d + ch);
+          dcr[q] = *reinterpret_cast<const uint2*>(dc + row * d + ch4);
+          yr[q] = *reinterpret_cast<const uint2*>(y + row * d + ch4);
         }
       }
 #pragma unroll
       for (int q = 0; q < UN; ++q) {
-        const int r = r0 + q * 8;
+        const int r = r0 + q * 16;
         if (r >= nrow) continue;
-        float2 dyv = make_float2(0.f, 0.f);
+        float dyv[4] = {0.f, 0.f, 0.f, 0.f};
         if (ok[q]) {
-          const float2 dcv = unpack_bf16(dcr[q]), yv = unpack_bf16(yr[q]);
-          const float yh0 = (yv.x - m0) * q0, yh1 = (yv.y - m1) * q1;
-          const float dz0 = dcv.x * silu_grad_f(yh0 * g0 + b0), dz1 = dcv.y * silu_grad_f(yh1 * g1 + b1);
-          dyv.x = g0 * q0 * (BN_TRAIN ? (dz0 - a10 - yh0 * a20) : dz0);
-          dyv.y = g1 * q1 * (BN_TRAIN ? (dz1 - a11 - yh1 * a21) : dz1);
+          const float2 d01 = unpack_bf16(dcr[q].x), d23 = unpack_bf16(dcr[q].y);
+          const float2 y01 = unpack_bf16(yr[q].x), y23 = unpack_bf16(yr[q].y);
+          const float dcv[4] = {d01.x, d01.y, d23.x, d23.y}, yv[4] = {y01.x, y01.y, y23.x, y23.y};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float yh = (yv[j] - pm[j]) * pq[j];
+            const float dz = dcv[j] * silu_grad_f(fmaf(yh, pg[j], pb[j]));
+            dyv[j] = pg[j] * pq[j] * (BN_TRAIN ? (dz - pa1[j] - yh * pa2[j]) : dz);
+          }
         }
-        sDY[r * 32 + lane] = dyv;
+        sDY4[r * 16 + hl] = make_float4(dyv[0], dyv[1], dyv[2], dyv[3]);
       }
     }
   }
@@ -313,18 +375,16 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
 
   // ---- phase 1: dg = correlate(dy, reversed taps) for this warp's 16 frames, then du through the GLU ----
   {
-    float w0[CM_MAXK], w1[CM_MAXK];                   // REVERSED taps: wr[j'] = w[k-1-j']
+    float2 w[CM_MAXK];                                // REVERSED taps: wr[j'] = w[k-1-j']
 #pragma unroll
-    for (int j = 0; j < CM_MAXK; ++j) {
-      const float2 wv = j < k ? *reinterpret_cast<const float2*>(sWt + (k - 1 - j) * CM_CH + lane * 2) : make_float2(0.f, 0.f);
-      w0[j] = wv.x; w1[j] = wv.y;
-    }
+    for (int j = 0; j < CM_MAXK; ++j)
+      w[j] = j < k ? *reinterpret_cast<const float2*>(sWt + (k - 1 - j) * CM_CH + lane * 2) : make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int grp = 0; grp < (CM_TT / 8) / CM_G; ++grp) {
       const int tl = warp * (CM_TT / 8) + grp * CM_G;
-      float a0[CM_G], a1[CM_G];
+      float2 a[CM_G];
 #pragma unroll
-      for (int i = 0; i < CM_G; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
+      for (int i = 0; i < CM_G; ++i) a[i] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < CM_G + CM_MAXK - 1; ++r) {
         if (r < CM_G + k - 1) {
@@ -332,7 +392,7 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
 #pragma unroll
           for (int i = 0; i < CM_G; ++i) {
             const int j = r - i;
-            if (j >= 0 && j < CM_MAXK) { a0[i] = fmaf(dyr.x, w0[j], a0[i]); a1[i] = fmaf(dyr.y, w1[j], a1[i]); }
+            if (j >= 0 && j < CM_MAXK) a[i] = ffma2(dyr, w[j], a[i]);
           }
         }
       }
@@ -344,18 +404,18 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
           const float2 av = unpack_bf16(*reinterpret_cast<const uint32_t*>(u + row * 2 * d + ch));
           const float2 bv = unpack_bf16(*reinterpret_cast<const uint32_t*>(u + row * 2 * d + d + ch));
           const float s0 = sigmoid_f(bv.x), s1 = sigmoid_f(bv.y);
-          *reinterpret_cast<uint32_t*>(du + row * 2 * d + ch) = pack_bf16(a0[i] * s0, a1[i] * s1);
+          *reinterpret_cast<uint32_t*>(du + row * 2 * d + ch) = pack_bf16(a[i].x * s0, a[i].y * s1);
           *reinterpret_cast<uint32_t*>(du + row * 2 * d + d + ch) =
-              pack_bf16(a0[i] * av.x * s0 * (1.f - s0), a1[i] * av.y * s1 * (1.f - s1));
+              pack_bf16(a[i].x * av.x * s0 * (1.f - s0), a[i].y * av.y * s1 * (1.f - s1));
         }
       }
     }
   }
 
   // ---- phase 2: dw[j] += dy[t] * g[t + j - h] over this warp's frames (taps are dead: registers are reused) ----
-  float acc0[CM_MAXK], acc1[CM_MAXK];
+  float2 acc[CM_MAXK];
 #pragma unroll
-  for (int j = 0; j < CM_MAXK; ++j) acc0[j] = acc1[j] = 0.f;
+  for (int j = 0; j < CM_MAXK; ++j) acc[j] = make_float2(0.f, 0.f);
   float dbs0 = 0.f, dbs1 = 0.f;
 #pragma unroll 1
   for (int grp = 0; grp < (CM_TT / 8) / CM_G; ++grp) {
@@ -373,7 +433,7 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
 #pragma unroll
         for (int i = 0; i < CM_G; ++i) {
           const int j = r - i;
-          if (j >= 0 && j < CM_MAXK) { acc0[j] = fmaf(dyc[i].x, gr.x, acc0[j]); acc1[j] = fmaf(dyc[i].y, gr.y, acc1[j]); }
+          if (j >= 0 && j < CM_MAXK) acc[j] = ffma2(dyc[i], gr, acc[j]);
         }
       }
     }
@@ -382,8 +442,8 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
 #pragma unroll
   for (int j = 0; j < CM_MAXK; ++j) {
     if (j < k) {
-      atomicAdd(&sW[(lane * 2) * (CM_MAXK + 1) + j], acc0[j]);
-      atomicAdd(&sW[(lane * 2 + 1) * (CM_MAXK + 1) + j], acc1[j]);
+      atomicAdd(&sW[(lane * 2) * (CM_MAXK + 1) + j], acc[j].x);
+      atomicAdd(&sW[(lane * 2 + 1) * (CM_MAXK + 1) + j], acc[j].y);
     }
   }
   atomicAdd(&sW[(lane * 2) * (CM_MAXK + 1) + CM_MAXK], dbs0);
@@ -471,10 +531,16 @@ extern "C" int b2c_convmod_bn_apply(const void* y, const float* mean, const floa
                                     const float* bn_b, void* out, int64_t rows, int d, void* stream) {
   B2C_REQUIRE(y && mean && rstd && bn_w && bn_b && out, "b2c_convmod_bn_apply: null pointer");
   B2C_REQUIRE(d % 8 == 0, "b2c_convmod_bn_apply: d must be a multiple of 8");
-  const int64_t n8 = rows * d / 8;
-  if (n8 <= 0) return 0;
-  bn_apply_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), mean, rstd, bn_w, bn_b, static_cast<__nv_bfloat16*>(out), n8, d);
+  B2C_REQUIRE(d <= 2048, "b2c_convmod_bn_apply: d must be <= 2048");
+  if (rows <= 0) return 0;
+  const int rpi = 256 / (d / 8);
+  int64_t nblk = static_cast<int64_t>(num_sms()) * 4;    // a few fat CTAs: the per-thread constants are set up once
+  int64_t rpb = (rows + nblk - 1) / nblk;
+  rpb = ((rpb + rpi - 1) / rpi) * rpi;
+  nblk = (rows + rpb - 1) / rpb;
+  bn_apply_kernel<<<static_cast<unsigned>(nblk), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), mean, rstd, bn_w, bn_b, static_cast<__nv_bfloat16*>(out), rows, d,
+      static_cast<int>(rpb));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -485,14 +551,15 @@ extern "C" int b2c_convmod_bn_bwd_reduce(const void* dc, const void* y, const fl
   B2C_REQUIRE(dc && y && mean && rstd && bn_w && bn_b && sums, "b2c_convmod_bn_bwd_reduce: null pointer");
   B2C_REQUIRE(d % 8 == 0, "b2c_convmod_bn_bwd_reduce: d must be a multiple of 8");
   if (rows <= 0) return 0;
-  const unsigned gx = static_cast<unsigned>((d + 63) / 64);
-  int64_t want_y = (static_cast<int64_t>(num_sms()) * 4 + gx - 1) / gx;
-  int rows_per_block = static_cast<int>((rows + want_y - 1) / want_y);
-  rows_per_block = ((rows_per_block + 7) / 8) * 8;
-  const unsigned gy = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
-  bn_bwd_reduce_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  B2C_REQUIRE(d <= 2048, "b2c_convmod_bn_bwd_reduce: d must be <= 2048");
+  const int rpi = 256 / (d / 8);
+  int64_t nblk = static_cast<int64_t>(num_sms()) * 2;    // every CTA ends with 2*d fp64 atomics: keep the CTA count low
+  int64_t rpb = (rows + nblk - 1) / nblk;
+  rpb = ((rpb + rpi - 1) / rpi) * rpi;
+  nblk = (rows + rpb - 1) / rpb;
+  bn_bwd_reduce_kernel<<<static_cast<unsigned>(nblk), 256, 2 * d * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dc), static_cast<const __nv_bfloat16*>(y), mean, rstd, bn_w, bn_b, sums, rows, d,
-      rows_per_block);
+      static_cast<int>(rpb));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

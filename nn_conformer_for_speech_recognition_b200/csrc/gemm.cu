@@ -36,6 +36,17 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int EPI_WARPS = 16;                 // 4 per TMEM lane quarter, each owning BN/4 columns of the tile
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+#ifndef B2C_DEFAULT_CLUSTER
+#define B2C_DEFAULT_CLUSTER 1                   // multicast cluster size picked when block_n = 0 (env B2C_GEMM_CLUSTER overrides)
+#endif
+
+#ifdef B2C_GEMM_TIMING
+// debug builds only (make EXTRA=-DB2C_GEMM_TIMING): cycle stamps of CTA 0, read back with b2c_debug_gemm_timing
+__device__ long long g_gemm_dbg[3 * 16 * 32];
+#define B2C_GT(role, it_, slot) do { if (blockIdx.x == 0 && (it_) < 16 && (slot) < 32) g_gemm_dbg[((role) * 16 + (it_)) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define B2C_GT(role, it_, slot) do {} while (0)
+#endif
 
 struct GemmParams {
   DropCfg drop;
@@ -80,15 +91,23 @@ enum : int {
 // [r BN/2, (r+1) BN/2); the leader (r = 0) issues every MMA and its commits fan out to both CTAs' barriers.
 // EXTRA = false compiles the training-only extras (saved pre-activation, dropout, fused column sums) out of the
 // specialised epilogues; the generic epilogue always keeps them (run-time switched).
-template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA>
+// CL > 1 (only with CTA2 = false): launched as clusters of CL CTAs that work on CL vertically adjacent 128-row tiles of
+// the SAME n-block.  Every CTA fetches 1/CL of the B tile and TMA-multicasts it into all CL shared memories, so the
+// B bytes cross the L2 -> SM fabric once per cluster instead of once per CTA (these GEMMs are bound by that fabric,
+// not by HBM or the tensor pipe: K is only 256..1024, so a 128 x BN tile re-reads BN x K weights for ~1-2 k cycles of
+// MMA).  A stage is recycled only after the MMAs of all CL CTAs that read it have retired (multicast commit).
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA, int CL = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmB,
                                                                        const GemmParams p) {
   using Cfg = GemmCfg<BN, CTA2>;
   constexpr int BNH = Cfg::BNH;
-  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
-  const int tile0 = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  static_assert(!(CTA2 && CL > 1), "multicast clusters and CTA pairs are separate paths");
+  constexpr int CDIV = CTA2 ? 2 : CL;                    // CTAs that share one tile index
+  constexpr uint16_t CL_MASK = static_cast<uint16_t>((1u << CL) - 1u);
+  const uint32_t rank = CDIV > 1 ? cluster_ctarank() : 0u;
+  const int tile0 = static_cast<int>(blockIdx.x) / CDIV;
+  const int tile_step = static_cast<int>(gridDim.x) / CDIV;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -105,7 +124,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);                      // multicast clusters: every CTA's MMAs release the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -118,7 +137,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CTA2) cluster_sync_all();                // peer barriers are initialised before anything signals them
+  if constexpr (CDIV > 1) cluster_sync_all();            // peer barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -127,15 +146,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+      [[maybe_unused]] int pit = 0;
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++pit) {
         const int n_blk = tile % p.n_tiles;
-        const int m_blk = ((tile / p.n_tiles) % p.m_tiles) * (CTA2 ? 2 : 1) + static_cast<int>(rank);
+        const int m_blk = ((tile / p.n_tiles) % p.m_tiles) * CDIV + static_cast<int>(rank);
         const int split = tile / (p.n_tiles * p.m_tiles);
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(p.total_kb, kb0 + p.kblocks_per_split);
-        const int b_row0 = n_blk * BN + static_cast<int>(rank) * BNH;      // this CTA's slice of B's N rows
+        const int b_row0 = n_blk * BN + (CTA2 ? static_cast<int>(rank) * BNH : 0);   // pair: this CTA's half of B's N rows
         for (int kb = kb0; kb < kb1; ++kb) {
+          B2C_GT(0, pit, 2 * (kb - kb0));
           mbar_wait(&empty_bar[s], ph ^ 1u);
+          B2C_GT(0, pit, 2 * (kb - kb0) + 1);
           uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
           if constexpr (!CTA2) {
@@ -146,11 +168,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
               for (int c = 0; c < BM / 64; ++c) tma_load_2d(sA + c * 8192, &tmA, &full_bar[s], m_blk * BM + c * 64, kb * BK);
             }
-            if constexpr (!B_MN) {
-              tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, b_row0);
-            } else {
+            if constexpr (CL == 1) {
+              if constexpr (!B_MN) {
+                tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, b_row0);
+              } else {
 #pragma unroll
-              for (int c = 0; c < BNH / 64; ++c) tma_load_2d(sB + c * 8192, &tmB, &full_bar[s], b_row0 + c * 64, kb * BK);
+                for (int c = 0; c < BNH / 64; ++c) tma_load_2d(sB + c * 8192, &tmB, &full_bar[s], b_row0 + c * 64, kb * BK);
+              }
+            } else {
+              // this CTA's 1/CL slice of the B tile, delivered to the same smem offset (and full barrier) of all CL CTAs
+              if constexpr (!B_MN) {
+                constexpr int RS = BN / CL;            // rows per slice (tensor-map box height)
+                tma_load_2d_mc(sB + rank * (RS * 128), &tmB, &full_bar[s], kb * BK, b_row0 + static_cast<int>(rank) * RS, CL_MASK);
+              } else {
+                constexpr int CS = (BN / 64) / CL;     // 64-column chunks per slice
+                static_assert(CS >= 1, "cluster too large for this tile width");
+#pragma unroll
+                for (int c = 0; c < CS; ++c) {
+                  const int cc = static_cast<int>(rank) * CS + c;
+                  tma_load_2d_mc(sB + cc * 8192, &tmB, &full_bar[s], b_row0 + cc * 64, kb * BK, CL_MASK);
+                }
+              }
             }
           } else {
             // both CTAs' bytes land on the LEADER's full barrier (it alone waits before issuing the pair MMA)
@@ -175,7 +213,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0 && rank == 0) {
+    if (lane == 0 && (!CTA2 || rank == 0)) {        // pairs: the leader issues for both CTAs
       constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BM : BM, BN, A_MN, B_MN);
       int s = 0;
       uint32_t ph = 0;
@@ -185,11 +223,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(p.total_kb, kb0 + p.kblocks_per_split);
         const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+        B2C_GT(1, it, 0);
         mbar_wait(&tempty_bar[as], aph ^ 1u);          // epilogue has drained this accumulator buffer
+        B2C_GT(1, it, 1);
         tc_fence_after();
         const uint32_t tm_acc = tmem_base + as * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
+          B2C_GT(1, it, 2 + 2 * (kb - kb0));
           mbar_wait(&full_bar[s], ph);
+          B2C_GT(1, it, 3 + 2 * (kb - kb0));
           tc_fence_after();
           const uint32_t a_addr = base + s * Cfg::STAGE_BYTES;
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
@@ -203,7 +245,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             else umma_bf16(tm_acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           // smem slot free once these MMAs retire (pair: in both CTAs)
-          if constexpr (CTA2) tc_commit_2sm(&empty_bar[s]); else tc_commit(&empty_bar[s]);
+          if constexpr (CTA2) tc_commit_2sm(&empty_bar[s]);
+          else if constexpr (CL > 1) tc_commit_mc(&empty_bar[s], CL_MASK);
+          else tc_commit(&empty_bar[s]);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
         }
         // accumulator complete -> epilogue (pair: each CTA's epilogue drains its own 128 rows)
@@ -229,7 +273,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     uint32_t it = 0;
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++it) {
       const int n_blk = tile % p.n_tiles;
-      const int m_blk = ((tile / p.n_tiles) % p.m_tiles) * (CTA2 ? 2 : 1) + static_cast<int>(rank);
+      const int m_blk = ((tile / p.n_tiles) % p.m_tiles) * CDIV + static_cast<int>(rank);
       const int split = tile / (p.n_tiles * p.m_tiles);
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const float* bias = split == 0 ? static_cast<const float*>(ep.bias) : nullptr;   // once per split-K
@@ -273,7 +317,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             }
         }
         if (ch == 0) {
+          if (ew == 0 && lane == 0) B2C_GT(2, it, 0);
           mbar_wait(&tfull_bar[as], aph);
+          if (ew == 0 && lane == 0) B2C_GT(2, it, 1);
           tc_fence_after();
         }
         uint32_t v[CW];
@@ -281,6 +327,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16) + col_t;
         if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         tmem_wait_ld();
+        if (ew == 0 && lane == 0) B2C_GT(2, it, 2 + 2 * ch);
         if (ch == Cfg::CHUNKS - 1) {                   // all of this warp's TMEM reads for the tile are done
           tc_fence_before();
           __syncwarp();
@@ -349,6 +396,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             }
             if (out_bf16) {
               const uint2 packed = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+#ifdef B2C_DBG_NOSTORE
+              if (packed.x == 0x12345678u && packed.y == 0x9abcdef0u)      // never true in practice: keeps the math alive
+#endif
               *reinterpret_cast<uint2*>(ob) = packed;
               ob += o_step;
               if (do_colsum) {                         // column sums of the ROUNDED values (what the next GEMM consumes)
@@ -370,6 +420,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             }
           }
         }
+        if (ew == 0 && lane == 0) B2C_GT(2, it, 3 + 2 * ch);
         if (do_colsum) {                               // warp-level: lanes sharing c_lane hold partials of the same columns
 #pragma unroll
           for (int o = LPR; o < 32; o <<= 1) {
@@ -386,26 +437,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CTA2) cluster_sync_all();                // the peer may still be reading operands / signalling barriers
+  if constexpr (CDIV > 1) cluster_sync_all();            // peers may still be multicasting into this CTA / signalling its barriers
   if (warp == 1) {
     tc_fence_after();
     if constexpr (CTA2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA, int CL = 1>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTA2>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CTA2, EXTRA>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CTA2, EXTRA, CL>;
   static bool configured = false;
   if (!configured) {
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
   p.n_tiles = static_cast<int>((p.N + BN - 1) / BN);
-  p.m_tiles = static_cast<int>((p.M + (CTA2 ? 2 * BM : BM) - 1) / (CTA2 ? 2 * BM : BM));      // M units: blocks or pairs
+  constexpr int CDIV = CTA2 ? 2 : CL;
+  p.m_tiles = static_cast<int>((p.M + CDIV * BM - 1) / (CDIV * BM));      // M units: blocks, pairs or clusters
   p.total_tiles = p.m_tiles * p.n_tiles * p.splits;
-  if constexpr (!CTA2) {
+  if constexpr (CL > 1) {
+    static int max_clusters = -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters < 0) {                     // co-resident clusters of this shape (GPC boundaries cost a few SMs)
+      cfg.gridDim = dim3(CL * (num_sms() / CL));
+      int n = 0;
+      B2C_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      max_clusters = n > 0 ? n : num_sms() / CL;
+    }
+    const int ncl = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
+    cfg.gridDim = dim3(CL * ncl);
+    B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  } else if constexpr (!CTA2) {
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     kern<<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
   } else {
@@ -431,6 +503,14 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams&
 
 using namespace b2c;
 
+#ifdef B2C_GEMM_TIMING
+extern "C" int b2c_debug_gemm_timing(long long* host_out) {
+  B2C_CUDA(cudaDeviceSynchronize());
+  B2C_CUDA(cudaMemcpyFromSymbol(host_out, g_gemm_dbg, sizeof(long long) * 3 * 16 * 32));
+  return 0;
+}
+#endif
+
 extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M,
                              int64_t N, int64_t K, int split_k, int block_n, const b2c_epilogue* ep, void* stream) {
   B2C_REQUIRE(A && B && ep && ep->out, "b2c_gemm_bf16: null pointer");
@@ -448,6 +528,7 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   // block_n: 0 = automatic; 64/128/256 = one CTA per 128 x block_n tile; -128/-256 = CTA pair per 256 x |block_n| tile
   int bn = block_n;
   bool cta2 = false;
+  int cl = 1;
   if (bn == 0) {
     // measured on B200 at the Conformer-M shapes (tools/kernel_bench.py): deep-K weight gradients gain from CTA pairs
     // (half the operand bytes per output), wide forward GEMMs from 128x256 tiles, the rest from 128x128
@@ -460,6 +541,16 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
     bn = -bn;
     cta2 = true;
     B2C_REQUIRE(bn == 128 || bn == 256, "b2c_gemm_bf16: CTA-pair tiles need block_n -128 or -256");
+  } else if (bn >= 1000) {                       // 1000*CL + BN: multicast cluster of CL CTAs along M (CL = 2, 4)
+    cl = bn / 1000;
+    bn %= 1000;
+    B2C_REQUIRE((cl == 2 || cl == 4) && (bn == 128 || bn == 256) && !a_mn && !(b_mn && bn == 128 && cl == 4),
+                "b2c_gemm_bf16: multicast clusters need block_n = 1000*{2,4} + {128,256} and a K-major A");
+  }
+  if (block_n == 0 && !cta2 && !a_mn && bn >= 128) {
+    // automatic: share the B tile across vertically adjacent tiles when the problem is tall enough to fill the clusters
+    static const int auto_cl = [] { const char* e = getenv("B2C_GEMM_CLUSTER"); return e ? atoi(e) : B2C_DEFAULT_CLUSTER; }();
+    if ((auto_cl == 2 || auto_cl == 4) && M >= 128ll * auto_cl * 8) cl = (b_mn && bn == 128 && auto_cl == 4) ? 2 : auto_cl;
   }
   B2C_REQUIRE(bn == 64 || bn == 128 || bn == 256, "b2c_gemm_bf16: block_n must be 64, 128 or 256");
   const int total_kb = static_cast<int>((K + BK - 1) / BK);
@@ -479,7 +570,7 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   if (!a_mn) rc = get_tensor_map_2d(&ta, A, 2, K, M, lda * 2, BK, BM, true);
   else       rc = get_tensor_map_2d(&ta, A, 2, M, K, lda * 2, 64, BK, true);
   if (rc) return rc;
-  if (!b_mn) rc = get_tensor_map_2d(&tb, B, 2, K, N, ldb * 2, BK, cta2 ? bn / 2 : bn, true);
+  if (!b_mn) rc = get_tensor_map_2d(&tb, B, 2, K, N, ldb * 2, BK, cta2 ? bn / 2 : bn / cl, true);
   else       rc = get_tensor_map_2d(&tb, B, 2, N, K, ldb * 2, 64, BK, true);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -517,6 +608,32 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
     }                                                                                              \
     B2C_LAUNCH1(BN_, true, false, EPI_GENERIC, C2);                                                \
   }
+#define B2C_LAUNCH_CL(BN_, BMN, E, CL_)                                                            \
+  do {                                                                                             \
+    if (extra) return launch_gemm<BN_, false, BMN, E, false, true, CL_>(ta, tb, p, st);            \
+    return launch_gemm<BN_, false, BMN, E, false, false, CL_>(ta, tb, p, st);                      \
+  } while (0)
+#define B2C_DISPATCH_CL(BN_, CL_, DG)                                                              \
+  if (bn == BN_ && cl == CL_ && !cta2 && !a_mn) {                                                  \
+    if (!b_mn) {                                                                                   \
+      if (epi == EPI_BF16) B2C_LAUNCH_CL(BN_, false, EPI_BF16, CL_);                               \
+      if (epi == EPI_SILU) B2C_LAUNCH_CL(BN_, false, EPI_SILU, CL_);                               \
+      if (epi == EPI_RESID) B2C_LAUNCH_CL(BN_, false, EPI_RESID, CL_);                             \
+      return launch_gemm<BN_, false, false, EPI_GENERIC, false, true, CL_>(ta, tb, p, st);         \
+    }                                                                                              \
+    if constexpr (DG) {                                                                            \
+      if (epi == EPI_BF16) B2C_LAUNCH_CL(BN_, true, EPI_BF16, CL_);                                \
+      if (epi == EPI_SILU_BWD) B2C_LAUNCH_CL(BN_, true, EPI_SILU_BWD, CL_);                        \
+      return launch_gemm<BN_, false, true, EPI_GENERIC, false, true, CL_>(ta, tb, p, st);          \
+    }                                                                                              \
+  }
+  B2C_DISPATCH_CL(128, 2, true)
+  B2C_DISPATCH_CL(128, 4, false)
+  B2C_DISPATCH_CL(256, 2, true)
+  B2C_DISPATCH_CL(256, 4, true)
+#undef B2C_DISPATCH_CL
+#undef B2C_LAUNCH_CL
+  B2C_REQUIRE(cl == 1, "b2c_gemm_bf16: no multicast-cluster kernel for this operand layout / tile");
   B2C_DISPATCH(64, false)
   B2C_DISPATCH(128, false)
   B2C_DISPATCH(256, false)

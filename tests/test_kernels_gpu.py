@@ -364,6 +364,42 @@ def test_gemm_cta_pair_forward(ops, M, N, K, bn):
     _close(x, want, rel=5e-3, name="pair resid")
 
 
+# ----------------------------------------------------------------------------------------------- GEMM, multicast clusters
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, 2256), (1000, 1024, 256, 2256), (777, 768, 320, 4256),
+                                      (23872, 256, 1024, 4256), (300, 144, 144, 2128), (2049, 384, 576, 4128),
+                                      (23872, 1024, 256, 4256), (130, 256, 256, 4256)])
+def test_gemm_multicast_cluster_forward(ops, M, N, K, bn):
+    """block_n = 1000*CL + BN: CL CTAs on vertically adjacent tiles share one TMA-multicast B tile; ragged M leaves
+    whole CTAs of a cluster without rows (they still take part in the multicast)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().T + bias
+    _close(ops.gemm(a, w, M=M, N=N, K=K, bias=bias, block_n=bn), ref, name="cluster bias")
+    out2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    h = ops.gemm(a, w, M=M, N=N, K=K, bias=bias, act=ops.ACT_SILU, out2=out2, block_n=bn)
+    _close(out2, ref, name="cluster pre-act")
+    _close(h, torch.nn.functional.silu(ref), name="cluster silu")
+    x = torch.randn(M, N, device="cuda", generator=g)
+    want = x + 0.5 * ref
+    ops.gemm(a, w, M=M, N=N, K=K, bias=bias, resid=x, out=x, alpha=0.5, block_n=bn)
+    _close(x, want, rel=5e-3, name="cluster resid")
+
+
+@pytest.mark.parametrize("bn", [2128, 2256, 4256])
+def test_gemm_multicast_cluster_dgrad(ops, bn):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 3000, 512, 256
+    dy = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(K, N, device="cuda", generator=g) / math.sqrt(K))
+    _close(ops.gemm(dy, w, M=M, N=N, K=K, b_mn=True, block_n=bn), dy.float() @ w.float(), name="cluster dgrad")
+    u = _bf(torch.randn(M, N, device="cuda", generator=g))
+    s = torch.sigmoid(u.float())
+    out = ops.gemm(dy, w, M=M, N=N, K=K, b_mn=True, act=ops.ACT_SILU_BWD, aux=u, block_n=bn)
+    _close(out, (dy.float() @ w.float()) * (s * (1 + u.float() * (1 - s))), name="cluster silu bwd")
+
+
 @pytest.mark.parametrize("bn", [-256, -128])
 def test_gemm_cta_pair_dgrad_wgrad(ops, bn):
     g = torch.Generator(device="cuda").manual_seed(5)

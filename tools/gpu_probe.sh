@@ -14,7 +14,7 @@ fi
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 : > gpurun_out/probe_summary.txt
 for t in $TESTS; do
-  timeout 420 python -m pytest "$FILE" -m gpu -q -x -k "$t" -p no:cacheprovider > gpurun_out/probe_$t.log 2>&1
+  timeout ${PROBE_TIMEOUT:-420} python -m pytest "$FILE" -m gpu -q -x -k "$t" -p no:cacheprovider > gpurun_out/probe_$t.log 2>&1
   rc=$?
   echo "$t rc=$rc $(tail -1 gpurun_out/probe_$t.log)" >> gpurun_out/probe_summary.txt
 done

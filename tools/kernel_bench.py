@@ -13,7 +13,12 @@ dev = "cuda"
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
+SKIP = False
+
+
 def timeit(fn, reps=20):
+    if SKIP:
+        return 0.0
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -49,11 +54,15 @@ def main():
     out_d = torch.empty(M, d, device=dev, dtype=bf)
 
     def rec(name, us, flops=0, nbytes=0):
+        if us == 0.0:
+            return
         res[name] = dict(us=round(us, 2), tflops=round(flops / us / 1e6, 1) if flops else None,
                          gbs=round(nbytes / us / 1e3, 1) if nbytes else None)
         print(f"{name:44s} {us:9.2f} us  {res[name]['tflops'] or '':>8} TF/s  {res[name]['gbs'] or '':>8} GB/s", flush=True)
 
-    for bn in (128, 256, -256):
+    only = [a for a in sys.argv[1:] if not a.startswith('--') and not a.endswith('.json')]
+    bns = (128, 256, -256) if 'gemm' in only or not only else ()
+    for bn in bns:
         rec(f"gemm ffn1 M{M} N{f} K{d} silu bn{bn}", timeit(lambda: ops.gemm(a_d, w_fd, M=M, N=f, K=d, bias=bias_f, act=ops.ACT_SILU, out=out_f, block_n=bn)),
             2 * M * f * d, M * d * 2 + M * f * 2)
         rec(f"gemm ffn2 M{M} N{d} K{f} resid bn{bn}", timeit(lambda: ops.gemm(a_f, w_df, M=M, N=d, K=f, bias=bias_d, resid=x, out=x, alpha=0.5, block_n=bn)),
@@ -67,16 +76,22 @@ def main():
         rec(f"gemm dgrad M{M} N{d} K{f} bn{bn}", timeit(lambda: ops.gemm(a_f, w_fd, M=M, N=d, K=f, b_mn=True, out=out_d, block_n=bn)),
             2 * M * f * d, M * f * 2 + M * d * 2)
     dW = torch.zeros(d, f, device=dev)
-    for split, bn in ((18, 128), (18, -256), (37, -256)):
+    SKIP_G = bool(only) and "gemm" not in only
+    for split, bn in (() if SKIP_G else ((18, 128), (18, -256), (37, -256))):
         rec(f"gemm wgrad M{d} N{f} K{M} split{split} bn{bn}", timeit(lambda: ops.gemm(a_d, a_f, M=d, N=f, K=M, a_mn=True, b_mn=True, out=dW, accumulate=True, split_k=split, block_n=bn)),
             2 * M * f * d, M * d * 2 + M * f * 2)
+    def sec(name):
+        global SKIP
+        SKIP = bool(only) and name not in only
     g, be = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+    sec("ln")
     rec("layernorm fwd bf16", timeit(lambda: ops.layernorm_fwd(x, g, be, out=out_d)), 0, M * d * 6)
     y, mean, rstd = ops.layernorm_fwd(x, g, be, save_stats=True)
     dx, dg, db = torch.zeros_like(x), torch.zeros(d, device=dev), torch.zeros(d, device=dev)
     rec("layernorm bwd (dy bf16, accumulate)", timeit(lambda: ops.layernorm_bwd(out_d, x, g, mean, rstd, dx, True, dg, db)), 0, M * d * (4 + 2 + 8))
     qkv = torch.randn(M, 3 * H * 64, device=dev).to(bf)
     lens = torch.full((B,), T, device=dev, dtype=torch.int32)
+    sec("attn")
     rec("attention fwd", timeit(lambda: ops.attention_fwd(qkv, lens, B, T, H, 0.125)), 4 * B * H * T * T * 64, M * 4 * H * 64 * 2)
     rec("attention fwd (train: lse + dropout 0.5)", timeit(lambda: ops.attention_fwd(qkv, lens, B, T, H, 0.125, save_lse=True, drop_p=0.5, drop_seed=1)), 4 * B * H * T * T * 64, 0)
     att, lse = ops.attention_fwd(qkv, lens, B, T, H, 0.125, save_lse=True, drop_p=0.5, drop_seed=1)
@@ -85,6 +100,7 @@ def main():
     u = torch.randn(M, 2 * d, device=dev).to(bf)
     wdw, bdw = torch.randn(d, k, device=dev) / 5, torch.zeros(d, device=dev)
     one, zero = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+    sec("convmod")
     rec("convmod eval (GLU+dw+BN+SiLU)", timeit(lambda: ops.convmod_eval(u, wdw, bdw, one, zero, zero, one, B, T)), 0, 3 * M * d * 2)
     rec("convmod dw fwd (train pass 1)", timeit(lambda: ops.convmod_dw_fwd(u, wdw, bdw, B, T)), 0, 3 * M * d * 2)
     yy, stats = ops.convmod_dw_fwd(u, wdw, bdw, B, T)
@@ -94,12 +110,14 @@ def main():
     rec("convmod bn bwd reduce", timeit(lambda: ops.convmod_bn_bwd_reduce(out_d, yy, mean_c, rstd_c, one, zero)), 0, 2 * M * d * 2)
     dwdw, dbdw = torch.zeros(d, k, device=dev), torch.zeros(d, device=dev)
     rec("convmod dw bwd", timeit(lambda: ops.convmod_dw_bwd(out_d, yy, u, mean_c, rstd_c, one, zero, sums, True, wdw, dwdw, dbdw, dg, db, B, T)), 0, M * d * 2 * 6)
+    sec("misc")
     rec("colsum bf16 [M,1024]", timeit(lambda: ops.colsum(a_f, torch.zeros(f, device=dev))), 0, M * f * 2)
     rec("scale_cast [M,256] dropout", timeit(lambda: ops.scale_cast(x, 0.5, 0.5, 3)), 0, M * d * 6)
     xin = torch.rand(B, 80, 1500, device=dev)
     W1, b1 = torch.randn(512, 1, 7, 7, device=dev) / 7, torch.zeros(512, device=dev)
     W2, b2 = torch.randn(128, 512, 3, 3, device=dev) / 68, torch.zeros(128, device=dev)
     Wc, bc = ops.convsub_compose(W1, b1, W2, b2, 2, 128)
+    sec("convsub")
     rec("convsub compose", timeit(lambda: ops.convsub_compose(W1, b1, W2, b2, 2, 128), 5))
     rec("convsub fwd (64x80x1500 -> bf16 tokens)", timeit(lambda: ops.convsub_fwd(xin, Wc, bc, 11, 4), 5), 2 * 121 * 128 * 18 * 373 * B, B * 80 * 1500 * 4 + M * 18 * 128 * 2)
     tok = ops.convsub_fwd(xin, Wc, bc, 11, 4)
@@ -113,6 +131,7 @@ def main():
     for p_ in params:
         p_.grad = torch.randn_like(p_) * 0.01
     opt = Adafactor(params, lr=2e-5, beta1=0.9)
+    sec("optim")
     rec(f"fused Adafactor step ({nparam/1e6:.1f} M params)", timeit(lambda: opt.step(), 5), 0, nparam * 28)
     if "--json" in sys.argv:
         json.dump(res, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
