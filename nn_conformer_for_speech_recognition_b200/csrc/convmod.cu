@@ -23,48 +23,79 @@ constexpr int CM_MAXK = 33;    // taps (repo default k=33, Conformer S/M/L k=31)
 constexpr int CM_G = 8;        // outputs per register window (backward)
 constexpr int CM_GF = 16;      // outputs per register window (forward: one window per warp)
 
-// stage GLU(u) for frames [t_lo, t_lo + nrow) of utterance b into smem (zero outside [0,T)) as fp32 [row][64].
-// A half-warp takes one row (lane = 4 adjacent channels: one 8-byte load from each GLU half, one conflict-free
-// 16-byte smem store), so a warp instruction covers two rows and the CTA 16; loads are issued UN row-pairs deep before
-// the first is consumed (memory-level parallelism: the un-batched version exposed one DRAM round trip per row).
-__device__ __forceinline__ void stage_glu(const __nv_bfloat16* __restrict__ u, float2* __restrict__ sG, int b, int T,
-                                          int d, int c0, int t_lo, int nrow) {
+constexpr int CM_UN = 10;      // row pairs per thread: 16 rows per CTA step x 10 = 160 >= 128 + (CM_MAXK - 1) - 1 rows
+static_assert(16 * CM_UN >= CM_TT + CM_MAXK - 1, "one batch must cover the tile and its halo");
+// Loads are UNCONDITIONAL from a clamped (always valid) address and the zero padding is applied when the value is
+// consumed: a predicated load into a pre-zeroed register made the compiler put a MOV behind every LDG, and a MOV that
+// reads a load's destination blocks in-order issue until the data is back -- the whole batch then ran one memory
+// latency after the other (ncu: long-scoreboard stalls on MOV, 47 % of the samples).
+__device__ __forceinline__ uint32_t glu_load(const __nv_bfloat16* __restrict__ u, uint2 (&av)[CM_UN], uint2 (&gv)[CM_UN],
+                                             int b, int T, int d, int c0, int t_lo, int nrow) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hl = lane & 15, rsel = lane >> 4;
   const int ch = c0 + hl * 4;
   const bool ch_ok = ch < d;                       // d % 8 == 0 and c0 % 64 == 0: a 4-channel group is all in or all out
-  constexpr int UN = 5;
+  const __nv_bfloat16* base = u + static_cast<int64_t>(b) * T * (2 * d) + (ch_ok ? ch : c0);
+  uint32_t okmask = 0;
+#pragma unroll
+  for (int q = 0; q < CM_UN; ++q) {
+    const int r = warp * 2 + rsel + q * 16, t = t_lo + r;
+    if (r < nrow && t >= 0 && t < T && ch_ok) okmask |= 1u << q;
+    const __nv_bfloat16* row = base + static_cast<int64_t>(min(max(t, 0), T - 1)) * (2 * d);
+    av[q] = *reinterpret_cast<const uint2*>(row);
+    gv[q] = *reinterpret_cast<const uint2*>(row + d);
+  }
+  return okmask;
+}
+__device__ __forceinline__ void glu_store(const uint2 (&av)[CM_UN], const uint2 (&gv)[CM_UN], uint32_t okmask,
+                                          float2* __restrict__ sG, int nrow) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hl = lane & 15, rsel = lane >> 4;
   float4* sG4 = reinterpret_cast<float4*>(sG);
-  for (int r0 = warp * 2 + rsel; r0 < nrow; r0 += 16 * UN) {
-    uint2 av[UN], gv[UN];
 #pragma unroll
-    for (int q = 0; q < UN; ++q) {
-      const int r = r0 + q * 16, t = t_lo + r;
-      av[q] = gv[q] = make_uint2(0u, 0u);
-      if (r < nrow && t >= 0 && t < T && ch_ok) {
-        const __nv_bfloat16* row = u + (static_cast<int64_t>(b) * T + t) * (2 * d);
-        av[q] = *reinterpret_cast<const uint2*>(row + ch);
-        gv[q] = *reinterpret_cast<const uint2*>(row + d + ch);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < UN; ++q) {
-      const int r = r0 + q * 16;
-      if (r < nrow) {
-        const float2 a0 = unpack_bf16(av[q].x), a1 = unpack_bf16(av[q].y);
-        const float2 g0 = unpack_bf16(gv[q].x), g1 = unpack_bf16(gv[q].y);
-        sG4[r * 16 + hl] = make_float4(a0.x * sigmoid_f(g0.x), a0.y * sigmoid_f(g0.y), a1.x * sigmoid_f(g1.x),
-                                       a1.y * sigmoid_f(g1.y));                          // zero rows: 0 * 0.5 = 0
-      }
+  for (int q = 0; q < CM_UN; ++q) {
+    const int r = warp * 2 + rsel + q * 16;
+    if (r < nrow) {
+      const float2 a0 = unpack_bf16(av[q].x), a1 = unpack_bf16(av[q].y);
+      const float2 g0 = unpack_bf16(gv[q].x), g1 = unpack_bf16(gv[q].y);
+      const float keep = (okmask >> q) & 1u ? 1.f : 0.f;                                 // zero padding / channel tail
+      sG4[r * 16 + hl] = make_float4(keep * a0.x * sigmoid_f(g0.x), keep * a0.y * sigmoid_f(g0.y),
+                                     keep * a1.x * sigmoid_f(g1.x), keep * a1.y * sigmoid_f(g1.y));
     }
   }
 }
+// stage GLU(u) for frames [t_lo, t_lo + nrow) of utterance b into smem (zero outside [0,T)) as fp32 [row][64].
+// A half-warp takes one row (lane = 4 adjacent channels: one 8-byte load from each GLU half, one conflict-free
+// 16-byte smem store), so a warp instruction covers two rows and the CTA 16; ALL loads of the tile are issued before
+// the first is consumed (one memory round trip per CTA; the row-at-a-time version exposed one per row).
+__device__ __forceinline__ void stage_glu(const __nv_bfloat16* __restrict__ u, float2* __restrict__ sG, int b, int T,
+                                          int d, int c0, int t_lo, int nrow) {
+  uint2 av[CM_UN], gv[CM_UN];
+  const uint32_t okmask = glu_load(u, av, gv, b, T, d, c0, t_lo, nrow);
+  glu_store(av, gv, okmask, sG, nrow);
+}
 
 // depthwise taps of this CTA's 64 channels -> smem, tap-major [k][64] (coalesced global read, conflict-free float2 reads)
-__device__ __forceinline__ void stage_taps(const float* __restrict__ wdw, float* __restrict__ sWt, int c0, int d, int k) {
+constexpr int CM_TAPLD = (CM_CH * CM_MAXK + 255) / 256;    // tap elements per thread (256 threads)
+__device__ __forceinline__ void load_taps(const float* __restrict__ wdw, float (&tv)[CM_TAPLD], int c0, int d, int k) {
   const int nch = min(CM_CH, d - c0);
-  for (int e = threadIdx.x; e < nch * k; e += blockDim.x) sWt[(e % k) * CM_CH + e / k] = __ldg(wdw + static_cast<int64_t>(c0) * k + e);
-  for (int e = nch * k + threadIdx.x; e < CM_CH * k; e += blockDim.x) sWt[(e % k) * CM_CH + e / k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < CM_TAPLD; ++i) {
+    const int e = threadIdx.x + i * 256;
+    tv[i] = e < nch * k ? __ldg(wdw + static_cast<int64_t>(c0) * k + e) : 0.f;
+  }
+}
+__device__ __forceinline__ void store_taps(const float (&tv)[CM_TAPLD], float* __restrict__ sWt, int k) {
+#pragma unroll
+  for (int i = 0; i < CM_TAPLD; ++i) {
+    const int e = threadIdx.x + i * 256;
+    if (e < CM_CH * k) sWt[(e % k) * CM_CH + e / k] = tv[i];
+  }
+}
+__device__ __forceinline__ void stage_taps(const float* __restrict__ wdw, float* __restrict__ sWt, int c0, int d, int k) {
+  float tv[CM_TAPLD];
+  load_taps(wdw, tv, c0, d, k);
+  store_taps(tv, sWt, k);
 }
 
 // MODE 0: eval  -> out = SiLU(BN_running(y))            (bn_scale/bn_shift folded per channel)
@@ -89,8 +120,12 @@ __global__ void __launch_bounds__(256, 2) convmod_fwd_kernel(const __nv_bfloat16
   const bool ch_ok = ch < d;
   float* sWt = reinterpret_cast<float*>(sG + (CM_TT + k - 1) * 32);
 
-  stage_taps(wdw, sWt, c0, d, k);
-  stage_glu(u, sG, b, T, d, c0, t0 - half, CM_TT + k - 1);
+  {
+    float tv[CM_TAPLD];
+    load_taps(wdw, tv, c0, d, k);                  // in flight together with the GLU loads below: one memory round trip
+    stage_glu(u, sG, b, T, d, c0, t0 - half, CM_TT + k - 1);
+    store_taps(tv, sWt, k);
+  }
   __syncthreads();
 
   float2 w[NTAP];                                  // taps of this lane's channel pair (FFMA2 operands)
@@ -187,10 +222,13 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
   if (tr >= rpi) return;
   float sc[8], sh[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = tg * 8 + j;
-    sc[j] = __ldg(rstd + c) * __ldg(bn_w + c);
-    sh[j] = __ldg(bn_b + c) - __ldg(mean + c) * sc[j];
+  for (int j4 = 0; j4 < 2; ++j4) {
+    const int c = tg * 8 + j4 * 4;
+    const float4 q = __ldg(reinterpret_cast<const float4*>(rstd + c)), gw = __ldg(reinterpret_cast<const float4*>(bn_w + c));
+    const float4 gb = __ldg(reinterpret_cast<const float4*>(bn_b + c)), mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+    sc[j4 * 4 + 0] = q.x * gw.x; sc[j4 * 4 + 1] = q.y * gw.y; sc[j4 * 4 + 2] = q.z * gw.z; sc[j4 * 4 + 3] = q.w * gw.w;
+    sh[j4 * 4 + 0] = gb.x - mu.x * sc[j4 * 4 + 0]; sh[j4 * 4 + 1] = gb.y - mu.y * sc[j4 * 4 + 1];
+    sh[j4 * 4 + 2] = gb.z - mu.z * sc[j4 * 4 + 2]; sh[j4 * 4 + 3] = gb.w - mu.w * sc[j4 * 4 + 3];
   }
   const int64_t r_end = min(rows, (static_cast<int64_t>(blockIdx.x) + 1) * rows_per_block);
   constexpr int UN = 4;
@@ -288,7 +326,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
 
 // pass 2: dy on the fly -> du (through depthwise conv + GLU), dwdw, dbdw (fp32 atomics), dbn_w/dbn_b (from sums)
 template <bool BN_TRAIN>
-__global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* __restrict__ dc,
+__global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16* __restrict__ dc,
                                                           const __nv_bfloat16* __restrict__ y,
                                                           const __nv_bfloat16* __restrict__ u,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -309,10 +347,13 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
   const int half = (k - 1) / 2;
   const int ch = c0 + lane * 2;
   const bool ch_ok = ch < d;
-  for (int i = threadIdx.x; i < CM_CH * (CM_MAXK + 1); i += blockDim.x) sW[i] = 0.f;
 
-  stage_taps(wdw, sWt, c0, d, k);
-  stage_glu(u, sG, b, T, d, c0, t0 - half, nrow);
+  float tv[CM_TAPLD];
+  uint2 av[CM_UN], gv[CM_UN];
+  load_taps(wdw, tv, c0, d, k);                      // taps + GLU operands: one batch of global loads; dc / y: a second
+  const uint32_t glu_ok = glu_load(u, av, gv, b, T, d, c0, t0 - half, nrow);
+  glu_store(av, gv, glu_ok, sG, nrow);
+  store_taps(tv, sWt, k);
   {
     if (ch_ok && blockIdx.x == 0 && blockIdx.z == 0 && warp == 0) {     // parameter grads of BN = the two sums
       atomicAdd(dbn_b + ch, static_cast<float>(sums[ch])); atomicAdd(dbn_b + ch + 1, static_cast<float>(sums[ch + 1]));
@@ -336,20 +377,19 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
       }
     }
     float4* sDY4 = reinterpret_cast<float4*>(sDY);
-    constexpr int UN = 5;
-    for (int r0 = warp * 2 + rsel; r0 < nrow; r0 += 16 * UN) {
+    constexpr int UN = CM_UN;
+    {
+      const int r0 = warp * 2 + rsel;
       uint2 dcr[UN], yr[UN];
       bool ok[UN];
+      const int chc = ch4_ok ? ch4 : c0;             // unconditional loads from a clamped address (see glu_load)
 #pragma unroll
       for (int q = 0; q < UN; ++q) {
         const int r = r0 + q * 16, t = t0 - half + r;
         ok[q] = r < nrow && t >= 0 && t < T && ch4_ok;
-        dcr[q] = yr[q] = make_uint2(0u, 0u);
-        if (ok[q]) {
-          const int64_t row = static_cast<int64_t>(b) * T + t;
-          dcr[q] = *reinterpret_cast<const uint2*>(dc + row * d + ch4);
-          yr[q] = *reinterpret_cast<const uint2*>(y + row * d + ch4);
-        }
+        const int64_t row = static_cast<int64_t>(b) * T + min(max(t, 0), T - 1);
+        dcr[q] = *reinterpret_cast<const uint2*>(dc + row * d + chc);
+        yr[q] = *reinterpret_cast<const uint2*>(y + row * d + chc);
       }
 #pragma unroll
       for (int q = 0; q < UN; ++q) {
@@ -438,22 +478,24 @@ __global__ void __launch_bounds__(256) convmod_bwd_kernel(const __nv_bfloat16* _
       }
     }
   }
-  // CTA-level reduction of dw / dbdw over the 8 warps (shared-memory atomics), then one global atomic each
-#pragma unroll
-  for (int j = 0; j < CM_MAXK; ++j) {
-    if (j < k) {
-      atomicAdd(&sW[(lane * 2) * (CM_MAXK + 1) + j], acc[j].x);
-      atomicAdd(&sW[(lane * 2 + 1) * (CM_MAXK + 1) + j], acc[j].y);
-    }
-  }
-  atomicAdd(&sW[(lane * 2) * (CM_MAXK + 1) + CM_MAXK], dbs0);
-  atomicAdd(&sW[(lane * 2 + 1) * (CM_MAXK + 1) + CM_MAXK], dbs1);
+  // CTA-level reduction of dw / dbdw over the 8 warps: the staged tiles are dead now, so every warp parks its partials
+  // in their place ([warp][tap][64 ch], conflict-free float2 stores -- the first version used 66 shared-memory
+  // atomics per thread here), 256 threads add the 8 copies, then one global atomic per (channel, tap)
   __syncthreads();
-  for (int i = threadIdx.x; i < CM_CH * (CM_MAXK + 1); i += blockDim.x) {
-    const int c = i / (CM_MAXK + 1), j = i % (CM_MAXK + 1);
-    if (c0 + c >= d) continue;
-    if (j == CM_MAXK) atomicAdd(dbdw + c0 + c, sW[i]);
-    else if (j < k) atomicAdd(dwdw + static_cast<int64_t>(c0 + c) * k + j, sW[i]);
+  float2* red2 = sbuf;                               // [8][CM_MAXK + 1][32] float2  (69.6 KB <= the two staged tiles)
+#pragma unroll
+  for (int j = 0; j < CM_MAXK; ++j) red2[(warp * (CM_MAXK + 1) + j) * 32 + lane] = acc[j];
+  red2[(warp * (CM_MAXK + 1) + CM_MAXK) * 32 + lane] = make_float2(dbs0, dbs1);
+  __syncthreads();
+  const float* red = reinterpret_cast<const float*>(sbuf);
+  for (int e = threadIdx.x; e < (CM_MAXK + 1) * CM_CH; e += blockDim.x) {
+    const int j = e / CM_CH, c = e % CM_CH;
+    if (c0 + c >= d || (j >= k && j != CM_MAXK)) continue;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[(w * (CM_MAXK + 1) + j) * CM_CH + c];
+    if (j == CM_MAXK) atomicAdd(dbdw + c0 + c, sum);
+    else atomicAdd(dwdw + static_cast<int64_t>(c0 + c) * k + j, sum);
   }
 }
 

@@ -303,7 +303,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(ep.aux) + row0 * ep.ld_aux + col;
         // every global READ of this chunk (residual / saved pre-activation) is issued into registers BEFORE waiting
         // for the accumulator, so its DRAM/L2 latency overlaps this tile's main loop (NIT <= 8: at most 32 registers)
+        // (separate register arrays per stream and loads straight into them: routing the 8-byte aux load through a
+        // uint4 slot made the compiler emit a MOV behind every LDG, which blocks in-order issue until that load returns
+        // -- the eight "prefetches" ran one memory latency after the other, 3 k cycles per tile)
         uint4 pre[NIT];
+        uint2 prea[NIT];
         if (col_ok && want_resid) {
 #pragma unroll
           for (int i = 0; i < NIT; ++i)
@@ -311,10 +315,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         } else if (col_ok && want_aux) {
 #pragma unroll
           for (int i = 0; i < NIT; ++i)
-            if (i * RPI < rows_left) {
-              const uint2 a = *reinterpret_cast<const uint2*>(ap + static_cast<int64_t>(i) * RPI * ep.ld_aux);
-              pre[i].x = a.x; pre[i].y = a.y;
-            }
+            if (i * RPI < rows_left) prea[i] = *reinterpret_cast<const uint2*>(ap + static_cast<int64_t>(i) * RPI * ep.ld_aux);
         }
         if (ch == 0) {
           if (ew == 0 && lane == 0) B2C_GT(2, it, 0);
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
               for (int j = 0; j < 4; ++j) f[j] *= sigmoid_fast(f[j]);
             } else if (want_aux) {                      // f = dL/dh ; aux = pre-activation u ; out = f * silu'(u)
-              const float2 a0 = unpack_bf16(pre[i].x), a1 = unpack_bf16(pre[i].y);
+              const float2 a0 = unpack_bf16(prea[i].x), a1 = unpack_bf16(prea[i].y);
               const float u[4] = {a0.x, a0.y, a1.x, a1.y};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {

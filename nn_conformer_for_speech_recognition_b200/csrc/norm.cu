@@ -98,8 +98,18 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const void
     if (row >= rows) break;
     const float mean = mean_in[row], rstd = rstd_in[row];
     const float4* xr = reinterpret_cast<const float4*>(x + row * d);
-    float4 xh[LN_MAXV], g[LN_MAXV];
+    float4 xh[LN_MAXV], g[LN_MAXV], prev[LN_MAXV];
     float s1 = 0.f, s2 = 0.f;
+    float4* dxr = reinterpret_cast<float4*>(dx + row * d);
+    // the running dx (residual-stream gradient) is fetched together with x and dy: one memory round trip per row
+    // instead of two (it used to be read only after the two reductions)
+    if (accumulate) {
+#pragma unroll
+      for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nv) prev[i] = dxr[c];
+      }
+    }
 #pragma unroll
     for (int i = 0; i < LN_MAXV; ++i) {
       const int c = lane + 32 * i;
@@ -124,7 +134,6 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const void
     }
     s1 = warp_sum(s1) / d;
     s2 = warp_sum(s2) / d;
-    float4* dxr = reinterpret_cast<float4*>(dx + row * d);
 #pragma unroll
     for (int i = 0; i < LN_MAXV; ++i) {
       const int c = lane + 32 * i;
@@ -135,8 +144,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const void
         o.z = rstd * (g[i].z - s1 - xh[i].z * s2);
         o.w = rstd * (g[i].w - s1 - xh[i].w * s2);
         if (accumulate) {
-          const float4 p = dxr[c];
-          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          o.x += prev[i].x; o.y += prev[i].y; o.z += prev[i].z; o.w += prev[i].w;
         }
         dxr[c] = o;
       }

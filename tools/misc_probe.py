@@ -16,6 +16,7 @@ for _ in range(2):
     ops.convmod_eval(u, wdw, bdw, one, zero, zero, one, B, T)
     yy, stats = ops.convmod_dw_fwd(u, wdw, bdw, B, T)
     mean_c, rstd_c = ops.convmod_bn_finalize(stats, M, None, None)
+    ops.convmod_bn_apply(yy, mean_c, rstd_c, one, zero)
     sums = ops.convmod_bn_bwd_reduce(dc, yy, mean_c, rstd_c, one, zero)
     dwdw, dbdw, dg, db = torch.zeros(d, k, device=dev), torch.zeros(d, device=dev), torch.zeros(d, device=dev), torch.zeros(d, device=dev)
     ops.convmod_dw_bwd(dc, yy, u, mean_c, rstd_c, one, zero, sums, True, wdw, dwdw, dbdw, dg, db, B, T)
