@@ -135,6 +135,18 @@ __device__ __forceinline__ void drop_scale2(const DropCfg& d, uint64_t idx_even,
   s1 = (h >> 16) >= d.thresh16 ? d.inv_keep : 0.f;
 }
 
+// streaming global loads that do not allocate in L1 (epilogue operands are read once; with ~200 KB of the SM's SRAM
+// carved out as shared memory the remaining L1 holds only ~200 lines)
+__device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint2 ldg_stream_v2(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -306,17 +306,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         // (separate register arrays per stream and loads straight into them: routing the 8-byte aux load through a
         // uint4 slot made the compiler emit a MOV behind every LDG, which blocks in-order issue until that load returns
         // -- the eight "prefetches" ran one memory latency after the other, 3 k cycles per tile)
+        if (ew == 0 && lane == 0) B2C_GT(2, it, 8 + 2 * ch);
         uint4 pre[NIT];
         uint2 prea[NIT];
         if (col_ok && want_resid) {
 #pragma unroll
           for (int i = 0; i < NIT; ++i)
-            if (i * RPI < rows_left) pre[i] = *reinterpret_cast<const uint4*>(rp + static_cast<int64_t>(i) * RPI * ep.ld_out);
+            if (i * RPI < rows_left) pre[i] = ldg_stream_v4(rp + static_cast<int64_t>(i) * RPI * ep.ld_out);
         } else if (col_ok && want_aux) {
 #pragma unroll
           for (int i = 0; i < NIT; ++i)
-            if (i * RPI < rows_left) prea[i] = *reinterpret_cast<const uint2*>(ap + static_cast<int64_t>(i) * RPI * ep.ld_aux);
+            if (i * RPI < rows_left) prea[i] = ldg_stream_v2(ap + static_cast<int64_t>(i) * RPI * ep.ld_aux);
         }
+        if (ew == 0 && lane == 0) B2C_GT(2, it, 9 + 2 * ch);
         if (ch == 0) {
           if (ew == 0 && lane == 0) B2C_GT(2, it, 0);
           mbar_wait(&tfull_bar[as], aph);
