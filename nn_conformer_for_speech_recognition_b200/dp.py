@@ -43,7 +43,8 @@ class GradSync:
         self.params = [p for m in modules for p in m.parameters() if p.requires_grad]
         self.buffers = [b for m in modules for b in m.buffers()]
         self.world = world if world is not None else dist.get_world_size()
-        self.buckets = make_buckets([p.numel() for p in self.params], int(bucket_mb * (1 << 20) / 4))
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.buckets = make_buckets([p.numel() for p in self.params], self.bucket_elems)
         self.avg = dist.get_backend() == "nccl"
 
     def broadcast_parameters(self, src: int = 0):
@@ -51,23 +52,43 @@ class GradSync:
             dist.broadcast(t.data, src)
 
     def finish(self):
-        """All-reduce (mean) every gradient; returns when the results are visible to the current stream."""
+        """All-reduce (mean) every gradient; returns when the results are visible to the current stream.
+
+        Gradients that are views of ONE buffer (the Conformer stack returns all of its ~500 parameter gradients as slices
+        of a single fp32 arena, autograd.py) are reduced IN PLACE as one flat span: no packing, no per-parameter
+        unpacking copies (those were ~500 launches = a tenth of the step at world size 2).  Everything else goes
+        through the bucketed pack / all-reduce / multi-tensor unpack path."""
         if self.world == 1:
             return
-        pending = []
-        for idx in self.buckets:
-            grads = [self.params[i].grad for i in idx if self.params[i].grad is not None]
-            if not grads:
+        op = dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM
+        by_storage = {}
+        for p in self.params:
+            g = p.grad
+            if g is None:
                 continue
+            by_storage.setdefault(g.untyped_storage().data_ptr(), []).append(g)
+        pending, loose = [], []
+        for grads in by_storage.values():
+            g0 = grads[0]
+            if len(grads) >= 8 and all(g.is_contiguous() and g.dtype == g0.dtype for g in grads):
+                lo = min(g.storage_offset() for g in grads)
+                hi = max(g.storage_offset() + g.numel() for g in grads)
+                if hi - lo <= 1.25 * sum(g.numel() for g in grads):         # dense enough: reduce the span itself
+                    flat = torch.empty(0, device=g0.device, dtype=g0.dtype).set_(g0.untyped_storage(), lo, (hi - lo,))
+                    pending.append((dist.all_reduce(flat, op=op, async_op=True), flat, None))
+                    continue
+            loose += grads
+        for idx in make_buckets([g.numel() for g in loose], self.bucket_elems):
+            grads = [loose[i] for i in idx]
             flat = torch.cat([g.reshape(-1) for g in grads])
-            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM, async_op=True)
-            pending.append((work, flat, grads))
+            pending.append((dist.all_reduce(flat, op=op, async_op=True), flat, grads))
         for work, flat, grads in pending:
             work.wait()
             if not self.avg:
                 flat.div_(self.world)
-            off = 0
-            for g in grads:
-                n = g.numel()
-                g.copy_(flat[off:off + n].view_as(g))
-                off += n
+            if grads is not None:
+                outs, off = [], 0
+                for g in grads:
+                    outs.append(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+                torch._foreach_copy_(grads, outs)

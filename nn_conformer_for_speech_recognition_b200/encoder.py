@@ -47,6 +47,49 @@ class _BridgeFn(torch.autograd.Function):
         return da, dW, db, None
 
 
+class _LinearFn(torch.autograd.Function):
+    """y[M,N] (fp32) = x[M,K] (fp32) W^T + b: bf16 operands on the tcgen05 GEMM, fp32 accumulation and output."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        K = x.shape[-1]
+        N = weight.shape[0]
+        x2 = x.detach().reshape(-1, K).to(torch.float32).contiguous()
+        M = x2.shape[0]
+        a = ops.scale_cast(x2, 1.0)
+        w_bf16 = ops.cast_bf16(weight.detach().contiguous())
+        ctx.save_for_backward(a, w_bf16)
+        ctx.shape = x.shape
+        y = ops.gemm(a, w_bf16, M=M, N=N, K=K, bias=bias, out_dtype=torch.float32)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, w_bf16 = ctx.saved_tensors
+        M, K = a.shape
+        N = w_bf16.shape[0]
+        db = torch.zeros(N, device=dy.device, dtype=torch.float32)
+        dyb = ops.scale_cast(dy.reshape(M, N).to(torch.float32).contiguous(), 1.0, colsum=db)
+        dW = torch.zeros((N, K), device=dy.device, dtype=torch.float32)
+        ops.gemm(dyb, a, M=N, N=K, K=M, a_mn=True, b_mn=True, out=dW, accumulate=True,
+                 split_k=max(1, min(32, ((M + 63) // 64) // 4)))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dyb, w_bf16, M=M, N=K, K=N, b_mn=True, out_dtype=torch.float32).view(ctx.shape)
+        return dx, dW, db
+
+
+class Linear(nn.Linear):
+    """`torch.nn.Linear` (same parameters / state_dict) whose forward and backward run on the tcgen05 GEMM kernel --
+    the building block for the pieces either side of the encoder (projection block, CTC head,
+    `asrnn.py:73-89,254`).  in_features and out_features must be multiples of 8."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.bias is None:
+            raise NotImplementedError("bias=False is not wired (every Linear on the reference path has a bias)")
+        return _LinearFn.apply(x, self.weight, self.bias)
+
+
 class ConformerEncoder(nn.Module):
     def __init__(self, hp, input_dim: int, num_heads: int, ffn_dim: int, num_layers: int,
                  depthwise_conv_kernel_size: int, dropout: float = 0.0, conv_out_nodes: int = 128,
