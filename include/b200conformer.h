@@ -77,6 +77,13 @@ int b2c_layernorm_fwd(const float* x, const float* gamma, const float* beta, voi
 int b2c_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
                       const float* rstd, float* dx, int dx_accumulate, float* dgamma, float* dbeta, int64_t rows, int d,
                       void* stream);
+/* same, and additionally  cast_out (bf16 [rows,d]) = alpha * dropout(dx_new)  with colsum (fp32 [d], optional) += column
+ * sums of cast_out: the operand and bias gradient the next sub-layer's backward starts from (fuses b2c_scale_cast, i.e.
+ * the gradient of `x + alpha*Dropout(f(x))` at conformer.py:185-209, into this pass over dx). */
+int b2c_layernorm_bwd_cast(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
+                           const float* rstd, float* dx, int dx_accumulate, float* dgamma, float* dbeta, int64_t rows,
+                           int d, void* cast_out, float alpha, float drop_p, uint64_t drop_seed, float* colsum,
+                           void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Conv-module chain  GLU -> depthwise conv1d('same', cross-correlation) -> BatchNorm1d -> SiLU

@@ -140,31 +140,33 @@ class _ConformerFn(torch.autograd.Function):
             P = lambda name: _get(layer, name)                                   # noqa: E731
 
             # ---- 5. final LayerNorm: the stream passes through it (no skip connection)
+            # every LayerNorm backward below also emits the NEXT sub-layer's starting operand: bf16(alpha * dropout(dx)) of
+            # the residual branch it is about to enter, with that branch's output-bias gradient (column sums) -- one
+            # pass over dx instead of LayerNorm-backward followed by a separate scale/cast kernel
             s5 = st["final"]
             dx_new = torch.empty_like(dx)
-            ops.layernorm_bwd(dx, s5["x"], P("final_layer_norm.weight"), s5["mean"], s5["rstd"], dx_new, False,
-                              G(li, "final_layer_norm.weight"), G(li, "final_layer_norm.bias"))
+            dyb = ops.layernorm_bwd(dx, s5["x"], P("final_layer_norm.weight"), s5["mean"], s5["rstd"], dx_new, False,
+                                    G(li, "final_layer_norm.weight"), G(li, "final_layer_norm.bias"),
+                                    cast=(0.5, drop_p, sd + 12 + 1, G(li, "ffn2.sequential.4.bias")))
             dx = dx_new
 
-            def ffn_bwd(pre, site):
+            def ffn_bwd(pre, site, dyb, next_cast):
                 s = st[pre]
-                # d(0.5*drop(.)) as bf16, with the bias gradient (column sums) fused into the same pass
-                dyb = ops.scale_cast(dx, 0.5, drop_p, sd + site + 1, colsum=G(li, pre + ".sequential.4.bias"))
                 wgrad(dyb, s["h"], d, f, G(li, pre + ".sequential.4.weight"))
                 du = ops.gemm(dyb, w[pre + ".sequential.4.weight"], M=M, N=f, K=d, b_mn=True, act=ops.ACT_SILU_BWD,
                               aux=s["u"], drop_p=drop_p, drop_seed=sd + site, colsum=G(li, pre + ".sequential.1.bias"))
                 wgrad(du, s["a"], f, d, G(li, pre + ".sequential.1.weight"))
                 da = ops.gemm(du, w[pre + ".sequential.1.weight"], M=M, N=d, K=f, b_mn=True)
-                ops.layernorm_bwd(da, s["x"], P(pre + ".sequential.0.weight"), s["mean"], s["rstd"], dx, True,
-                                  G(li, pre + ".sequential.0.weight"), G(li, pre + ".sequential.0.bias"))
+                return ops.layernorm_bwd(da, s["x"], P(pre + ".sequential.0.weight"), s["mean"], s["rstd"], dx, True,
+                                         G(li, pre + ".sequential.0.weight"), G(li, pre + ".sequential.0.bias"),
+                                         cast=next_cast)
 
-            # ---- 4. FFN2
-            ffn_bwd("ffn2", 12)
+            # ---- 4. FFN2 (leaves the conv module's starting operand behind)
+            dyb = ffn_bwd("ffn2", 12, dyb, (1.0, drop_p, sd + 8, G(li, "conv_module.sequential.5.bias")))
 
             # ---- 3. conv module
             s = st["conv"]
             bn = layer.conv_module.sequential[3]
-            dyb = ops.scale_cast(dx, 1.0, drop_p, sd + 8, colsum=G(li, "conv_module.sequential.5.bias"))
             wgrad(dyb, s["c"], d, d, G(li, "conv_module.sequential.5.weight"))
             dc = ops.gemm(dyb, w["conv_module.sequential.5.weight"], M=M, N=d, K=d, b_mn=True)
             sums = ops.convmod_bn_bwd_reduce(dc, s["y"], s["bmean"], s["brstd"], bn.weight, bn.bias)
@@ -175,12 +177,12 @@ class _ConformerFn(torch.autograd.Function):
             ops.colsum(du, G(li, "conv_module.sequential.0.bias"))
             wgrad(du, s["a"], 2 * d, d, G(li, "conv_module.sequential.0.weight"))
             da = ops.gemm(du, w["conv_module.sequential.0.weight"], M=M, N=d, K=2 * d, b_mn=True)
-            ops.layernorm_bwd(da, s["x"], P("conv_module.layer_norm.weight"), s["mean"], s["rstd"], dx, True,
-                              G(li, "conv_module.layer_norm.weight"), G(li, "conv_module.layer_norm.bias"))
+            dyb = ops.layernorm_bwd(da, s["x"], P("conv_module.layer_norm.weight"), s["mean"], s["rstd"], dx, True,
+                                    G(li, "conv_module.layer_norm.weight"), G(li, "conv_module.layer_norm.bias"),
+                                    cast=(1.0, drop_p, sd + 5, G(li, "self_attn.out_proj.bias")))
 
             # ---- 2. attention
             s = st["attn"]
-            dyb = ops.scale_cast(dx, 1.0, drop_p, sd + 5, colsum=G(li, "self_attn.out_proj.bias"))
             wgrad(dyb, s["att"], d, Hd, G(li, "self_attn.out_proj.weight"))
             datt = ops.gemm(dyb, w["self_attn.out_proj.weight"], M=M, N=Hd, K=d, b_mn=True)
             if rel:
@@ -195,11 +197,12 @@ class _ConformerFn(torch.autograd.Function):
             ops.colsum(dqkv, G(li, "self_attn.in_proj_bias"))
             wgrad(dqkv, s["a"], nq * Hd, d, G(li, "self_attn.in_proj_weight"))
             da = ops.gemm(dqkv, w["self_attn.in_proj_weight"], M=M, N=d, K=nq * Hd, b_mn=True)
-            ops.layernorm_bwd(da, s["x"], P("self_attn_layer_norm.weight"), s["mean"], s["rstd"], dx, True,
-                              G(li, "self_attn_layer_norm.weight"), G(li, "self_attn_layer_norm.bias"))
+            dyb = ops.layernorm_bwd(da, s["x"], P("self_attn_layer_norm.weight"), s["mean"], s["rstd"], dx, True,
+                                    G(li, "self_attn_layer_norm.weight"), G(li, "self_attn_layer_norm.bias"),
+                                    cast=(0.5, drop_p, sd + 0 + 1, G(li, "ffn1.sequential.4.bias")))
 
             # ---- 1. FFN1
-            ffn_bwd("ffn1", 0)
+            ffn_bwd("ffn1", 0, dyb, None)
             ctx.state[li] = None                  # free this layer's saved activations
 
         if side is not None:

@@ -73,7 +73,15 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const floa
 }
 
 // dx = rstd * (g - mean_d(g) - xhat * mean_d(g*xhat)),  g = dy*gamma ; dgamma += dy*xhat ; dbeta += dy
-template <bool DY_BF16, int LN_MAXV>
+// CAST: additionally emits  cast_out = bf16(alpha * dropout(dx_new))  and its column sums -- the operand (and bias
+// gradient) the NEXT sub-layer's backward starts from (what b2c_scale_cast would compute in a second pass over dx).
+struct LnCast {
+  __nv_bfloat16* out;
+  float* colsum;
+  float alpha;
+  DropCfg drop;
+};
+template <bool DY_BF16, int LN_MAXV, bool CAST>
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const void* __restrict__ dy,
                                                                       const float* __restrict__ x,
                                                                       const float* __restrict__ gamma,
@@ -82,15 +90,19 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const void
                                                                       float* __restrict__ dx, int accumulate,
                                                                       float* __restrict__ dgamma,
                                                                       float* __restrict__ dbeta, int64_t rows, int d,
-                                                                      int rows_per_warp) {
-  extern __shared__ float red[];           // [2][d] per-block partial dgamma / dbeta
+                                                                      int rows_per_warp, LnCast cast) {
+  extern __shared__ float red[];           // [2][d] per-block partial dgamma / dbeta (+ [d] cast column sums)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = d >> 2;
-  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) red[i] = 0.f;
+  for (int i = threadIdx.x; i < (CAST ? 3 : 2) * d; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
-  float4 dg[LN_MAXV], db[LN_MAXV];
+  float4 dg[LN_MAXV], db[LN_MAXV], cs[CAST ? LN_MAXV : 1];
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < (CAST ? LN_MAXV : 1); ++i) cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  DropCfg drop = cast.drop;
+  if (CAST && drop.thresh16) drop = drop_resolve(drop);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp) * rows_per_warp;
   for (int rr = 0; rr < rows_per_warp; ++rr) {
@@ -147,6 +159,20 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const void
           o.x += prev[i].x; o.y += prev[i].y; o.z += prev[i].z; o.w += prev[i].w;
         }
         dxr[c] = o;
+        if constexpr (CAST) {
+          float f[4] = {o.x * cast.alpha, o.y * cast.alpha, o.z * cast.alpha, o.w * cast.alpha};
+          const uint64_t idx = static_cast<uint64_t>(row) * d + 4 * c;
+          if (drop.thresh16) {
+            float s0, s1, s2, s3;
+            drop_scale2(drop, idx, s0, s1);
+            drop_scale2(drop, idx + 2, s2, s3);
+            f[0] *= s0; f[1] *= s1; f[2] *= s2; f[3] *= s3;
+          }
+          const uint2 packed = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+          *reinterpret_cast<uint2*>(cast.out + idx) = packed;
+          const float2 p0 = unpack_bf16(packed.x), p1 = unpack_bf16(packed.y);   // sums of the ROUNDED values
+          cs[i].x += p0.x; cs[i].y += p0.y; cs[i].z += p1.x; cs[i].w += p1.y;
+        }
       }
     }
   }
@@ -159,12 +185,19 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const void
       atomicAdd(&red[4 * c + 2], dg[i].z); atomicAdd(&red[4 * c + 3], dg[i].w);
       atomicAdd(&red[d + 4 * c + 0], db[i].x); atomicAdd(&red[d + 4 * c + 1], db[i].y);
       atomicAdd(&red[d + 4 * c + 2], db[i].z); atomicAdd(&red[d + 4 * c + 3], db[i].w);
+      if constexpr (CAST) {
+        atomicAdd(&red[2 * d + 4 * c + 0], cs[i].x); atomicAdd(&red[2 * d + 4 * c + 1], cs[i].y);
+        atomicAdd(&red[2 * d + 4 * c + 2], cs[i].z); atomicAdd(&red[2 * d + 4 * c + 3], cs[i].w);
+      }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     atomicAdd(dgamma + i, red[i]);
     atomicAdd(dbeta + i, red[d + i]);
+    if constexpr (CAST) {
+      if (cast.colsum) atomicAdd(cast.colsum + i, red[2 * d + i]);
+    }
   }
 }
 
@@ -303,29 +336,53 @@ extern "C" int b2c_layernorm_fwd(const float* x, const float* gamma, const float
   return 0;
 }
 
-extern "C" int b2c_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
-                                 const float* rstd, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
-                                 int64_t rows, int d, void* stream) {
+static int layernorm_bwd_launch(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
+                                const float* rstd, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
+                                int64_t rows, int d, const LnCast* cast, void* stream) {
   B2C_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "b2c_layernorm_bwd: null pointer");
   B2C_REQUIRE(d % 4 == 0 && d > 0 && d <= 128 * LN_MAX_CHUNKS, "b2c_layernorm_bwd: d=%d must be a multiple of 4, <= 1024", d);
   if (rows <= 0) return 0;
-  // ~4 blocks per SM; each warp walks a contiguous run of rows so parameter-gradient atomics stay rare
-  const int64_t target_warps = static_cast<int64_t>(num_sms()) * 8 * LN_WARPS;
+  // ONE wave of CTAs (3 co-resident per SM at 256 threads x ~80 registers): each warp walks a contiguous run of rows, so
+  // the parameter-gradient atomics stay rare and no partial last wave trails behind (995 CTAs on 444 slots used to run
+  // as 2.24 waves)
+  const int64_t target_warps = static_cast<int64_t>(num_sms()) * 3 * LN_WARPS;
   int rows_per_warp = static_cast<int>((rows + target_warps - 1) / target_warps);
   if (rows_per_warp < 1) rows_per_warp = 1;
   const int64_t warps = (rows + rows_per_warp - 1) / rows_per_warp;
   const unsigned grid = static_cast<unsigned>((warps + LN_WARPS - 1) / LN_WARPS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = 2 * d * sizeof(float);
+  const size_t smem = (cast ? 3 : 2) * d * sizeof(float);
+  LnCast c0 = {};
 #define B2C_LN_BWD(BF, NV)                                                                                      \
-  layernorm_bwd_kernel<BF, NV><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma, \
-                                                                  dbeta, rows, d, rows_per_warp)
+  do {                                                                                                          \
+    if (cast) layernorm_bwd_kernel<BF, NV, true><<<grid, LN_WARPS * 32, smem, st>>>(                           \
+        dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma, dbeta, rows, d, rows_per_warp, *cast);            \
+    else layernorm_bwd_kernel<BF, NV, false><<<grid, LN_WARPS * 32, smem, st>>>(                               \
+        dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma, dbeta, rows, d, rows_per_warp, c0);               \
+  } while (0)
   const int nv = (d / 4 + 31) / 32;
   if (dy_dtype == B2C_BF16) { if (nv <= 2) B2C_LN_BWD(true, 2); else if (nv <= 4) B2C_LN_BWD(true, 4); else B2C_LN_BWD(true, 8); }
   else                      { if (nv <= 2) B2C_LN_BWD(false, 2); else if (nv <= 4) B2C_LN_BWD(false, 4); else B2C_LN_BWD(false, 8); }
 #undef B2C_LN_BWD
   B2C_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int b2c_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
+                                 const float* rstd, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
+                                 int64_t rows, int d, void* stream) {
+  return layernorm_bwd_launch(dy, dy_dtype, x, gamma, mean, rstd, dx, dx_accumulate, dgamma, dbeta, rows, d, nullptr, stream);
+}
+
+extern "C" int b2c_layernorm_bwd_cast(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
+                                      const float* rstd, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
+                                      int64_t rows, int d, void* cast_out, float alpha, float drop_p, uint64_t drop_seed,
+                                      float* colsum, void* stream) {
+  B2C_REQUIRE(cast_out, "b2c_layernorm_bwd_cast: null cast_out");
+  LnCast c;
+  c.out = static_cast<__nv_bfloat16*>(cast_out); c.colsum = colsum; c.alpha = alpha;
+  c.drop = make_drop(drop_p, drop_seed);
+  return layernorm_bwd_launch(dy, dy_dtype, x, gamma, mean, rstd, dx, dx_accumulate, dgamma, dbeta, rows, d, &c, stream);
 }
 
 extern "C" int b2c_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {

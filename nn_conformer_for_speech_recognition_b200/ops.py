@@ -79,12 +79,21 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, o
     return (out, mean, rstd) if save_stats else out
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx, accumulate: bool, dgamma, dbeta):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, accumulate: bool, dgamma, dbeta, cast=None):
+    """cast = (alpha, drop_p, drop_seed, colsum): also return bf16(alpha * dropout(dx_new)) (what `scale_cast(dx, ...)`
+    would compute in a second pass) with its column sums accumulated into `colsum`."""
     d = x.shape[-1]
     rows = x.numel() // d
-    call("b2c_layernorm_bwd", ptr(dy), BF16 if dy.dtype == torch.bfloat16 else F32, ptr(x), ptr(gamma), ptr(mean),
-         ptr(rstd), ptr(dx), int(accumulate), ptr(dgamma), ptr(dbeta), rows, d, stream_ptr())
-    return dx
+    if cast is None:
+        call("b2c_layernorm_bwd", ptr(dy), BF16 if dy.dtype == torch.bfloat16 else F32, ptr(x), ptr(gamma), ptr(mean),
+             ptr(rstd), ptr(dx), int(accumulate), ptr(dgamma), ptr(dbeta), rows, d, stream_ptr())
+        return dx
+    alpha, drop_p, drop_seed, colsum = cast
+    out = torch.empty((rows, d), device=dx.device, dtype=torch.bfloat16)
+    call("b2c_layernorm_bwd_cast", ptr(dy), BF16 if dy.dtype == torch.bfloat16 else F32, ptr(x), ptr(gamma), ptr(mean),
+         ptr(rstd), ptr(dx), int(accumulate), ptr(dgamma), ptr(dbeta), rows, d, ptr(out), alpha, drop_p, drop_seed,
+         ptr(colsum), stream_ptr())
+    return out
 
 
 def convmod_eval(u, wdw, bdw, bn_w, bn_b, bn_mean, bn_var, B: int, T: int, eps: float = 1e-5):

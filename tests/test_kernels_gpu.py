@@ -141,6 +141,30 @@ def test_layernorm_fwd_bwd(ops, rows, d):
 
 
 # ----------------------------------------------------------------------------------------------- conv module chain
+def test_layernorm_bwd_fused_cast_equals_separate_scale_cast(ops):
+    """b2c_layernorm_bwd_cast = b2c_layernorm_bwd followed by b2c_scale_cast on the new dx, bit for bit (same dropout
+    stream, same rounded column sums up to fp32 summation order)."""
+    torch.manual_seed(4)
+    rows, d = 1000, 256
+    x = torch.randn(rows, d, device="cuda")
+    gamma, beta = torch.randn(d, device="cuda"), torch.randn(d, device="cuda")
+    _, mean, rstd = ops.layernorm_fwd(x, gamma, beta, save_stats=True)
+    dy = _bf(torch.randn(rows, d, device="cuda"))
+    dx0 = torch.randn(rows, d, device="cuda")
+    for drop_p in (0.0, 0.5):
+        dxa, dxb = dx0.clone(), dx0.clone()
+        dg, db = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+        ops.layernorm_bwd(dy, x, gamma, mean, rstd, dxa, True, dg, db)
+        cs_ref = torch.zeros(d, device="cuda")
+        ref = ops.scale_cast(dxa, 0.5, drop_p, 77, colsum=cs_ref)
+        dg2, db2, cs = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+        got = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dxb, True, dg2, db2, cast=(0.5, drop_p, 77, cs))
+        assert torch.equal(dxa, dxb)
+        assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+        _close(cs, cs_ref, rel=1e-4, abs_=1e-3, name="fused cast colsum")
+        _close(dg2, dg, rel=1e-4, abs_=1e-3, name="dgamma")
+
+
 def _convmod_ref(u, wdw, bdw, bn_w, bn_b, mean, var, B, T, d, k):
     u = u.float().view(B, T, 2 * d)
     g = u[..., :d] * torch.sigmoid(u[..., d:])
