@@ -424,42 +424,51 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
   }
 }
 
-#ifdef B2C_ATTN_TIMING
-#define B2C_TS(slot) if ((tid == 0 || tid == 300) && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 1) \
-    reinterpret_cast<long long*>(p.delta_dbg)[(tid ? 64 : 0) + i * 8 + (slot)] = clock64();
-#else
-#define B2C_TS(slot)
-#endif
-// One kernel for dQ, dK, dV.  CTA = (128-key block j, head, utterance), 512 threads (four per tile row, 32 columns
-// each: the tile math is latency bound, 4 warps per scheduler hide it), loops over the utterance's query blocks i with Q_i / dO_i double-buffered by TMA:
+// One kernel for dQ, dK, dV.  CTA = (128-key block j, head, utterance), 16 math warps + 1 issuer warp, loops over the
+// utterance's query blocks i with Q_i / dO_i double-buffered by TMA:
 //   UMMA  S = Q_i K_j^T, dP = dO_i V_j^T                  -> TMEM [0,128) and [128,256)
-//   regs  P = exp2(S*scale - lse), dS = P o (dP - delta)   -> smem (bf16, K-major SW128), dropout regenerated
+//   regs  P = exp2(S*scale - lse), dS = P o (dP - delta)   -> smem (bf16, K-major SW128, DOUBLE-buffered), dropout regenerated
 //   UMMA  dV += P^T dO_i, dK += dS^T Q_i  (accumulate over i in TMEM), dQp = dS K_j (fresh)
 //   regs  dQp -> this key block's fp32 partial slab (plain 128 B stores); attn_dq_cast_kernel sums the slabs -> bf16
 // S and dP are recomputed here from the saved log-sum-exp, so no T x T tensor ever reaches HBM.
+//
+// Warp specialisation: the 512 math threads (four per tile row, 32 columns each: the tile math is latency bound) never
+// issue an MMA.  Warp 16's elected lane owns TMA and tcgen05.mma: when the math threads have published P/dS of block i
+// (mbarrier, 512 arrivals) it issues S/dP of block i+1 FIRST and then the three products of block i, so the math warps
+// are back at work on block i+1 after ~1 k cycles while block i's 24 UMMAs (2.5 k cycles to issue from one thread +
+// 1 k to run -- previously spent with all 512 threads parked on a barrier) drain underneath; dQp of block i is read out
+// after the tile math of block i+1.  P/dS are double-buffered so block i+1's tile math does not wait for them.
 template <bool REL>
-__global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
+__global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                           const __grid_constant__ CUtensorMap tmDO,
                                                           const AttnBwdParams p, float* __restrict__ dq_f32) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  constexpr uint32_t OFF_K = 0, OFF_V = 16384, OFF_Q = 32768 /*2 bufs*/, OFF_DO = 65536 /*2 bufs*/, OFF_P = 98304,
-                     OFF_DS = 131072, OFF_BAR = 163840;
+  constexpr uint32_t OFF_K = 0, OFF_V = 16384, OFF_Q = 32768 /*2 bufs*/, OFF_DO = 65536 /*2 bufs*/, OFF_P = 98304 /*2 bufs*/,
+                     OFF_DS = 163840 /*2 bufs*/, OFF_BAR = 229376;
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* bar_q = bar_kv + 1;            // [2]
-  uint64_t* bar_s = bar_kv + 3;
-  uint64_t* bar_acc = bar_kv + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 5);
+  uint64_t* bar_q = bar_kv + 1;            // [2] Q_i / dO_i landed
+  uint64_t* bar_s = bar_kv + 3;            // S / dP of the next block are in TMEM
+  uint64_t* bar_acc = bar_kv + 4;          // dV / dK / dQp products of a block have retired
+  uint64_t* bar_tile = bar_kv + 5;         // [2] P / dS buffer published by the 512 math threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 7);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool issuer_warp = warp == 16;
 #ifdef B2C_ATTN_TIMING
-#define B2C_TK(slot) if (tid == 0 && blockIdx.x == 1 && blockIdx.y == 1 && (blockIdx.z == 1 || blockIdx.z == 40)) \
-    reinterpret_cast<long long*>(p.delta_dbg)[128 + (blockIdx.z == 40 ? 16 : 0) + (slot)] = clock64();
+  // stamps live BEHIND the real partial-dQ slabs: a timing run allocates one extra slab (tools/attn_timing.py)
+  long long* dbg = reinterpret_cast<long long*>(static_cast<float*>(p.delta_dbg) +
+                                                static_cast<size_t>((p.T + AT_BK - 1) / AT_BK) * p.B * p.T * p.H * AT_DH);
+#define B2C_TK(slot) if (tid == 0 && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 40) dbg[slot] = clock64();
+#define B2C_TM(i_, slot) if (tid == 0 && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 40) dbg[16 + (i_) * 8 + (slot)] = clock64();
+#define B2C_TI(i_, slot) if (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 40) dbg[64 + (i_) * 8 + (slot)] = clock64();
 #else
 #define B2C_TK(slot)
+#define B2C_TM(i_, slot)
+#define B2C_TI(i_, slot)
 #endif
   B2C_TK(0)
-  const int row = tid & 127, cq = tid >> 7;          // cq: which 32 tile columns / 16 head-dim columns this thread owns
+  const int row = tid & 127, cq = (tid >> 7) & 3;    // cq: which 32 tile columns / 16 head-dim columns this thread owns
   const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int len = min(p.lengths[b], p.T);
   const int key0 = j * AT_BK, row_base = b * p.T;
@@ -468,6 +477,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant_
   __nv_bfloat16* dk_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.k_col + h * AT_DH + cq * 16 : nullptr;
   __nv_bfloat16* dv_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.v_col + h * AT_DH + cq * 16 : nullptr;
   if (key0 >= len) {                       // every key of this block is masked: P = 0 -> dK = dV = 0, dQ partial = 0
+    if (issuer_warp) return;
     for (int i = 0; i < (p.T + AT_BQ - 1) / AT_BQ; ++i) {
       const int q_idx = i * AT_BQ + row;
       if (q_idx < p.T) {
@@ -488,6 +498,7 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant_
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO);
     mbar_init(bar_kv, 1); mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1); mbar_init(bar_s, 1); mbar_init(bar_acc, 1);
+    mbar_init(&bar_tile[0], 512); mbar_init(&bar_tile[1], 512);
     fence_barrier_init();
   }
   if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 512); }
@@ -499,107 +510,122 @@ __global__ void __launch_bounds__(512, 1) attn_bwd_kernel(const __grid_constant_
   const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
   const int nqb = (p.T + AT_BQ - 1) / AT_BQ;
-  auto load_q = [&](int i) {
-    const int bf = i & 1;
-    mbar_expect_tx(&bar_q[bf], 32768);
-    tma_load_2d(smem + OFF_Q + bf * 16384, &tmQKV, &bar_q[bf], p.q_col + h * AT_DH, row_base + i * AT_BQ);
-    tma_load_2d(smem + OFF_DO + bf * 16384, &tmDO, &bar_q[bf], h * AT_DH, row_base + i * AT_BQ);
-  };
-  if (tid == 0) {
-    mbar_expect_tx(bar_kv, 32768);
-    tma_load_2d(smem + OFF_K, &tmQKV, bar_kv, p.k_col + h * AT_DH, row_base + key0);
-    tma_load_2d(smem + OFF_V, &tmQKV, bar_kv, p.v_col + h * AT_DH, row_base + key0);
-    load_q(0);
-  }
-  constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, false, false);
-  constexpr uint32_t idesc_mm = umma_idesc_bf16(128, 64, true, true);
-  constexpr uint32_t idesc_km = umma_idesc_bf16(128, 64, false, true);
-  // S = Q K^T and dP = dO V^T of query block i (one elected thread); their accumulators are free as soon as the tile
-  // math of block i-1 has read them, so they are issued one block AHEAD, right behind the dV/dK/dQ products
-  auto issue_s_dp = [&](int i) {
-    const uint32_t bf = i & 1;
-    const uint32_t q_addr = base + OFF_Q + bf * 16384, do_addr = base + OFF_DO + bf * 16384;
-    mbar_wait(&bar_q[bf], (i >> 1) & 1);
-    tc_fence_after();
+
+  if (issuer_warp) {
+    // ================================ TMA + MMA issuer (one elected lane) ================================
+    if ((tid & 31) == 0) {
+      auto load_q = [&](int i) {
+        const int bf = i & 1;
+        mbar_expect_tx(&bar_q[bf], 32768);
+        tma_load_2d(smem + OFF_Q + bf * 16384, &tmQKV, &bar_q[bf], p.q_col + h * AT_DH, row_base + i * AT_BQ);
+        tma_load_2d(smem + OFF_DO + bf * 16384, &tmDO, &bar_q[bf], h * AT_DH, row_base + i * AT_BQ);
+      };
+      constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_mm = umma_idesc_bf16(128, 64, true, true);
+      constexpr uint32_t idesc_km = umma_idesc_bf16(128, 64, false, true);
+      auto issue_s_dp = [&](int i) {       // S = Q_i K^T and dP = dO_i V^T
+        const uint32_t bf = i & 1;
+        const uint32_t q_addr = base + OFF_Q + bf * 16384, do_addr = base + OFF_DO + bf * 16384;
+        mbar_wait(&bar_q[bf], (i >> 1) & 1);
+        tc_fence_after();
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_bf16(tmem_base + TM_S, umma_desc_sw128(q_addr + k * 32, 16, 1024),
-                umma_desc_sw128(base + OFF_K + k * 32, 16, 1024), idesc_kk, k > 0);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + TM_S, umma_desc_sw128(q_addr + k * 32, 16, 1024),
+                    umma_desc_sw128(base + OFF_K + k * 32, 16, 1024), idesc_kk, k > 0);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_bf16(tmem_base + TM_DP, umma_desc_sw128(do_addr + k * 32, 16, 1024),
-                umma_desc_sw128(base + OFF_V + k * 32, 16, 1024), idesc_kk, k > 0);
-    tc_commit(bar_s);
-  };
-  if (tid == 0) {
-    if (nqb > 1) load_q(1);
-    mbar_wait(bar_kv, 0);
-    B2C_TK(2)
-    issue_s_dp(0);
-  }
-  for (int i = 0; i < nqb; ++i) {
-    const uint32_t ph = i & 1, bf = i & 1;
-    B2C_TS(0)
-    const uint32_t q_addr = base + OFF_Q + bf * 16384, do_addr = base + OFF_DO + bf * 16384;
-    const int q_idx = i * AT_BQ + row;
-    const int64_t stat = static_cast<int64_t>(b * p.H + h) * p.T + min(q_idx, p.T - 1);
-    const float lse_r = q_idx < p.T ? p.lse[stat] : INFINITY, delta_r = q_idx < p.T ? p.delta[stat] : 0.f;
-    mbar_wait(bar_s, ph);
-    tc_fence_after();
-    B2C_TS(1)
-    attn_bwd_tile_math<REL>(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P, smem + OFF_DS, row, cq, key0, len,
-                            lse_r, delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad,
-                            (REL && q_idx < p.T) ? (static_cast<int64_t>(row_base + q_idx) * p.H + h) * p.Rp : -1, q_idx);
-    B2C_TS(2)
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    B2C_TS(3)
-    if (tid == 0) {
-      tc_fence_after();
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + TM_DP, umma_desc_sw128(do_addr + k * 32, 16, 1024),
+                    umma_desc_sw128(base + OFF_V + k * 32, 16, 1024), idesc_kk, k > 0);
+        tc_commit(bar_s);
+      };
+      mbar_expect_tx(bar_kv, 32768);
+      tma_load_2d(smem + OFF_K, &tmQKV, bar_kv, p.k_col + h * AT_DH, row_base + key0);
+      tma_load_2d(smem + OFF_V, &tmQKV, bar_kv, p.v_col + h * AT_DH, row_base + key0);
+      load_q(0);
+      if (nqb > 1) load_q(1);
+      mbar_wait(bar_kv, 0);
+      issue_s_dp(0);
+      for (int i = 0; i < nqb; ++i) {
+        const uint32_t bf = i & 1;
+        const uint32_t q_addr = base + OFF_Q + bf * 16384, do_addr = base + OFF_DO + bf * 16384;
+        const uint32_t p_addr = base + OFF_P + bf * 32768, ds_addr = base + OFF_DS + bf * 32768;
+        // P/dS of block i published; S/dP accumulators read out; dQp of block i-1 drained
+        B2C_TI(i, 0)
+        mbar_wait(&bar_tile[bf], (i >> 1) & 1);
+        tc_fence_after();
+        B2C_TI(i, 1)
+        if (i + 1 < nqb) issue_s_dp(i + 1);  // first: the math warps continue with block i+1 as soon as these retire
+        B2C_TI(i, 2)
 #pragma unroll
-      for (int k = 0; k < 8; ++k)          // dV += P^T dO   (reduction over the 128 queries)
-        umma_bf16(tmem_base + TM_DV, umma_desc_sw128(base + OFF_P + k * 2048, 16384, 1024),
-                  umma_desc_sw128(do_addr + k * 2048, 8192, 1024), idesc_mm, (i | k) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)          // dV += P^T dO   (reduction over the 128 queries)
+          umma_bf16(tmem_base + TM_DV, umma_desc_sw128(p_addr + k * 2048, 16384, 1024),
+                    umma_desc_sw128(do_addr + k * 2048, 8192, 1024), idesc_mm, (i | k) ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)          // dK += dS^T Q
-        umma_bf16(tmem_base + TM_DK, umma_desc_sw128(base + OFF_DS + k * 2048, 16384, 1024),
-                  umma_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_mm, (i | k) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)          // dK += dS^T Q
+          umma_bf16(tmem_base + TM_DK, umma_desc_sw128(ds_addr + k * 2048, 16384, 1024),
+                    umma_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_mm, (i | k) ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)          // dQp = dS K     (reduction over the 128 keys; K tile read MN-major)
-        umma_bf16(tmem_base + TM_DQ, umma_desc_sw128(base + OFF_DS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                  umma_desc_sw128(base + OFF_K + k * 2048, 8192, 1024), idesc_km, k > 0);
-      tc_commit(bar_acc);
-      if (i + 1 < nqb) issue_s_dp(i + 1);  // queued behind the three products: runs while the CTA drains dQ below
+        for (int k = 0; k < 8; ++k)          // dQp = dS K     (reduction over the 128 keys; K tile read MN-major)
+          umma_bf16(tmem_base + TM_DQ, umma_desc_sw128(ds_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    umma_desc_sw128(base + OFF_K + k * 2048, 8192, 1024), idesc_km, k > 0);
+        tc_commit(bar_acc);
+        B2C_TI(i, 3)
+        if (i + 2 < nqb) {                   // this block's Q/dO buffer is free once its products have retired
+          mbar_wait(bar_acc, i & 1);
+          load_q(i + 2);
+        }
+        B2C_TI(i, 4)
+      }
     }
-    B2C_TS(4)
-    mbar_wait(bar_acc, ph);                // all three products done: P/dS and this block's Q/dO buffer are free again
-    tc_fence_after();
-    if (tid == 0 && i + 2 < nqb) load_q(i + 2);
-    B2C_TS(5)
-    {
+  } else {
+    // ================================ 512 math threads ================================
+    auto drain_dq = [&](int i) {             // dQp of block i: TMEM -> this key block's partial slab (plain stores)
+      const int q_idx = i * AT_BQ + row;
+      mbar_wait(bar_acc, i & 1);
+      tc_fence_after();
       uint32_t v[16];
       __syncwarp();
       tmem_ld16(tm_lane + TM_DQ + cq * 16, v);
       tmem_wait_ld();
       if (q_idx < p.T) {
-        // plain stores into THIS key block's partial-dQ slab (summed by attn_dq_cast_kernel): fp32 atomics on 75 MB per
-        // layer were the bottleneck of the first version
+        // fp32 atomics on 75 MB per layer were the bottleneck of the first version: one slab per key block instead
         float* dst = dq_f32 + (static_cast<int64_t>(j) * p.B * p.T + row_base + q_idx) * (p.H * AT_DH) + h * AT_DH + cq * 16;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           *reinterpret_cast<float4*>(dst + g * 4) = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
                                                                 __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
       }
+    };
+    for (int i = 0; i < nqb; ++i) {
+      const uint32_t ph = i & 1, bf = i & 1;
+      const int q_idx = i * AT_BQ + row;
+      const int64_t stat = static_cast<int64_t>(b * p.H + h) * p.T + min(q_idx, p.T - 1);
+      const float lse_r = q_idx < p.T ? p.lse[stat] : INFINITY, delta_r = q_idx < p.T ? p.delta[stat] : 0.f;
+      if (i >= 2) {                          // products of block i-2 read this P/dS buffer: retired before it is rewritten
+        // (already observed: drain_dq(i-2) waited on the same barrier phase)
+      }
+      B2C_TM(i, 0)
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      B2C_TM(i, 1)
+      attn_bwd_tile_math<REL>(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P + bf * 32768, smem + OFF_DS + bf * 32768, row,
+                              cq, key0, len, lse_r, delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad,
+                              (REL && q_idx < p.T) ? (static_cast<int64_t>(row_base + q_idx) * p.H + h) * p.Rp : -1, q_idx);
+      B2C_TM(i, 2)
+      if (i > 0) drain_dq(i - 1);            // block i-1's products ran underneath this block's tile math
+      B2C_TM(i, 3)
+      fence_proxy_async();                   // P/dS (generic-proxy stores) -> visible to the UMMA async proxy
+      tc_fence_before();
+      mbar_arrive(&bar_tile[bf]);
+      B2C_TM(i, 4)
     }
-    B2C_TS(6)
-    tc_fence_before();
-    __syncthreads();
-    B2C_TS(7)
+    drain_dq(nqb - 1);
   }
+  tc_fence_before();
+  __syncthreads();
   tc_fence_after();
   B2C_TK(3)
-  {
+  if (!issuer_warp) {
     uint32_t v[16];
     __syncwarp();
     tmem_ld16(tm_lane + TM_DV + cq * 16, v);
@@ -655,7 +681,7 @@ __global__ void __launch_bounds__(256) attn_dq_cast_kernel(const float* __restri
       make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b4.x, b4.y), pack_bf16(b4.z, b4.w));
 }
 
-constexpr uint32_t ATTN_BWD_SMEM = 163840 + 64 + 1024;
+constexpr uint32_t ATTN_BWD_SMEM = 229376 + 128 + 1024;
 
 }  // namespace b2c
 
@@ -752,8 +778,8 @@ static int attention_bwd_launch(const void* qkv, int64_t ld, int64_t k_off, int6
   p.delta_dbg = dq_f32;     // timing builds scribble cycle stamps over the head of the dQ workspace
   p.bd = bd; p.dbd = static_cast<__nv_bfloat16*>(dbd); p.Rp = Rp;
   dim3 grid((T + AT_BK - 1) / AT_BK, H, B);
-  if (rel) attn_bwd_kernel<true><<<grid, 512, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
-  else attn_bwd_kernel<false><<<grid, 512, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
+  if (rel) attn_bwd_kernel<true><<<grid, 544, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
+  else attn_bwd_kernel<false><<<grid, 544, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
   const int64_t n8 = rows * H * AT_DH / 8;
   attn_dq_cast_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, st>>>(dq_f32, static_cast<__nv_bfloat16*>(dqkv),
                                                                                rows, H * AT_DH, ld, 0, (T + AT_BK - 1) / AT_BK);
