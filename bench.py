@@ -443,6 +443,8 @@ def main():
         pk = peaks()
         if not args.no_instrument:
             # instrumented (event-per-launch) step: per-kernel device time, measured live on the launching stream
+            from nn_conformer_for_speech_recognition_b200 import conformer as _cf
+            _cf._LAYER_CALLS = False               # per-launch events need per-launch calls (eval normally makes one C call per layer)
             prof = _lib.profile_begin()
             host_prepare()
             if args.mode == "train":              # eager, instrumented: one CUDA-event pair per launch
@@ -462,12 +464,27 @@ def main():
             top = sorted(agg.items(), key=lambda kv: -kv[1][1])
             line["kernel_time_share"] = {k_: round(v[1] / total, 4) for k_, v in top[:8]}
             line["kernel_time_share_note"] = "eager instrumented step (CUDA-event pair per launch); includes launch gaps"
+            # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture of one
+            # eager step of this same command (profiles/r01_traffic_train.json, tools/traffic_summary.py); null when the
+            # capture does not cover the mode
+            traffic = {}
+            tp = os.path.join(ROOT, "profiles", "r01_traffic_train.json")
+            if args.mode == "train" and args.model == "M" and os.path.exists(tp):
+                traffic = json.load(open(tp))
+
+            def traffic_of(prefix):
+                sel = [v for k_, v in traffic.items() if prefix in k_]
+                n_ = sum(v["launches"] for v in sel)
+                return sum(v["dram_bytes_per_launch"] * v["launches"] for v in sel) / n_ if n_ else None
             # roofline of the dominant kernel family: every tcgen05 GEMM launch of one step re-issued back to back
             n_g, us_g, fl_g, _ = _lib.replay(rows, "b2c_gemm_bf16")
             ach = fl_g / (n_g * us_g * 1e-6) / 1e12 if n_g else 0.0
             line["roofline"] = dict(kernel="gemm_tcgen05_kernel: all GEMM launches of one step (fwd, dgrad, wgrad), replayed back to back",
                                     bound="tensor", achieved=ach, peak=pk["sustained"], unit="TFLOP/s", frac=ach / pk["sustained"],
-                                    traffic=None, peak_source=pk["src"] + " bf16_tflops_sustained (kernels timed inside a long train)",
+                                    traffic=traffic_of("gemm_tcgen05_kernel"),
+                                    traffic_note="mean DRAM bytes per GEMM launch, ncu capture of one eager step (profiles/r01_traffic_train.json)",
+                                    peak_source=pk["src"] + " bf16_tflops_sustained (kernels timed inside a long train)",
+                                    bound_note="measured limiter is shared-memory bandwidth (operand fills + MMA operand reads + epilogue transpose), see DESIGN.md section 4",
                                     launches=n_g, avg_us=us_g, flops_per_launch=fl_g / max(n_g, 1))
             cname = "b2c_convmod_dw_fwd" if args.mode == "train" else "b2c_convmod_eval_fwd"
             n_c, us_c, _, by_c = _lib.replay(rows, cname)
@@ -475,7 +492,8 @@ def main():
                 gbs = by_c / (n_c * us_c * 1e-6) / 1e9
                 line["roofline_hbm"] = dict(kernel=cname + " (GLU+depthwise[+BN+SiLU]); also FP32-FMA bound: 31 FMA per element",
                                             bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
-                                            traffic=None, launches=n_c, avg_us=us_c, bytes_per_launch=by_c / n_c)
+                                            traffic=traffic_of("convmod_fwd_kernel"), launches=n_c, avg_us=us_c,
+                                            bytes_per_launch=by_c / n_c)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"], _ = run_reference(args, cfg, T, standalone=False)

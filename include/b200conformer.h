@@ -211,6 +211,36 @@ int b2c_adafactor_step(const void* tensors_dev, int n_tensors, const void* chunk
                        float* beta2t_dev, float lr, float beta1, float eps1, float clip, float decay_rate, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * One call per Conformer layer, eval mode (torchaudio ConformerLayer.forward, conformer.py:176-212, dropout inactive,
+ * BatchNorm on running statistics): enqueues the layer's kernels on `stream`.  For the eager inference / NST
+ * pseudo-labelling path (Runner.generate_labels, runner.py:255-281), where per-launch host overhead dominates.
+ *   x        fp32 [B*T, d] residual stream, updated IN PLACE (layer input -> layer output)
+ *   weights  GEMM weights bf16 row-major (out, in), attention heads zero-padded to 64 (in_w [3*H*64, d], in_b [3*H*64],
+ *            out_w [d, H*64]); LayerNorm / bias / depthwise / BatchNorm tensors fp32 as stored by the module
+ *   workspace >= b2c_conformer_layer_eval_workspace(...) bytes, 256-byte aligned, reusable across layers
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct b2c_ffn_weights {
+  const float* ln_w; const float* ln_b;
+  const void* w1; const float* b1;          /* Linear(d, f) */
+  const void* w2; const float* b2;          /* Linear(f, d) */
+} b2c_ffn_weights;
+typedef struct b2c_layer_weights {
+  b2c_ffn_weights ffn1;
+  const float* att_ln_w; const float* att_ln_b;
+  const void* in_w; const float* in_b; const void* out_w; const float* out_b;
+  const float* conv_ln_w; const float* conv_ln_b;
+  const void* pw1_w; const float* pw1_b;    /* Conv1d(d, 2d, 1) */
+  const float* dw_w; const float* dw_b;     /* depthwise Conv1d(d, d, k): [d, k] */
+  const float* bn_w; const float* bn_b; const float* bn_mean; const float* bn_var;
+  const void* pw2_w; const float* pw2_b;    /* Conv1d(d, d, 1) */
+  b2c_ffn_weights ffn2;
+  const float* final_ln_w; const float* final_ln_b;
+} b2c_layer_weights;
+size_t b2c_conformer_layer_eval_workspace(int B, int T, int d, int f, int H);
+int b2c_conformer_layer_eval(float* x, const b2c_layer_weights* weights, const int32_t* lengths, int B, int T, int d, int f,
+                             int H, int head_dim, int k, float bn_eps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Small memory-bound helpers
  * ------------------------------------------------------------------------------------------------------- */
 /* multi-tensor fp32 -> bf16 cast; optional zero padding of rows/cols (pads attention heads to 64):

@@ -29,6 +29,18 @@ class Epilogue(Structure):
                 ("colsum", c_void_p)]
 
 
+class FfnWeights(Structure):
+    _fields_ = [(n, c_void_p) for n in ("ln_w", "ln_b", "w1", "b1", "w2", "b2")]
+
+
+class LayerWeights(Structure):                       # struct b2c_layer_weights, include/b200conformer.h
+    _fields_ = ([("ffn1", FfnWeights)] +
+                [(n, c_void_p) for n in ("att_ln_w", "att_ln_b", "in_w", "in_b", "out_w", "out_b", "conv_ln_w", "conv_ln_b",
+                                         "pw1_w", "pw1_b", "dw_w", "dw_b", "bn_w", "bn_b", "bn_mean", "bn_var", "pw2_w",
+                                         "pw2_b")] +
+                [("ffn2", FfnWeights), ("final_ln_w", c_void_p), ("final_ln_b", c_void_p)])
+
+
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 # name -> argtypes ; every function returns int unless listed in _RESTYPES
 SIGNATURES = {
@@ -48,6 +60,7 @@ SIGNATURES = {
     "b2c_attention_fwd": [_P, _L, _L, _L, _P, _P, _L, _P, _I, _I, _I, _F, _F, c_uint64, _P],
     "b2c_attention_rel_fwd": [_P, _L, _L, _L, _L, _P, _L, _L, _P, _P, _L, _P, _I, _I, _I, _F, _F, c_uint64, _P],
     "b2c_attention_rel_bwd": [_P, _L, _L, _L, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _F, c_uint64, _P],
+    "b2c_conformer_layer_eval": [_P, POINTER(LayerWeights), _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, ctypes.c_size_t, _P],
     "b2c_convsub_compose": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "b2c_convsub_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "b2c_convsub_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -62,6 +75,7 @@ SIGNATURES = {
     "b2c_repack_heads": [_P, _P, _L, _I, _I, _I, _P],
 }
 HOST_SIGNATURES = {
+    "b2c_conformer_layer_eval_workspace": ([_I, _I, _I, _I, _I], ctypes.c_size_t),
     "b2c_last_error": ([], c_char_p),
     "b2c_mt19937_seed_host": ([POINTER(c_uint32), c_uint64], None),
     "b2c_mt19937_randint_host": ([POINTER(c_uint32), c_int64, c_int64], c_int64),
@@ -69,7 +83,7 @@ HOST_SIGNATURES = {
 
 _lib = None
 LAUNCHES = 0          # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 2, "b2c_convsub_compose_bwd": 2, "b2c_attention_bwd": 4, "b2c_attention_rel_bwd": 4, "b2c_adafactor_step": 5, "b2c_version": 0, "b2c_device_check": 0}
+_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 2, "b2c_convsub_compose_bwd": 2, "b2c_attention_bwd": 4, "b2c_attention_rel_bwd": 4, "b2c_conformer_layer_eval": 20, "b2c_adafactor_step": 5, "b2c_version": 0, "b2c_device_check": 0}
 
 
 def load() -> ctypes.CDLL:

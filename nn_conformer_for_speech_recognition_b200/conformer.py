@@ -20,6 +20,7 @@ There is no CPU or eager-PyTorch fallback: without the built library or off sm_1
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -28,6 +29,7 @@ from torch import nn
 from . import _lib, ops
 
 HEAD_PAD = 64          # the attention kernel's head dimension
+_LAYER_CALLS = os.environ.get("B2C_LAYER_CALLS", "1") != "0"      # 0: eval issues every launch from Python (debug / profiling)
 
 
 class _FeedForwardModule(nn.Module):
@@ -174,6 +176,34 @@ class _WeightCache:
         self.key = sig
         return self.bf16
 
+    def layer_structs(self):
+        """ctypes `b2c_layer_weights` per layer for the one-call-per-layer eval path (rebuilt with the bf16 copies)."""
+        weights = self.get()
+        if getattr(self, "_structs_key", None) != self.key:
+            out = []
+            for layer, w in zip(self.owner.conformer_layers, weights):
+                P = lambda name: _get(layer, name).data_ptr()                       # noqa: E731
+                B = lambda name: w[name].data_ptr()                                 # noqa: E731
+                lw = _lib.LayerWeights()
+                for pre, dst in (("ffn1", lw.ffn1), ("ffn2", lw.ffn2)):
+                    dst.ln_w, dst.ln_b = P(pre + ".sequential.0.weight"), P(pre + ".sequential.0.bias")
+                    dst.w1, dst.b1 = B(pre + ".sequential.1.weight"), P(pre + ".sequential.1.bias")
+                    dst.w2, dst.b2 = B(pre + ".sequential.4.weight"), P(pre + ".sequential.4.bias")
+                lw.att_ln_w, lw.att_ln_b = P("self_attn_layer_norm.weight"), P("self_attn_layer_norm.bias")
+                lw.in_w, lw.in_b = B("self_attn.in_proj_weight"), w["in_bias"].data_ptr()
+                lw.out_w, lw.out_b = B("self_attn.out_proj.weight"), P("self_attn.out_proj.bias")
+                lw.conv_ln_w, lw.conv_ln_b = P("conv_module.layer_norm.weight"), P("conv_module.layer_norm.bias")
+                lw.pw1_w, lw.pw1_b = B("conv_module.sequential.0.weight"), P("conv_module.sequential.0.bias")
+                lw.dw_w, lw.dw_b = P("conv_module.sequential.2.weight"), P("conv_module.sequential.2.bias")
+                bn = layer.conv_module.sequential[3]
+                lw.bn_w, lw.bn_b = bn.weight.data_ptr(), bn.bias.data_ptr()
+                lw.bn_mean, lw.bn_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+                lw.pw2_w, lw.pw2_b = B("conv_module.sequential.5.weight"), P("conv_module.sequential.5.bias")
+                lw.final_ln_w, lw.final_ln_b = P("final_layer_norm.weight"), P("final_layer_norm.bias")
+                out.append(lw)
+            self._structs, self._structs_key = out, self.key
+        return self._structs
+
     def _build_padded(self, dev):
         """head_dim < 64 (Conformer-S: 36): zero-pad every head to 64 in the in/out projections so the attention
         kernel sees head dim 64.  Weight preparation only (runs when parameters change), done with torch indexing."""
@@ -310,6 +340,18 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
     dev = x.device
     save = train_state is not None
     bf = torch.bfloat16
+    if not save and not bn_train and not force_two_pass and not model.rel_att and _LAYER_CALLS:
+        # eval: ONE C call per layer (b2c_conformer_layer_eval enqueues the same 20 launches): the per-launch Python /
+        # ctypes cost otherwise exceeds the GPU time of a layer in the eager inference / NST sweep path
+        import ctypes
+        structs = model._cache.layer_structs()
+        bn0 = model.conformer_layers[0].conv_module.sequential[3]
+        nbytes = _lib.load().b2c_conformer_layer_eval_workspace(B, T, d, f, H)
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        for lw in structs:
+            _lib.call("b2c_conformer_layer_eval", x.data_ptr(), ctypes.byref(lw), lengths_i32.data_ptr(), B, T, d, f, H,
+                      model.head_dim, k, bn0.eps, ws.data_ptr(), nbytes, _lib.stream_ptr())
+        return x
     rel = model.rel_att
     nq = 4 if rel else 3                               # rel_att: the in-projection also emits q + pos_bias_v
     pe = model.rel_table(T, dev) if rel else None

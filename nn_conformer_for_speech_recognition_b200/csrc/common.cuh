@@ -128,6 +128,18 @@ __device__ __forceinline__ void drop_scale4(const DropCfg& d, uint64_t idx4, flo
 #pragma unroll
   for (int j = 0; j < 4; ++j) s[j] = ((h >> (8 * j)) & 0xFFu) >= t8 ? inv_keep8 : 0.f;
 }
+// Same idea for the elementwise sites (GEMM epilogues, scale/cast passes): ONE hash per 4 consecutive elements
+// (idx4 a multiple of 4), 8 bits per decision -- the epilogues are issue bound and the per-pair hash was ~5 integer
+// instructions per element.  Forward and backward of a site call this same function, so masks always agree.
+__device__ __forceinline__ void drop_scale4g(const DropCfg& d, uint64_t idx4, float& s0, float& s1, float& s2, float& s3) {
+  const uint32_t h = drop_hash32(d.seed, idx4 >> 2);
+  const uint32_t t8 = d.thresh16 >> 8;
+  const float k = 256.f / (256.f - static_cast<float>(t8));
+  s0 = (h & 0xFFu) >= t8 ? k : 0.f;
+  s1 = ((h >> 8) & 0xFFu) >= t8 ? k : 0.f;
+  s2 = ((h >> 16) & 0xFFu) >= t8 ? k : 0.f;
+  s3 = (h >> 24) >= t8 ? k : 0.f;
+}
 // scales for elements idx (even) and idx+1
 __device__ __forceinline__ void drop_scale2(const DropCfg& d, uint64_t idx_even, float& s0, float& s1) {
   const uint32_t h = drop_hash32(d.seed, idx_even >> 1);

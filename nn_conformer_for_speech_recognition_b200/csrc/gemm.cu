@@ -388,8 +388,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             }
             if (do_drop) {
               float s0, s1, s2, s3;
-              drop_scale2(drop, di, s0, s1);
-              drop_scale2(drop, di + 2, s2, s3);
+              drop_scale4g(drop, di, s0, s1, s2, s3);
               f[0] *= s0; f[1] *= s1; f[2] *= s2; f[3] *= s3;
               di += di_step;
             }
