@@ -91,6 +91,7 @@ struct DropCfg {
                              // replay the same launches with fresh masks; forward and backward of a step see one value
   uint32_t thresh16;         // 0 = dropout off
   float inv_keep;
+  float inv_keep8;           // 256 / (256 - (thresh16 >> 8)): scale of the 8-bit-per-decision variants
 };
 const uint64_t* dropout_epoch_ptr();       // host.cpp: lazily allocated per-process device word
 __host__ __device__ __forceinline__ uint64_t drop_mix_seed(uint64_t z) {
@@ -106,6 +107,7 @@ inline DropCfg make_drop(float p, uint64_t seed) {
   d.thresh16 = p > 0.f ? static_cast<uint32_t>(p * 65536.0 + 0.5) : 0u;
   if (d.thresh16 > 65535u) d.thresh16 = 65535u;
   d.inv_keep = p > 0.f ? 65536.f / static_cast<float>(65536u - d.thresh16) : 1.f;
+  d.inv_keep8 = 256.f / (256.f - static_cast<float>(d.thresh16 >> 8));
   return d;
 }
 // fold the step epoch into the key (call once per thread, before the first drop_scale2)
@@ -134,7 +136,7 @@ __device__ __forceinline__ void drop_scale4(const DropCfg& d, uint64_t idx4, flo
 __device__ __forceinline__ void drop_scale4g(const DropCfg& d, uint64_t idx4, float& s0, float& s1, float& s2, float& s3) {
   const uint32_t h = drop_hash32(d.seed, idx4 >> 2);
   const uint32_t t8 = d.thresh16 >> 8;
-  const float k = 256.f / (256.f - static_cast<float>(t8));
+  const float k = d.inv_keep8;
   s0 = (h & 0xFFu) >= t8 ? k : 0.f;
   s1 = ((h >> 8) & 0xFFu) >= t8 ? k : 0.f;
   s2 = ((h >> 16) & 0xFFu) >= t8 ? k : 0.f;

@@ -102,7 +102,7 @@ __device__ __forceinline__ void stage_taps(const float* __restrict__ wdw, float*
 // MODE 1: train -> y (bf16) + per-channel sum / sumsq   (stats fp64 [2][d], atomics once per CTA per channel)
 // KT = compile-time tap count (31, 33) or 0 = run-time k: with KT known the window loop has no branches and no dead taps
 template <int MODE, int KT>
-__global__ void __launch_bounds__(256, 2) convmod_fwd_kernel(const __nv_bfloat16* __restrict__ u,
+__global__ void __launch_bounds__(256, 3) convmod_fwd_kernel(const __nv_bfloat16* __restrict__ u,
                                                           const float* __restrict__ wdw, const float* __restrict__ bdw,
                                                           const float* __restrict__ bn_w, const float* __restrict__ bn_b,
                                                           const float* __restrict__ bn_mean,
@@ -128,10 +128,9 @@ __global__ void __launch_bounds__(256, 2) convmod_fwd_kernel(const __nv_bfloat16
   }
   __syncthreads();
 
-  float2 w[NTAP];                                  // taps of this lane's channel pair (FFMA2 operands)
-#pragma unroll
-  for (int j = 0; j < NTAP; ++j)
-    w[j] = j < k ? *reinterpret_cast<const float2*>(sWt + j * CM_CH + lane * 2) : make_float2(0.f, 0.f);
+  // taps of this lane's channel pair are fetched from shared memory just in time (tap j is live for window rows
+  // j .. j + CM_GF - 1 only): 16 taps in registers instead of all 31 -> 3 CTAs per SM instead of 2
+  float2 w[NTAP];
   float2 bias = make_float2(0.f, 0.f);
   if (ch_ok) bias = *reinterpret_cast<const float2*>(bdw + ch);
   float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
@@ -152,6 +151,7 @@ __global__ void __launch_bounds__(256, 2) convmod_fwd_kernel(const __nv_bfloat16
     // window rows tl .. tl + CM_GF + k - 2 ; output i uses rows tl+i .. tl+i+k-1 with taps 0..k-1
 #pragma unroll
     for (int r = 0; r < CM_GF + NTAP - 1; ++r) {
+      if (r < NTAP) w[r] = r < k ? *reinterpret_cast<const float2*>(sWt + r * CM_CH + lane * 2) : make_float2(0.f, 0.f);
       if (KT || r < CM_GF + k - 1) {
         const float2 g = sG[(tl + r) * 32 + lane];
 #pragma unroll
