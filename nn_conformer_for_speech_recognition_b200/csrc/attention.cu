@@ -601,9 +601,7 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
       const int q_idx = i * AT_BQ + row;
       const int64_t stat = static_cast<int64_t>(b * p.H + h) * p.T + min(q_idx, p.T - 1);
       const float lse_r = q_idx < p.T ? p.lse[stat] : INFINITY, delta_r = q_idx < p.T ? p.delta[stat] : 0.f;
-      if (i >= 2) {                          // products of block i-2 read this P/dS buffer: retired before it is rewritten
-        // (already observed: drain_dq(i-2) waited on the same barrier phase)
-      }
+      // (the products of block i-2 that read this P/dS buffer have retired: drain_dq(i-2) waited for them)
       B2C_TM(i, 0)
       mbar_wait(bar_s, ph);
       tc_fence_after();

@@ -76,6 +76,8 @@ __device__ __forceinline__ void stage_glu(const __nv_bfloat16* __restrict__ u, f
 }
 
 // depthwise taps of this CTA's 64 channels -> smem, tap-major [k][64] (coalesced global read, conflict-free float2 reads)
+constexpr int CM_WP = CM_CH + 2;   // tap-row pitch in shared memory: 66 floats (consecutive taps of a channel land 2 banks apart: the
+                                   // transposing store is 2-way conflicted instead of 31-way; float2 reads stay 8-byte aligned)
 constexpr int CM_TAPLD = (CM_CH * CM_MAXK + 255) / 256;    // tap elements per thread (256 threads)
 __device__ __forceinline__ void load_taps(const float* __restrict__ wdw, float (&tv)[CM_TAPLD], int c0, int d, int k) {
   const int nch = min(CM_CH, d - c0);
@@ -89,7 +91,7 @@ __device__ __forceinline__ void store_taps(const float (&tv)[CM_TAPLD], float* _
 #pragma unroll
   for (int i = 0; i < CM_TAPLD; ++i) {
     const int e = threadIdx.x + i * 256;
-    if (e < CM_CH * k) sWt[(e % k) * CM_CH + e / k] = tv[i];
+    if (e < CM_CH * k) sWt[(e % k) * CM_WP + e / k] = tv[i];
   }
 }
 __device__ __forceinline__ void stage_taps(const float* __restrict__ wdw, float* __restrict__ sWt, int c0, int d, int k) {
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(256, 3) convmod_fwd_kernel(const __nv_bfloat16
     // window rows tl .. tl + CM_GF + k - 2 ; output i uses rows tl+i .. tl+i+k-1 with taps 0..k-1
 #pragma unroll
     for (int r = 0; r < CM_GF + NTAP - 1; ++r) {
-      if (r < NTAP) w[r] = r < k ? *reinterpret_cast<const float2*>(sWt + r * CM_CH + lane * 2) : make_float2(0.f, 0.f);
+      if (r < NTAP) w[r] = r < k ? *reinterpret_cast<const float2*>(sWt + r * CM_WP + lane * 2) : make_float2(0.f, 0.f);
       if (KT || r < CM_GF + k - 1) {
         const float2 g = sG[(tl + r) * 32 + lane];
 #pragma unroll
@@ -418,10 +420,22 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
     float2 w[CM_MAXK];                                // REVERSED taps: wr[j'] = w[k-1-j']
 #pragma unroll
     for (int j = 0; j < CM_MAXK; ++j)
-      w[j] = j < k ? *reinterpret_cast<const float2*>(sWt + (k - 1 - j) * CM_CH + lane * 2) : make_float2(0.f, 0.f);
+      w[j] = j < k ? *reinterpret_cast<const float2*>(sWt + (k - 1 - j) * CM_WP + lane * 2) : make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int grp = 0; grp < (CM_TT / 8) / CM_G; ++grp) {
       const int tl = warp * (CM_TT / 8) + grp * CM_G;
+      // the GLU operands of this group's 8 frames are fetched (unconditionally, clamped) BEFORE the tap window runs, so
+      // their latency hides under its 250 FFMA2s instead of being exposed once per frame in the store loop below
+      uint32_t ua[CM_G], ug[CM_G];
+      {
+        const __nv_bfloat16* ub = u + static_cast<int64_t>(b) * T * (2 * d) + (ch_ok ? ch : c0);
+#pragma unroll
+        for (int i = 0; i < CM_G; ++i) {
+          const __nv_bfloat16* rowp = ub + static_cast<int64_t>(min(t0 + tl + i, T - 1)) * (2 * d);
+          ua[i] = *reinterpret_cast<const uint32_t*>(rowp);
+          ug[i] = *reinterpret_cast<const uint32_t*>(rowp + d);
+        }
+      }
       float2 a[CM_G];
 #pragma unroll
       for (int i = 0; i < CM_G; ++i) a[i] = make_float2(0.f, 0.f);
@@ -441,8 +455,7 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
         const int t = t0 + tl + i;
         if (t < T && ch_ok) {
           const int64_t row = static_cast<int64_t>(b) * T + t;
-          const float2 av = unpack_bf16(*reinterpret_cast<const uint32_t*>(u + row * 2 * d + ch));
-          const float2 bv = unpack_bf16(*reinterpret_cast<const uint32_t*>(u + row * 2 * d + d + ch));
+          const float2 av = unpack_bf16(ua[i]), bv = unpack_bf16(ug[i]);
           const float s0 = sigmoid_f(bv.x), s1 = sigmoid_f(bv.y);
           *reinterpret_cast<uint32_t*>(du + row * 2 * d + ch) = pack_bf16(a[i].x * s0, a[i].y * s1);
           *reinterpret_cast<uint32_t*>(du + row * 2 * d + d + ch) =
@@ -530,7 +543,7 @@ extern "C" int b2c_convmod_eval_fwd(const void* u, const float* wdw, const float
   B2C_REQUIRE(u && wdw && bdw && bn_w && bn_b && bn_mean && bn_var && out, "b2c_convmod_eval_fwd: null pointer");
   if (int rc = check_convmod(B, T, d, k, "b2c_convmod_eval_fwd")) return rc;
   dim3 grid((T + CM_TT - 1) / CM_TT, (d + CM_CH - 1) / CM_CH, B);
-  const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) + CM_CH * k * sizeof(float);
+  const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) + CM_WP * k * sizeof(float);
   if (int rc = convmod_fwd_attr()) return rc;
 #define B2C_CM_FWD(KT_)                                                                                          \
   convmod_fwd_kernel<0, KT_><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(                           \
@@ -547,7 +560,7 @@ extern "C" int b2c_convmod_dw_fwd(const void* u, const float* wdw, const float* 
   B2C_REQUIRE(u && wdw && bdw && y && stats, "b2c_convmod_dw_fwd: null pointer");
   if (int rc = check_convmod(B, T, d, k, "b2c_convmod_dw_fwd")) return rc;
   dim3 grid((T + CM_TT - 1) / CM_TT, (d + CM_CH - 1) / CM_CH, B);
-  const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) + CM_CH * k * sizeof(float);
+  const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) + CM_WP * k * sizeof(float);
   if (int rc = convmod_fwd_attr()) return rc;
 #define B2C_CM_FWD(KT_)                                                                                          \
   convmod_fwd_kernel<1, KT_><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(                           \
@@ -615,7 +628,7 @@ extern "C" int b2c_convmod_dw_bwd(const void* dc, const void* y, const void* u, 
   if (int rc = check_convmod(B, T, d, k, "b2c_convmod_dw_bwd")) return rc;
   dim3 grid((T + CM_TT - 1) / CM_TT, (d + CM_CH - 1) / CM_CH, B);
   const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) * 2 + CM_CH * (CM_MAXK + 1) * sizeof(float) +
-                      CM_CH * k * sizeof(float);
+                      CM_WP * k * sizeof(float);
   static bool configured = false;
   if (!configured) {
     B2C_CUDA(cudaFuncSetAttribute(convmod_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
