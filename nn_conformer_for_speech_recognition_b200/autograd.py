@@ -45,9 +45,10 @@ def _side_stream(dev) -> torch.cuda.Stream:
 
 
 def _split_k(tokens: int, out_tiles: int, sms: int = 148) -> int:
-    """split factor for a weight-gradient GEMM: enough CTAs to fill the chip, at least 4 K-blocks each."""
+    """split factor for a weight-gradient GEMM: ONE wave of CTAs (`out_tiles` = 128 x 256 output tiles), at least 4
+    K-blocks each (measured, tools/wgrad_probe.py: more splits only add fp32 reductions)."""
     kb = (tokens + 63) // 64
-    want = max(1, (2 * sms + out_tiles - 1) // out_tiles)
+    want = max(1, sms // max(1, out_tiles))
     return max(1, min(want, kb // 4 if kb >= 4 else 1))
 
 
@@ -121,7 +122,7 @@ class _ConformerFn(torch.autograd.Function):
 
         def wgrad(dyb, act, Mo, No, out):
             """out[Mo,No] += dyb[tokens,Mo]^T act[tokens,No]"""
-            tiles = ((Mo + 127) // 128) * ((No + 127) // 128)
+            tiles = ((Mo + 127) // 128) * ((No + 255) // 256)
             if side is None:
                 ops.gemm(dyb, act, M=Mo, N=No, K=M, a_mn=True, b_mn=True, out=out.view(Mo, No), accumulate=True,
                          split_k=_split_k(M, tiles))

@@ -529,10 +529,12 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   bool cta2 = false;
   int cl = 1;
   if (bn == 0) {
-    // measured on B200 at the Conformer-M shapes (tools/kernel_bench.py): deep-K weight gradients gain from CTA pairs
-    // (half the operand bytes per output), wide forward GEMMs from 128x256 tiles, the rest from 128x128
-    static const bool allow2 = [] { const char* e = getenv("B2C_GEMM_2SM"); return !(e && e[0] == '0'); }();
-    if (allow2 && a_mn && b_mn && N >= 256 && M >= 256) { bn = 256; cta2 = true; }
+    // measured on B200 at the Conformer-M shapes (tools/kernel_bench.py, tools/wgrad_probe.py): weight gradients and
+    // wide forward GEMMs run best on 128x256 tiles of single CTAs (weight gradients with a split-K that gives ONE wave:
+    // 256x1024 at split 18 takes 16.8 us against 20.5 us for CTA pairs at split 37), the rest on 128x128.
+    // B2C_GEMM_2SM=1 forces the CTA-pair path for weight gradients.
+    static const bool force2 = [] { const char* e = getenv("B2C_GEMM_2SM"); return e && e[0] == '1'; }();
+    if (a_mn && b_mn && N >= 256 && M >= 256) { bn = 256; cta2 = force2; }
     else if (ep->act == B2C_ACT_SILU_BWD) bn = (N >= 128) ? 128 : 64;
     else if (N >= 512 || (N >= 256 && K >= 512)) bn = 256;
     else bn = (N >= 128) ? 128 : 64;
