@@ -47,6 +47,13 @@ int b2c_device_check(void);
  *                           v *= alpha;  then  out = bf16(v) | out = v + resid (fp32) | atomicAdd(out, v) (fp32);
  *                           colsum[n] += sum_m v  (optional, bf16 outputs).
  * ------------------------------------------------------------------------------------------------------- */
+/* Value stored in `out2` (the saved pre-activation of act = SILU) where the activation itself is dropped by the fused
+ * dropout: SiLU'(B2C_DROPPED_PREACT) == 0 exactly, so the backward dgrad (act = SILU_BWD, aux = that tensor,
+ * alpha = 1 / keep-probability, see b2c_dropout_keep_scale) needs no mask regeneration. */
+#define B2C_DROPPED_PREACT (-1.0e4f)
+/* exact scale the fused dropout applies to kept elements for probability p (the keep decision uses 8 bits per element) */
+float b2c_dropout_keep_scale(float p);
+
 typedef struct b2c_epilogue {
   const void* bias;   /* fp32 [N] or NULL */
   const void* aux;    /* bf16 [M, ld_aux]: pre-activation for B2C_ACT_SILU_BWD, else NULL */

@@ -75,6 +75,7 @@ SIGNATURES = {
     "b2c_repack_heads": [_P, _P, _L, _I, _I, _I, _P],
 }
 HOST_SIGNATURES = {
+    "b2c_dropout_keep_scale": ([c_float], c_float),
     "b2c_conformer_layer_eval_workspace": ([_I, _I, _I, _I, _I], ctypes.c_size_t),
     "b2c_last_error": ([], c_char_p),
     "b2c_mt19937_seed_host": ([POINTER(c_uint32), c_uint64], None),

@@ -78,6 +78,7 @@ class _ConformerFn(torch.autograd.Function):
         dh = model.head_dim
         scale = 1.0 / math.sqrt(dh)
         drop_p, seed = ctx.drop_p, ctx.seed
+        keep_scale = float(_lib.load().b2c_dropout_keep_scale(drop_p)) if drop_p > 0 else 1.0
         weights = model._cache.get()
         dev = dy.device
         dx = dy.reshape(M, d).to(torch.float32).contiguous()
@@ -154,8 +155,10 @@ class _ConformerFn(torch.autograd.Function):
             def ffn_bwd(pre, site, dyb, next_cast):
                 s = st[pre]
                 wgrad(dyb, s["h"], d, f, G(li, pre + ".sequential.4.weight"))
+                # s["u"] holds B2C_DROPPED_PREACT where the forward dropped the activation (SiLU' = 0 there), so the mask is
+                # not regenerated: kept elements only need the 1/keep scale
                 du = ops.gemm(dyb, w[pre + ".sequential.4.weight"], M=M, N=f, K=d, b_mn=True, act=ops.ACT_SILU_BWD,
-                              aux=s["u"], drop_p=drop_p, drop_seed=sd + site, colsum=G(li, pre + ".sequential.1.bias"))
+                              aux=s["u"], alpha=keep_scale, colsum=G(li, pre + ".sequential.1.bias"))
                 wgrad(du, s["a"], f, d, G(li, pre + ".sequential.1.weight"))
                 da = ops.gemm(du, w[pre + ".sequential.1.weight"], M=M, N=d, K=f, b_mn=True)
                 return ops.layernorm_bwd(da, s["x"], P(pre + ".sequential.0.weight"), s["mean"], s["rstd"], dx, True,

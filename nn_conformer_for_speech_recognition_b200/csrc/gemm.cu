@@ -69,7 +69,10 @@ struct GemmCfg {
   static constexpr uint32_t STG_WARP_BYTES = 32 * CW * 4;                // fp32 transpose buffer per warp
   static constexpr uint32_t STG_OFF = STAGES * STAGE_BYTES;
   static constexpr uint32_t BAR_OFF = STG_OFF + EPI_WARPS * STG_WARP_BYTES;
+  static constexpr uint32_t CS_OFF = BAR_OFF + 256;                      // per-CTA column-sum accumulators (training epilogues)
+  static constexpr uint32_t CS_MAXN = 4096;
   static constexpr uint32_t SMEM = BAR_OFF + 256 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr uint32_t SMEM_EXTRA = SMEM + CS_MAXN * 4;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
@@ -118,6 +121,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // fused column sums (bias gradients): accumulated per CTA in shared memory and flushed with ONE global atomic per
+  // column at the end -- one atomic per column per 32-row chunk (766 k of them on 1024 addresses for the FFN dgrad) cost
+  // more than the rest of the epilogue
+  float* cs_smem = reinterpret_cast<float*>(smem + Cfg::CS_OFF);
+  const bool cs_in_smem = EXTRA && p.ep.colsum != nullptr && p.N <= static_cast<int64_t>(Cfg::CS_MAXN);
+  if (cs_in_smem)
+    for (int i = threadIdx.x; i < static_cast<int>(p.N); i += GEMM_THREADS) cs_smem[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -284,8 +294,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const bool out_bf16 = G ? (ep.out_dtype == B2C_BF16) : (EPI == EPI_BF16 || EPI == EPI_SILU || EPI == EPI_SILU_BWD);
       const bool do_accum = G ? (ep.accumulate != 0) : (EPI == EPI_ACCUM);
       const bool do_out2 = (G || (EXTRA && EPI == EPI_SILU)) && ep.out2 != nullptr;
-      const bool do_drop = (G || (EXTRA && EPI != EPI_BF16 && EPI != EPI_ACCUM)) && p.drop.thresh16 != 0;
-      const bool do_alpha = (G || EPI == EPI_RESID || EPI == EPI_ACCUM) && ep.alpha != 1.f;
+      const bool do_drop = (G || (EXTRA && (EPI == EPI_SILU || EPI == EPI_RESID))) && p.drop.thresh16 != 0;
+      const bool do_alpha = (G || EPI == EPI_RESID || EPI == EPI_ACCUM || EPI == EPI_SILU_BWD) && ep.alpha != 1.f;
 #pragma unroll 1
       for (int ch = 0; ch < Cfg::CHUNKS; ++ch) {
         const int col_t = part * Cfg::SPAN + ch * CW;  // first column of this chunk inside the tile
@@ -344,7 +354,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           *reinterpret_cast<uint4*>(stg + lane * CW + ((c ^ (lane & SWZ)) << 2)) =
               make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         __syncwarp();
-        const bool do_colsum = (G || (EXTRA && EPI != EPI_RESID && EPI != EPI_ACCUM)) && ep.colsum != nullptr && out_bf16;
+        const bool do_colsum = (G || (EXTRA && EPI == EPI_SILU_BWD)) && ep.colsum != nullptr && out_bf16;
         float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
         if (col_ok) {
           // loop-carried pointers / indices: one 64-bit add per stream per row step instead of re-deriving
@@ -370,8 +380,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             if (i * RPI >= rows_left) break;
             const float4 a4 = *reinterpret_cast<const float4*>(stg + rd_off[i % PC] + (i / PC) * (PC * RPI * CW));
             float f[4] = {a4.x + bv.x, a4.y + bv.y, a4.z + bv.z, a4.w + bv.w};
-            if (do_out2) {                             // pre-activation copy (saved for the backward pass)
-              *reinterpret_cast<uint2*>(o2) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+            float ds0 = 1.f, ds1 = 1.f, ds2 = 1.f, ds3 = 1.f;     // dropout scales of this float4 (1 = dropout off)
+            if (do_drop) {
+              drop_scale4g(drop, di, ds0, ds1, ds2, ds3);
+              di += di_step;
+            }
+            if (do_out2) {
+              // pre-activation copy (saved for the backward pass).  Where the activation is about to be DROPPED the copy
+              // holds B2C_DROPPED_PREACT instead: SiLU'(-1e4) is exactly 0, so the backward dgrad (act = SILU_BWD,
+              // alpha = 1/keep) needs no mask regeneration -- the dropout hash costs a third of that kernel's epilogue
+              const float u0 = ds0 != 0.f ? f[0] : B2C_DROPPED_PREACT, u1 = ds1 != 0.f ? f[1] : B2C_DROPPED_PREACT;
+              const float u2 = ds2 != 0.f ? f[2] : B2C_DROPPED_PREACT, u3 = ds3 != 0.f ? f[3] : B2C_DROPPED_PREACT;
+              *reinterpret_cast<uint2*>(o2) = make_uint2(pack_bf16(u0, u1), pack_bf16(u2, u3));
               o2 += o2_step;
             }
             if (do_silu) {
@@ -380,19 +400,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             } else if (want_aux) {                      // f = dL/dh ; aux = pre-activation u ; out = f * silu'(u)
               const float2 a0 = unpack_bf16(prea[i].x), a1 = unpack_bf16(prea[i].y);
               const float u[4] = {a0.x, a0.y, a1.x, a1.y};
+              // SiLU'(u) = s + u s (1 - s), s = sigmoid(u) = (1 + t)/2, t = tanh(u/2)  =>  SiLU' = (1 + t + (u/2)(1 - t^2)) / 2:
+              // one MUFU and three FFMAs, with the 1/keep factor (alpha) folded into the last one
+              const float ha = (G || EPI == EPI_SILU_BWD) ? 0.5f * ep.alpha : 0.5f;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float sg = sigmoid_fast(u[j]);
-                f[j] *= sg * fmaf(u[j], 1.f - sg, 1.f);
+                const float hu = 0.5f * u[j];
+                const float t = tanh_approx(hu);
+                const float r = fmaf(hu, fmaf(-t, t, 1.f), t);
+                f[j] *= fmaf(ha, r, ha);
               }
             }
-            if (do_drop) {
-              float s0, s1, s2, s3;
-              drop_scale4g(drop, di, s0, s1, s2, s3);
-              f[0] *= s0; f[1] *= s1; f[2] *= s2; f[3] *= s3;
-              di += di_step;
-            }
-            if (do_alpha) {
+            if (do_drop) { f[0] *= ds0; f[1] *= ds1; f[2] *= ds2; f[3] *= ds3; }
+            if (do_alpha && !want_aux) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) f[j] *= ep.alpha;
             }
@@ -400,10 +420,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
               const uint2 packed = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
               *reinterpret_cast<uint2*>(ob) = packed;
               ob += o_step;
-              if (do_colsum) {                         // column sums of the ROUNDED values (what the next GEMM consumes)
-                const float2 p0 = unpack_bf16(packed.x), p1 = unpack_bf16(packed.y);
-                cs0 += p0.x; cs1 += p0.y; cs2 += p1.x; cs3 += p1.y;
-              }
+              if (do_colsum) { cs0 += f[0]; cs1 += f[1]; cs2 += f[2]; cs3 += f[3]; }   // bias gradient, from the fp32 values
             } else {
               if (do_accum) {                          // split-K / gradient accumulation: fp32 reductions in L2
                 asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(of), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3])
@@ -427,8 +444,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             cs2 += __shfl_xor_sync(0xffffffffu, cs2, o); cs3 += __shfl_xor_sync(0xffffffffu, cs3, o);
           }
           if (r_lane == 0 && col_ok) {
-            atomicAdd(ep.colsum + col, cs0); atomicAdd(ep.colsum + col + 1, cs1);
-            atomicAdd(ep.colsum + col + 2, cs2); atomicAdd(ep.colsum + col + 3, cs3);
+            float* dst = cs_in_smem ? cs_smem + col : ep.colsum + col;
+            atomicAdd(dst, cs0); atomicAdd(dst + 1, cs1); atomicAdd(dst + 2, cs2); atomicAdd(dst + 3, cs3);
           }
         }
       }
@@ -436,6 +453,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   tc_fence_before();
   __syncthreads();
+  if (cs_in_smem)
+    for (int i = threadIdx.x; i < static_cast<int>(p.N); i += GEMM_THREADS) {
+      const float v = cs_smem[i];
+      if (v != 0.f) atomicAdd(p.ep.colsum + i, v);
+    }
   if constexpr (CDIV > 1) cluster_sync_all();            // peers may still be multicasting into this CTA / signalling its barriers
   if (warp == 1) {
     tc_fence_after();
@@ -449,7 +471,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams&
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CTA2, EXTRA, CL>;
   static bool configured = false;
   if (!configured) {
-    B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM));
     configured = true;
   }
   p.n_tiles = static_cast<int>((p.N + BN - 1) / BN);
@@ -460,7 +482,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams&
     static int max_clusters = -1;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.dynamicSmemBytes = EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -478,14 +500,14 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams&
     B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   } else if constexpr (!CTA2) {
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
+    kern<<<grid, GEMM_THREADS, EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM, st>>>(ta, tb, p);
   } else {
     const int pairs = num_sms() / 2;
     const int npair = p.total_tiles < pairs ? p.total_tiles : pairs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * npair);
     cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.dynamicSmemBytes = EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -579,9 +601,9 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   int epi = EPI_GENERIC;
   const bool plain = !ep->out2 && !ep->aux && !ep->resid && !ep->accumulate && ep->act == B2C_ACT_NONE && ep->alpha == 1.f;
   if (ep->out_dtype == B2C_BF16 && plain && ep->drop_p == 0.f && !ep->colsum) epi = EPI_BF16;
-  else if (ep->out_dtype == B2C_BF16 && ep->act == B2C_ACT_SILU && !ep->resid && ep->alpha == 1.f) epi = EPI_SILU;
+  else if (ep->out_dtype == B2C_BF16 && ep->act == B2C_ACT_SILU && !ep->resid && ep->alpha == 1.f && !ep->colsum) epi = EPI_SILU;
   else if (ep->out_dtype == B2C_F32 && ep->resid && !ep->accumulate && ep->act == B2C_ACT_NONE && !ep->out2) epi = EPI_RESID;
-  else if (ep->out_dtype == B2C_BF16 && ep->act == B2C_ACT_SILU_BWD && !ep->out2 && !ep->bias && ep->alpha == 1.f) epi = EPI_SILU_BWD;
+  else if (ep->out_dtype == B2C_BF16 && ep->act == B2C_ACT_SILU_BWD && !ep->out2 && !ep->bias && ep->drop_p == 0.f) epi = EPI_SILU_BWD;
   else if (ep->out_dtype == B2C_F32 && ep->accumulate && ep->act == B2C_ACT_NONE && !ep->out2 && !ep->bias && ep->drop_p == 0.f) epi = EPI_ACCUM;
   const bool extra = ep->out2 || ep->colsum || ep->drop_p > 0.f;
 #define B2C_LAUNCH(BN_, AM, BMN, E, C2)                                                           \

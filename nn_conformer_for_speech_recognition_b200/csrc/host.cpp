@@ -143,3 +143,10 @@ extern "C" int b2c_device_check(void) {
   B2C_REQUIRE(major == 10, "this library is built for sm_100a only; device reports sm_%d%d", major, minor);
   return 0;
 }
+
+extern "C" float b2c_dropout_keep_scale(float p) {      // mirrors make_drop(): 8-bit keep decision per element
+  if (!(p > 0.f)) return 1.f;
+  uint32_t t16 = static_cast<uint32_t>(p * 65536.0 + 0.5);
+  if (t16 > 65535u) t16 = 65535u;
+  return 256.f / (256.f - static_cast<float>(t16 >> 8));
+}
