@@ -375,7 +375,8 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 template <bool REL>
 __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint32_t tm_s, uint32_t tm_dp, uint8_t* sP,
                                                    uint8_t* sdS, int row, int cq, int key0, int len, float lse_r,
-                                                   float delta_r, uint64_t drop_row, int64_t rel_row, int q_idx) {
+                                                   float delta_r, uint64_t drop_row, int64_t rel_row, int q_idx,
+                                                   uint64_t* bar_sfree) {
   const DropCfg drop = drop_resolve(p.drop);
   const float inv_keep8 = 256.f / (256.f - static_cast<float>(drop.thresh16 >> 8));
   const int c = cq * 32;
@@ -384,6 +385,10 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
   tmem_ld32(tm_s + c, vs);
   tmem_ld32(tm_dp + c, vd);
   tmem_wait_ld();
+  // S / dP now live in registers: the issuer may overwrite the accumulators with the next block's products while this
+  // block's ~4 k cycles of tile math run
+  tc_fence_before();
+  mbar_arrive(bar_sfree);
   const bool full = key0 + c + 32 <= len;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -452,7 +457,8 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
   uint64_t* bar_s = bar_kv + 3;            // S / dP of the next block are in TMEM
   uint64_t* bar_acc = bar_kv + 4;          // dV / dK / dQp products of a block have retired
   uint64_t* bar_tile = bar_kv + 5;         // [2] P / dS buffer published by the 512 math threads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 7);
+  uint64_t* bar_sfree = bar_kv + 7;        // S / dP accumulators read out by the 512 math threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 8);
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool issuer_warp = warp == 16;
 #ifdef B2C_ATTN_TIMING
@@ -498,7 +504,7 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO);
     mbar_init(bar_kv, 1); mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1); mbar_init(bar_s, 1); mbar_init(bar_acc, 1);
-    mbar_init(&bar_tile[0], 512); mbar_init(&bar_tile[1], 512);
+    mbar_init(&bar_tile[0], 512); mbar_init(&bar_tile[1], 512); mbar_init(bar_sfree, 512);
     fence_barrier_init();
   }
   if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 512); }
@@ -549,12 +555,16 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
         const uint32_t bf = i & 1;
         const uint32_t q_addr = base + OFF_Q + bf * 16384, do_addr = base + OFF_DO + bf * 16384;
         const uint32_t p_addr = base + OFF_P + bf * 32768, ds_addr = base + OFF_DS + bf * 32768;
-        // P/dS of block i published; S/dP accumulators read out; dQp of block i-1 drained
         B2C_TI(i, 0)
+        if (i + 1 < nqb) {                   // S/dP of block i are in registers: the next block's products go first
+          mbar_wait(bar_sfree, i & 1);
+          tc_fence_after();
+          issue_s_dp(i + 1);
+        }
+        B2C_TI(i, 1)
+        // P/dS of block i published; dQp of block i-1 drained
         mbar_wait(&bar_tile[bf], (i >> 1) & 1);
         tc_fence_after();
-        B2C_TI(i, 1)
-        if (i + 1 < nqb) issue_s_dp(i + 1);  // first: the math warps continue with block i+1 as soon as these retire
         B2C_TI(i, 2)
 #pragma unroll
         for (int k = 0; k < 8; ++k)          // dV += P^T dO   (reduction over the 128 queries)
@@ -608,7 +618,8 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
       B2C_TM(i, 1)
       attn_bwd_tile_math<REL>(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P + bf * 32768, smem + OFF_DS + bf * 32768, row,
                               cq, key0, len, lse_r, delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad,
-                              (REL && q_idx < p.T) ? (static_cast<int64_t>(row_base + q_idx) * p.H + h) * p.Rp : -1, q_idx);
+                              (REL && q_idx < p.T) ? (static_cast<int64_t>(row_base + q_idx) * p.H + h) * p.Rp : -1, q_idx,
+                              bar_sfree);
       B2C_TM(i, 2)
       if (i > 0) drain_dq(i - 1);            // block i-1's products ran underneath this block's tile math
       B2C_TM(i, 3)
