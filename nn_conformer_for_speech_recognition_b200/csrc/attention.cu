@@ -446,6 +446,7 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
 template <bool REL>
 __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                           const __grid_constant__ CUtensorMap tmDO,
+                                                          const __grid_constant__ CUtensorMap tmDQ,
                                                           const AttnBwdParams p, float* __restrict__ dq_f32) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
     return;
   }
   if (tid == 0) {
-    tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ);
     mbar_init(bar_kv, 1); mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1); mbar_init(bar_s, 1); mbar_init(bar_acc, 1);
     mbar_init(&bar_tile[0], 512); mbar_init(&bar_tile[1], 512); mbar_init(bar_sfree, 512);
     fence_barrier_init();
@@ -589,21 +590,29 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
     }
   } else {
     // ================================ 512 math threads ================================
-    auto drain_dq = [&](int i) {             // dQp of block i: TMEM -> this key block's partial slab (plain stores)
-      const int q_idx = i * AT_BQ + row;
+    // dQp of block i: TMEM -> registers -> the P buffer of block i (its readers, the dV products, have retired) as two
+    // 128B-swizzled [128 rows][32 fp32] boxes -> ONE thread issues two TMA stores into this key block's partial slab.
+    // With ~230 KB of shared memory there is no L1 left and the per-thread 64-byte row pieces cost 1.8 k cycles per
+    // block as plain stores; the TMA unit also clips the rows past the utterance end (3-D map: column, frame, slab*B+b).
+    auto drain_dq = [&](int i) {
       mbar_wait(bar_acc, i & 1);
       tc_fence_after();
       uint32_t v[16];
       __syncwarp();
       tmem_ld16(tm_lane + TM_DQ + cq * 16, v);
       tmem_wait_ld();
-      if (q_idx < p.T) {
-        // fp32 atomics on 75 MB per layer were the bottleneck of the first version: one slab per key block instead
-        float* dst = dq_f32 + (static_cast<int64_t>(j) * p.B * p.T + row_base + q_idx) * (p.H * AT_DH) + h * AT_DH + cq * 16;
+      uint8_t* stg = smem + OFF_P + (i & 1) * 32768 + (cq >> 1) * 16384 + row * 128;
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          *reinterpret_cast<float4*>(dst + g * 4) = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
-                                                                __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(stg + ((((cq & 1) * 4 + g) ^ (row & 7)) << 4)) =
+            make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      fence_proxy_async();
+      named_barrier_sync(1, 512);            // all 512 math threads have staged their pieces
+      if (tid == 0) {
+        const uint8_t* src = smem + OFF_P + (i & 1) * 32768;
+        tma_store_3d(&tmDQ, src, h * AT_DH, i * AT_BQ, j * p.B + b);
+        tma_store_3d(&tmDQ, src + 16384, h * AT_DH + 32, i * AT_BQ, j * p.B + b);
+        tma_store_commit();
       }
     };
     for (int i = 0; i < nqb; ++i) {
@@ -613,6 +622,10 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
       const float lse_r = q_idx < p.T ? p.lse[stat] : INFINITY, delta_r = q_idx < p.T ? p.delta[stat] : 0.f;
       // (the products of block i-2 that read this P/dS buffer have retired: drain_dq(i-2) waited for them)
       B2C_TM(i, 0)
+      if (i >= 2) {                          // P[i & 1] was the staging buffer of dQp(i-2): its TMA stores must have read it
+        if (tid == 0) tma_store_wait_read();
+        named_barrier_sync(1, 512);
+      }
       mbar_wait(bar_s, ph);
       tc_fence_after();
       B2C_TM(i, 1)
@@ -629,6 +642,7 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
       B2C_TM(i, 4)
     }
     drain_dq(nqb - 1);
+    if (tid == 0) tma_store_wait_read();     // shared memory stays valid until the last stores have read it
   }
   tc_fence_before();
   __syncthreads();
@@ -787,8 +801,13 @@ static int attention_bwd_launch(const void* qkv, int64_t ld, int64_t k_off, int6
   p.delta_dbg = dq_f32;     // timing builds scribble cycle stamps over the head of the dQ workspace
   p.bd = bd; p.dbd = static_cast<__nv_bfloat16*>(dbd); p.Rp = Rp;
   dim3 grid((T + AT_BK - 1) / AT_BK, H, B);
-  if (rel) attn_bwd_kernel<true><<<grid, 544, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
-  else attn_bwd_kernel<false><<<grid, 544, ATTN_BWD_SMEM, st>>>(tq, td, p, dq_f32);
+  CUtensorMap tdq;   // partial-dQ slabs as [slab * B + b][frame][H*64] fp32: the frame dimension clips at T per utterance
+  if (int rc = get_tensor_map_3d(&tdq, dq_f32, 4, static_cast<uint64_t>(H) * AT_DH, static_cast<uint64_t>(T),
+                                 static_cast<uint64_t>(grid.x) * B, static_cast<uint64_t>(H) * AT_DH * 4,
+                                 static_cast<uint64_t>(T) * H * AT_DH * 4, 32, 128, true))
+    return rc;
+  if (rel) attn_bwd_kernel<true><<<grid, 544, ATTN_BWD_SMEM, st>>>(tq, td, tdq, p, dq_f32);
+  else attn_bwd_kernel<false><<<grid, 544, ATTN_BWD_SMEM, st>>>(tq, td, tdq, p, dq_f32);
   const int64_t n8 = rows * H * AT_DH / 8;
   attn_dq_cast_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, st>>>(dq_f32, static_cast<__nv_bfloat16*>(dqkv),
                                                                                rows, H * AT_DH, ld, 0, (T + AT_BK - 1) / AT_BK);

@@ -8,6 +8,8 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <utility>
+#include <vector>
 
 #include "b200conformer.h"
 #include "common.cuh"
@@ -60,6 +62,46 @@ struct MapKeyHash {
   }
 };
 static_assert(sizeof(MapKey) == 48, "MapKey must be padding-free");
+
+// 3-D fp32/bf16 map (dims inner -> outer d0, d1, d2; byte strides of d1 and d2), box {b0, b1, 1}.  Small per-process cache.
+int get_tensor_map_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, bool swizzle128) {
+  struct Key3 {
+    const void* base; uint64_t d0, d1, d2, s1, s2; uint32_t b0, b1, eb, swz;
+    bool operator==(const Key3& o) const { return memcmp(this, &o, sizeof(Key3)) == 0; }
+  };
+  static std::mutex mu;
+  static std::vector<std::pair<Key3, CUtensorMap>> cache;
+  Key3 key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.d0 = d0; key.d1 = d1; key.d2 = d2; key.s1 = stride1_bytes; key.s2 = stride2_bytes;
+  key.b0 = b0; key.b1 = b1; key.eb = static_cast<uint32_t>(elem_bytes); key.swz = swizzle128;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& e : cache)
+      if (e.first == key) { *out = e.second; return 0; }
+  }
+  EncodeTiledFn fn = encode_fn();
+  B2C_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  B2C_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && stride1_bytes % 16 == 0 && stride2_bytes % 16 == 0,
+              "TMA needs 16-byte aligned base and pitches");
+  B2C_REQUIRE(b0 * elem_bytes <= 128 || !swizzle128, "TMA box inner extent exceeds the 128B swizzle span");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2C_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", static_cast<int>(r));
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 64) cache.clear();
+    cache.emplace_back(key, *out);
+  }
+  return 0;
+}
 
 int get_tensor_map_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
                       uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
