@@ -447,6 +447,7 @@ template <bool REL>
 __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                           const __grid_constant__ CUtensorMap tmDO,
                                                           const __grid_constant__ CUtensorMap tmDQ,
+                                                          const __grid_constant__ CUtensorMap tmDKV,
                                                           const AttnBwdParams p, float* __restrict__ dq_f32) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
     return;
   }
   if (tid == 0) {
-    tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ);
+    tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ); tma_prefetch_desc(&tmDKV);
     mbar_init(bar_kv, 1); mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1); mbar_init(bar_s, 1); mbar_init(bar_acc, 1);
     mbar_init(&bar_tile[0], 512); mbar_init(&bar_tile[1], 512); mbar_init(bar_sfree, 512);
     fence_barrier_init();
@@ -649,30 +650,30 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
   tc_fence_after();
   B2C_TK(3)
   if (!issuer_warp) {
+    // dV / dK: TMEM -> bf16 -> the (now idle) V / K tiles as 128B-swizzled [128 keys][64] boxes -> two TMA stores that
+    // clip at the utterance end (the per-thread 32-byte row pieces were as slow here as for dQ)
     uint32_t v[16];
-    __syncwarp();
-    tmem_ld16(tm_lane + TM_DV + cq * 16, v);
-    tmem_wait_ld();
-    if (dv_dst) {
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      __syncwarp();
+      tmem_ld16(tm_lane + (which ? TM_DK : TM_DV) + cq * 16, v);
+      tmem_wait_ld();
+      uint8_t* stg = smem + (which ? OFF_K : OFF_V) + row * 128;
 #pragma unroll
       for (int g = 0; g < 2; ++g)
-        reinterpret_cast<uint4*>(dv_dst)[g] =
+        *reinterpret_cast<uint4*>(stg + (((cq * 2 + g) ^ (row & 7)) << 4)) =
             make_uint4(pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
                        pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
                        pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
                        pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
     }
-    __syncwarp();
-    tmem_ld16(tm_lane + TM_DK + cq * 16, v);
-    tmem_wait_ld();
-    if (dk_dst) {
-#pragma unroll
-      for (int g = 0; g < 2; ++g)
-        reinterpret_cast<uint4*>(dk_dst)[g] =
-            make_uint4(pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
-                       pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
-                       pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
-                       pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+    fence_proxy_async();
+    named_barrier_sync(1, 512);
+    if (tid == 0) {
+      tma_store_3d(&tmDKV, smem + OFF_V, p.v_col + h * AT_DH, key0, b);
+      tma_store_3d(&tmDKV, smem + OFF_K, p.k_col + h * AT_DH, key0, b);
+      tma_store_commit();
+      tma_store_wait_read();
     }
   }
   tc_fence_before();
@@ -806,8 +807,12 @@ static int attention_bwd_launch(const void* qkv, int64_t ld, int64_t k_off, int6
                                  static_cast<uint64_t>(grid.x) * B, static_cast<uint64_t>(H) * AT_DH * 4,
                                  static_cast<uint64_t>(T) * H * AT_DH * 4, 32, 128, true))
     return rc;
-  if (rel) attn_bwd_kernel<true><<<grid, 544, ATTN_BWD_SMEM, st>>>(tq, td, tdq, p, dq_f32);
-  else attn_bwd_kernel<false><<<grid, 544, ATTN_BWD_SMEM, st>>>(tq, td, tdq, p, dq_f32);
+  CUtensorMap tdkv;  // dqkv as [b][frame][ld] bf16 (dK / dV tiles are stored through it, clipped at T)
+  if (int rc = get_tensor_map_3d(&tdkv, dqkv, 2, static_cast<uint64_t>(ld), static_cast<uint64_t>(T), static_cast<uint64_t>(B),
+                                 static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(T) * ld * 2, 64, 128, true))
+    return rc;
+  if (rel) attn_bwd_kernel<true><<<grid, 544, ATTN_BWD_SMEM, st>>>(tq, td, tdq, tdkv, p, dq_f32);
+  else attn_bwd_kernel<false><<<grid, 544, ATTN_BWD_SMEM, st>>>(tq, td, tdq, tdkv, p, dq_f32);
   const int64_t n8 = rows * H * AT_DH / 8;
   attn_dq_cast_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, st>>>(dq_f32, static_cast<__nv_bfloat16*>(dqkv),
                                                                                rows, H * AT_DH, ld, 0, (T + AT_BK - 1) / AT_BK);
