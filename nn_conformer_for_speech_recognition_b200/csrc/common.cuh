@@ -29,6 +29,9 @@ int cuda_fail(cudaError_t e, const char* what);      // records message, returns
 int get_tensor_map_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
                       uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128);
 
+// same with an explicit swizzle mode: 0 = none, 1 = 128 B, 2 = 64 B
+int get_tensor_map_2d_sw(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
+                         uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle);
 int get_tensor_map_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, bool swizzle128);
 
@@ -232,6 +235,11 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -102,6 +102,8 @@ enum : int {
 template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA, int CL = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmB,
+                                                                       const __grid_constant__ CUtensorMap tmO,
+                                                                       const __grid_constant__ CUtensorMap tmO2,
                                                                        const GemmParams p) {
   using Cfg = GemmCfg<BN, CTA2>;
   constexpr int BNH = Cfg::BNH;
@@ -296,6 +298,87 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const bool do_out2 = (G || (EXTRA && EPI == EPI_SILU)) && ep.out2 != nullptr;
       const bool do_drop = (G || (EXTRA && (EPI == EPI_SILU || EPI == EPI_RESID))) && p.drop.thresh16 != 0;
       const bool do_alpha = (G || EPI == EPI_RESID || EPI == EPI_ACCUM || EPI == EPI_SILU_BWD) && ep.alpha != 1.f;
+      // ---- bf16 outputs without residual / aux operands: everything happens in the row-per-thread domain the TMEM
+      // load delivers.  Bias / SiLU / dropout are elementwise, the 32 x 32 chunk is packed to bf16 and parked as a
+      // 64B-swizzled 2 KB box (conflict-free 16-byte stores; the saved pre-activation gets a second box), and ONE lane
+      // hands it to the TMA store unit, which also clips at M and N.  Against the fp32 transpose path this halves the
+      // epilogue's shared-memory traffic (the resource these skinny-K GEMMs are bound by) and removes the LDS / address
+      // arithmetic / STG stream entirely -- with ~28 KB of L1 left the STGs alone were a quarter of the epilogue.
+      constexpr bool ROWDOM = (EPI == EPI_BF16 || EPI == EPI_SILU) && Cfg::CW == 32;
+      if constexpr (ROWDOM) {
+        uint8_t* box = reinterpret_cast<uint8_t*>(stg);
+        const int64_t grow0 = static_cast<int64_t>(m_blk) * BM + q * 32;
+        const uint64_t drow = static_cast<uint64_t>(grow0 + lane) * p.N;
+#pragma unroll 1
+        for (int ch = 0; ch < Cfg::CHUNKS; ++ch) {
+          const int col_t = part * Cfg::SPAN + ch * CW;
+          const int64_t col0 = static_cast<int64_t>(n_blk) * BN + col_t;
+          if (lane == 0) tma_store_wait_read();          // the stores issued from this buffer have read it
+          __syncwarp();
+          if (ch == 0) {
+            mbar_wait(&tfull_bar[as], aph);
+            tc_fence_after();
+          }
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16) + col_t, v);
+          tmem_wait_ld();
+          if (ch == Cfg::CHUNKS - 1) {                   // all of this warp's TMEM reads for the tile are done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CTA2) mbar_arrive_cluster(tempty_lead0 + as * 8); else mbar_arrive(&tempty_bar[as]);
+            }
+          }
+          uint32_t ph[16], pu[16];
+          // p = 0.5 (the reference's dropout, asrnn.py:29): ONE hash decides the thread's 32 consecutive columns, one bit
+          // each.  This mask has no second consumer (the backward reads it off the saved pre-activation), so its
+          // granularity is free; other probabilities use the 8-bit-per-element generator.
+          const bool half = do_drop && p.drop.thresh16 == 32768u;
+          uint32_t keep_bits = 0xFFFFFFFFu;
+          if (half) keep_bits = drop_hash32(drop.seed ^ 0x2545F4914F6CDD1Dull, (drow + static_cast<uint64_t>(col0)) >> 5);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias && col0 + 4 * g < p.N) bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + 4 * g));   // warp-uniform address
+            float f[4] = {__uint_as_float(v[4 * g]) + bv.x, __uint_as_float(v[4 * g + 1]) + bv.y,
+                          __uint_as_float(v[4 * g + 2]) + bv.z, __uint_as_float(v[4 * g + 3]) + bv.w};
+            float ds0 = 1.f, ds1 = 1.f, ds2 = 1.f, ds3 = 1.f;
+            if (half) {
+              ds0 = (keep_bits >> (4 * g)) & 1u ? 2.f : 0.f; ds1 = (keep_bits >> (4 * g + 1)) & 1u ? 2.f : 0.f;
+              ds2 = (keep_bits >> (4 * g + 2)) & 1u ? 2.f : 0.f; ds3 = (keep_bits >> (4 * g + 3)) & 1u ? 2.f : 0.f;
+            } else if (do_drop) {
+              drop_scale4g(drop, drow + static_cast<uint64_t>(col0 + 4 * g), ds0, ds1, ds2, ds3);
+            }
+            if (do_out2) {                               // dropped positions carry B2C_DROPPED_PREACT (see below)
+              pu[2 * g] = pack_bf16(ds0 != 0.f ? f[0] : B2C_DROPPED_PREACT, ds1 != 0.f ? f[1] : B2C_DROPPED_PREACT);
+              pu[2 * g + 1] = pack_bf16(ds2 != 0.f ? f[2] : B2C_DROPPED_PREACT, ds3 != 0.f ? f[3] : B2C_DROPPED_PREACT);
+            }
+            if (do_silu) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) f[j] *= sigmoid_fast(f[j]);
+            }
+            if (do_drop) { f[0] *= ds0; f[1] *= ds1; f[2] *= ds2; f[3] *= ds3; }
+            ph[2 * g] = pack_bf16(f[0], f[1]);
+            ph[2 * g + 1] = pack_bf16(f[2], f[3]);
+          }
+          const uint32_t sw = (lane >> 1) & 3;           // SWIZZLE_64B: 16-byte chunk index ^ ((row >> 1) & 3)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            *reinterpret_cast<uint4*>(box + lane * 64 + ((c ^ sw) << 4)) = make_uint4(ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
+            if (do_out2)
+              *reinterpret_cast<uint4*>(box + 2048 + lane * 64 + ((c ^ sw) << 4)) = make_uint4(pu[4 * c], pu[4 * c + 1], pu[4 * c + 2], pu[4 * c + 3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && col0 < p.N && grow0 < p.M) {
+            tma_store_2d(&tmO, box, static_cast<int>(col0), static_cast<int>(grow0));
+            if (do_out2) tma_store_2d(&tmO2, box + 2048, static_cast<int>(col0), static_cast<int>(grow0));
+            tma_store_commit();
+          }
+        }
+      }
+      if constexpr (!ROWDOM)
 #pragma unroll 1
       for (int ch = 0; ch < Cfg::CHUNKS; ++ch) {
         const int col_t = part * Cfg::SPAN + ch * CW;  // first column of this chunk inside the tile
@@ -451,6 +534,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       }
     }
   }
+  if (warp >= 2 && lane == 0) tma_store_wait_read();    // row-domain epilogues: shared memory outlives the last bulk stores
   tc_fence_before();
   __syncthreads();
   if (cs_in_smem)
@@ -466,7 +550,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA, int CL = 1>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                       GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTA2>;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CTA2, EXTRA, CL>;
   static bool configured = false;
@@ -497,10 +582,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams&
     }
     const int ncl = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
     cfg.gridDim = dim3(CL * ncl);
-    B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, p));
   } else if constexpr (!CTA2) {
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    kern<<<grid, GEMM_THREADS, EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM, st>>>(ta, tb, p);
+    kern<<<grid, GEMM_THREADS, EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM, st>>>(ta, tb, to, to2, p);
   } else {
     const int pairs = num_sms() / 2;
     const int npair = p.total_tiles < pairs ? p.total_tiles : pairs;
@@ -514,7 +599,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams&
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, p));
   }
   B2C_CUDA(cudaGetLastError());
   return 0;
@@ -597,21 +682,30 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   else       rc = get_tensor_map_2d(&tb, B, 2, N, K, ldb * 2, 64, BK, true);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // bf16 outputs of the plain / SiLU epilogues leave through TMA stores (row-domain epilogue): 32 x 32 boxes, 64B swizzle
+  const bool rowdom_ok = ep->out_dtype == B2C_BF16 && bn >= 128 && ep->ld_out % 8 == 0 &&
+                         (!ep->out2 || (ep->ld_out2 % 8 == 0 && (reinterpret_cast<uintptr_t>(ep->out2) & 15) == 0));
+  CUtensorMap to = ta, to2 = ta;
+  if (rowdom_ok) {
+    if ((rc = get_tensor_map_2d_sw(&to, ep->out, 2, N, M, ep->ld_out * 2, 32, 32, 2))) return rc;
+    if (ep->out2 && (rc = get_tensor_map_2d_sw(&to2, ep->out2, 2, N, M, ep->ld_out2 * 2, 32, 32, 2))) return rc;
+  }
   // pick the specialised epilogue when the request matches one of the hot-path patterns, else the generic kernel
   int epi = EPI_GENERIC;
   const bool plain = !ep->out2 && !ep->aux && !ep->resid && !ep->accumulate && ep->act == B2C_ACT_NONE && ep->alpha == 1.f;
-  if (ep->out_dtype == B2C_BF16 && plain && ep->drop_p == 0.f && !ep->colsum) epi = EPI_BF16;
-  else if (ep->out_dtype == B2C_BF16 && ep->act == B2C_ACT_SILU && !ep->resid && ep->alpha == 1.f && !ep->colsum) epi = EPI_SILU;
+  if (ep->out_dtype == B2C_BF16 && plain && ep->drop_p == 0.f && !ep->colsum && (rowdom_ok || bn < 128)) epi = EPI_BF16;
+  else if (ep->out_dtype == B2C_BF16 && ep->act == B2C_ACT_SILU && !ep->resid && ep->alpha == 1.f && !ep->colsum && !ep->aux &&
+           (rowdom_ok || bn < 128)) epi = EPI_SILU;
   else if (ep->out_dtype == B2C_F32 && ep->resid && !ep->accumulate && ep->act == B2C_ACT_NONE && !ep->out2) epi = EPI_RESID;
   else if (ep->out_dtype == B2C_BF16 && ep->act == B2C_ACT_SILU_BWD && !ep->out2 && !ep->bias && ep->drop_p == 0.f) epi = EPI_SILU_BWD;
   else if (ep->out_dtype == B2C_F32 && ep->accumulate && ep->act == B2C_ACT_NONE && !ep->out2 && !ep->bias && ep->drop_p == 0.f) epi = EPI_ACCUM;
   const bool extra = ep->out2 || ep->colsum || ep->drop_p > 0.f;
 #define B2C_LAUNCH(BN_, AM, BMN, E, C2)                                                           \
   do {                                                                                             \
-    if (extra) return launch_gemm<BN_, AM, BMN, E, C2, true>(ta, tb, p, st);                       \
-    return launch_gemm<BN_, AM, BMN, E, C2, false>(ta, tb, p, st);                                 \
+    if (extra) return launch_gemm<BN_, AM, BMN, E, C2, true>(ta, tb, to, to2, p, st);                       \
+    return launch_gemm<BN_, AM, BMN, E, C2, false>(ta, tb, to, to2, p, st);                                 \
   } while (0)
-#define B2C_LAUNCH1(BN_, AM, BMN, E, C2) return launch_gemm<BN_, AM, BMN, E, C2, true>(ta, tb, p, st)
+#define B2C_LAUNCH1(BN_, AM, BMN, E, C2) return launch_gemm<BN_, AM, BMN, E, C2, true>(ta, tb, to, to2, p, st)
 #define B2C_DISPATCH(BN_, C2)                                                                      \
   if (bn == BN_ && cta2 == C2) {                                                                   \
     if (!a_mn && !b_mn) {                                                                          \
@@ -633,8 +727,8 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   }
 #define B2C_LAUNCH_CL(BN_, BMN, E, CL_)                                                            \
   do {                                                                                             \
-    if (extra) return launch_gemm<BN_, false, BMN, E, false, true, CL_>(ta, tb, p, st);            \
-    return launch_gemm<BN_, false, BMN, E, false, false, CL_>(ta, tb, p, st);                      \
+    if (extra) return launch_gemm<BN_, false, BMN, E, false, true, CL_>(ta, tb, to, to2, p, st);            \
+    return launch_gemm<BN_, false, BMN, E, false, false, CL_>(ta, tb, to, to2, p, st);                      \
   } while (0)
 #define B2C_DISPATCH_CL(BN_, CL_, DG)                                                              \
   if (bn == BN_ && cl == CL_ && !cta2 && !a_mn) {                                                  \
@@ -642,12 +736,12 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
       if (epi == EPI_BF16) B2C_LAUNCH_CL(BN_, false, EPI_BF16, CL_);                               \
       if (epi == EPI_SILU) B2C_LAUNCH_CL(BN_, false, EPI_SILU, CL_);                               \
       if (epi == EPI_RESID) B2C_LAUNCH_CL(BN_, false, EPI_RESID, CL_);                             \
-      return launch_gemm<BN_, false, false, EPI_GENERIC, false, true, CL_>(ta, tb, p, st);         \
+      return launch_gemm<BN_, false, false, EPI_GENERIC, false, true, CL_>(ta, tb, to, to2, p, st);         \
     }                                                                                              \
     if constexpr (DG) {                                                                            \
       if (epi == EPI_BF16) B2C_LAUNCH_CL(BN_, true, EPI_BF16, CL_);                                \
       if (epi == EPI_SILU_BWD) B2C_LAUNCH_CL(BN_, true, EPI_SILU_BWD, CL_);                        \
-      return launch_gemm<BN_, false, true, EPI_GENERIC, false, true, CL_>(ta, tb, p, st);          \
+      return launch_gemm<BN_, false, true, EPI_GENERIC, false, true, CL_>(ta, tb, to, to2, p, st);          \
     }                                                                                              \
   }
   B2C_DISPATCH_CL(128, 2, true)

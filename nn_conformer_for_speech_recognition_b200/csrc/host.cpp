@@ -105,12 +105,18 @@ int get_tensor_map_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64
 
 int get_tensor_map_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
                       uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
+  return get_tensor_map_2d_sw(out, base, elem_bytes, inner, outer, ld_bytes, box_inner, box_outer, swizzle128 ? 1 : 0);
+}
+
+int get_tensor_map_2d_sw(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
+                         uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle) {
+  const bool swizzle128 = swizzle == 1;
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.base = base; key.inner = inner; key.outer = outer; key.ld = ld_bytes;
-  key.bi = box_inner; key.bo = box_outer; key.eb = static_cast<uint32_t>(elem_bytes); key.swz = swizzle128;
+  key.bi = box_inner; key.bo = box_outer; key.eb = static_cast<uint32_t>(elem_bytes); key.swz = static_cast<uint32_t>(swizzle);
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -121,13 +127,14 @@ int get_tensor_map_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64
   B2C_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld_bytes % 16 == 0,
               "TMA needs 16-byte aligned base and pitch (pitch=%llu)", (unsigned long long)ld_bytes);
   B2C_REQUIRE(box_inner * elem_bytes <= 128 || !swizzle128, "TMA box inner extent exceeds the 128B swizzle span");
+  B2C_REQUIRE(swizzle != 2 || box_inner * elem_bytes <= 64, "TMA box inner extent exceeds the 64B swizzle span");
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B2C_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu box=%ux%u)",
               static_cast<int>(r), (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_bytes,
