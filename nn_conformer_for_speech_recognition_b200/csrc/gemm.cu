@@ -53,6 +53,7 @@ struct GemmParams {
   int64_t M, N, K;
   int kblocks_per_split, total_kb;
   int m_tiles, n_tiles, splits, total_tiles;
+  int tiles_full;            // tiles [tiles_full, total_tiles) are HALF-width tail tiles (two per full tile); == total_tiles when unused
   b2c_epilogue ep;
 };
 
@@ -89,6 +90,27 @@ enum : int {
   EPI_ACCUM = 5,     // out += alpha * acc   (fp32 red.global.add.v4)               weight gradients (split-K)
 };
 
+// Tile schedule.  Tiles [0, tiles_full) are full 128 x BN tiles, n fastest.  When the last wave of a launch would be
+// less than half full (187 tiles on 148 SMs: the second wave runs at 26 %), its tiles are issued as TWO half-width
+// tiles each (hh = 0 / 1), so that wave costs ~0.67 of a full one instead of 1.0 -- single CTAs without split-K only.
+struct TileCoord { int m_blk, n_blk, split, hh; };
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, int cdiv, uint32_t rank) {
+  TileCoord t;
+  if (tile < p.tiles_full) {
+    t.n_blk = tile % p.n_tiles;
+    t.m_blk = ((tile / p.n_tiles) % p.m_tiles) * cdiv + static_cast<int>(rank);
+    t.split = tile / (p.n_tiles * p.m_tiles);
+    t.hh = -1;
+  } else {
+    const int t2 = tile - p.tiles_full, b = p.tiles_full + (t2 >> 1);
+    t.n_blk = b % p.n_tiles;
+    t.m_blk = b / p.n_tiles;
+    t.split = 0;
+    t.hh = t2 & 1;
+  }
+  return t;
+}
+
 // CTA2 = true: launched as clusters of two CTAs; tile = 256 x BN per pair (tcgen05.mma.cta_group::2, M = 256).  CTA r of
 // the pair owns rows [128 r, 128 r + 128) of the tile (A slab, accumulator, epilogue) and loads B rows
 // [r BN/2, (r+1) BN/2); the leader (r = 0) issues every MMA and its commits fan out to both CTAs' barriers.
@@ -104,6 +126,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                                                                        const __grid_constant__ CUtensorMap tmB,
                                                                        const __grid_constant__ CUtensorMap tmO,
                                                                        const __grid_constant__ CUtensorMap tmO2,
+                                                                       const __grid_constant__ CUtensorMap tmBh,
                                                                        const GemmParams p) {
   using Cfg = GemmCfg<BN, CTA2>;
   constexpr int BNH = Cfg::BNH;
@@ -160,12 +183,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       uint32_t ph = 0;
       [[maybe_unused]] int pit = 0;
       for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++pit) {
-        const int n_blk = tile % p.n_tiles;
-        const int m_blk = ((tile / p.n_tiles) % p.m_tiles) * CDIV + static_cast<int>(rank);
-        const int split = tile / (p.n_tiles * p.m_tiles);
+        const TileCoord tc = decode_tile(p, tile, CDIV, rank);
+        const int n_blk = tc.n_blk, m_blk = tc.m_blk, split = tc.split;
+        const bool half_tile = tc.hh >= 0;
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(p.total_kb, kb0 + p.kblocks_per_split);
-        const int b_row0 = n_blk * BN + (CTA2 ? static_cast<int>(rank) * BNH : 0);   // pair: this CTA's half of B's N rows
+        const int b_row0 = n_blk * BN + (CTA2 ? static_cast<int>(rank) * BNH : 0) + (tc.hh > 0 ? BN / 2 : 0);   // pair: this CTA's half of B's N rows
         for (int kb = kb0; kb < kb1; ++kb) {
           B2C_GT(0, pit, 2 * (kb - kb0));
           mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -173,7 +196,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
           if constexpr (!CTA2) {
-            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+            mbar_expect_tx(&full_bar[s], half_tile ? Cfg::A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES);
             if constexpr (!A_MN) {
               tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m_blk * BM);
             } else {
@@ -182,10 +205,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             }
             if constexpr (CL == 1) {
               if constexpr (!B_MN) {
-                tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, b_row0);
+                if (half_tile) tma_load_2d(sB, &tmBh, &full_bar[s], kb * BK, b_row0);
+                else tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, b_row0);
               } else {
 #pragma unroll
-                for (int c = 0; c < BNH / 64; ++c) tma_load_2d(sB + c * 8192, &tmB, &full_bar[s], b_row0 + c * 64, kb * BK);
+                for (int c = 0; c < BNH / 64; ++c)
+                  if (!half_tile || c < BNH / 128) tma_load_2d(sB + c * 8192, &tmB, &full_bar[s], b_row0 + c * 64, kb * BK);
               }
             } else {
               // this CTA's 1/CL slice of the B tile, delivered to the same smem offset (and full barrier) of all CL CTAs
@@ -230,8 +255,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       int s = 0;
       uint32_t ph = 0;
       uint32_t it = 0;
+      constexpr uint32_t idesc_half = umma_idesc_bf16(CTA2 ? 2 * BM : BM, BN / 2, A_MN, B_MN);
       for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++it) {
-        const int split = tile / (p.n_tiles * p.m_tiles);
+        const TileCoord tc = decode_tile(p, tile, CDIV, rank);
+        const int split = tc.split;
+        const uint32_t idesc_t = tc.hh >= 0 ? idesc_half : idesc;
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(p.total_kb, kb0 + p.kblocks_per_split);
         const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
@@ -254,7 +282,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             const uint64_t db = B_MN ? umma_desc_sw128(b_addr + k * 2048, 8192, 1024)
                                      : umma_desc_sw128(b_addr + k * 32, 16, 1024);
             if constexpr (CTA2) umma_bf16_2sm(tm_acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16(tm_acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tm_acc, da, db, idesc_t, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           // smem slot free once these MMAs retire (pair: in both CTAs)
           if constexpr (CTA2) tc_commit_2sm(&empty_bar[s]);
@@ -284,10 +312,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const uint32_t tempty_lead0 = CTA2 ? mapa_u32(&tempty_bar[0], 0) : 0u;
     uint32_t it = 0;
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++it) {
-      const int n_blk = tile % p.n_tiles;
-      const int m_blk = ((tile / p.n_tiles) % p.m_tiles) * CDIV + static_cast<int>(rank);
-      const int split = tile / (p.n_tiles * p.m_tiles);
+      const TileCoord tc = decode_tile(p, tile, CDIV, rank);
+      const int m_blk = tc.m_blk, split = tc.split;
+      const int64_t ncol0 = static_cast<int64_t>(tc.n_blk) * BN + (tc.hh > 0 ? BN / 2 : 0);   // first global column of the tile
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+      if (tc.hh >= 0 && part >= 2) {                   // half-width tail tile: this warp's columns do not exist
+        mbar_wait(&tfull_bar[as], aph);                // (stay in step with the tile sequence before releasing the buffer)
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        continue;
+      }
       const float* bias = split == 0 ? static_cast<const float*>(ep.bias) : nullptr;   // once per split-K
       constexpr bool G = EPI == EPI_GENERIC;
       const bool want_resid = G ? (ep.resid && !ep.accumulate && ep.out_dtype == B2C_F32) : (EPI == EPI_RESID);
@@ -312,7 +348,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll 1
         for (int ch = 0; ch < Cfg::CHUNKS; ++ch) {
           const int col_t = part * Cfg::SPAN + ch * CW;
-          const int64_t col0 = static_cast<int64_t>(n_blk) * BN + col_t;
+          const int64_t col0 = ncol0 + col_t;
           if (lane == 0) tma_store_wait_read();          // the stores issued from this buffer have read it
           __syncwarp();
           if (ch == 0) {
@@ -382,7 +418,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll 1
       for (int ch = 0; ch < Cfg::CHUNKS; ++ch) {
         const int col_t = part * Cfg::SPAN + ch * CW;  // first column of this chunk inside the tile
-        const int64_t col = static_cast<int64_t>(n_blk) * BN + col_t + c_lane * 4;
+        const int64_t col = ncol0 + col_t + c_lane * 4;
         const bool col_ok = col < p.N;
         const int64_t row0 = static_cast<int64_t>(m_blk) * BM + q * 32 + r_lane;
         const int64_t rl64 = p.M - row0;
@@ -551,7 +587,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 
 template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA, int CL = 1>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
-                       GemmParams& p, cudaStream_t st) {
+                       const CUtensorMap& tbh, GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTA2>;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CTA2, EXTRA, CL>;
   static bool configured = false;
@@ -563,6 +599,16 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   constexpr int CDIV = CTA2 ? 2 : CL;
   p.m_tiles = static_cast<int>((p.M + CDIV * BM - 1) / (CDIV * BM));      // M units: blocks, pairs or clusters
   p.total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  p.tiles_full = p.total_tiles;
+  if constexpr (!CTA2 && CL == 1 && !A_MN && BN >= 128) {
+    // a last wave that is at most half full is issued as half-width tiles (see decode_tile)
+    static const bool tail_ok = [] { const char* e = getenv("B2C_GEMM_TAIL"); return !(e && e[0] == '0'); }();
+    const int nsm = num_sms(), rem = p.total_tiles % nsm;
+    if (tail_ok && p.splits == 1 && p.total_tiles > nsm && rem > 0 && 2 * rem <= nsm) {
+      p.tiles_full = p.total_tiles - rem;
+      p.total_tiles = p.tiles_full + 2 * rem;
+    }
+  }
   if constexpr (CL > 1) {
     static int max_clusters = -1;
     cudaLaunchConfig_t cfg = {};
@@ -582,10 +628,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     }
     const int ncl = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
     cfg.gridDim = dim3(CL * ncl);
-    B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, p));
+    B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, tbh, p));
   } else if constexpr (!CTA2) {
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    kern<<<grid, GEMM_THREADS, EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM, st>>>(ta, tb, to, to2, p);
+    kern<<<grid, GEMM_THREADS, EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM, st>>>(ta, tb, to, to2, tbh, p);
   } else {
     const int pairs = num_sms() / 2;
     const int npair = p.total_tiles < pairs ? p.total_tiles : pairs;
@@ -599,7 +645,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, p));
+    B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, tbh, p));
   }
   B2C_CUDA(cudaGetLastError());
   return 0;
@@ -681,6 +727,8 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   if (!b_mn) rc = get_tensor_map_2d(&tb, B, 2, K, N, ldb * 2, BK, cta2 ? bn / 2 : bn / cl, true);
   else       rc = get_tensor_map_2d(&tb, B, 2, N, K, ldb * 2, 64, BK, true);
   if (rc) return rc;
+  CUtensorMap tbh = tb;                  // B boxes of half-width tail tiles (K-major B only; MN-major B loads fewer chunks)
+  if (!b_mn && !cta2 && cl == 1 && bn >= 128 && (rc = get_tensor_map_2d(&tbh, B, 2, K, N, ldb * 2, BK, bn / 2, true))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // bf16 outputs of the plain / SiLU epilogues leave through TMA stores (row-domain epilogue): 32 x 32 boxes, 64B swizzle
   const bool rowdom_ok = ep->out_dtype == B2C_BF16 && bn >= 128 && ep->ld_out % 8 == 0 &&
@@ -702,10 +750,10 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   const bool extra = ep->out2 || ep->colsum || ep->drop_p > 0.f;
 #define B2C_LAUNCH(BN_, AM, BMN, E, C2)                                                           \
   do {                                                                                             \
-    if (extra) return launch_gemm<BN_, AM, BMN, E, C2, true>(ta, tb, to, to2, p, st);                       \
-    return launch_gemm<BN_, AM, BMN, E, C2, false>(ta, tb, to, to2, p, st);                                 \
+    if (extra) return launch_gemm<BN_, AM, BMN, E, C2, true>(ta, tb, to, to2, tbh, p, st);                       \
+    return launch_gemm<BN_, AM, BMN, E, C2, false>(ta, tb, to, to2, tbh, p, st);                                 \
   } while (0)
-#define B2C_LAUNCH1(BN_, AM, BMN, E, C2) return launch_gemm<BN_, AM, BMN, E, C2, true>(ta, tb, to, to2, p, st)
+#define B2C_LAUNCH1(BN_, AM, BMN, E, C2) return launch_gemm<BN_, AM, BMN, E, C2, true>(ta, tb, to, to2, tbh, p, st)
 #define B2C_DISPATCH(BN_, C2)                                                                      \
   if (bn == BN_ && cta2 == C2) {                                                                   \
     if (!a_mn && !b_mn) {                                                                          \
@@ -727,8 +775,8 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   }
 #define B2C_LAUNCH_CL(BN_, BMN, E, CL_)                                                            \
   do {                                                                                             \
-    if (extra) return launch_gemm<BN_, false, BMN, E, false, true, CL_>(ta, tb, to, to2, p, st);            \
-    return launch_gemm<BN_, false, BMN, E, false, false, CL_>(ta, tb, to, to2, p, st);                      \
+    if (extra) return launch_gemm<BN_, false, BMN, E, false, true, CL_>(ta, tb, to, to2, tbh, p, st);            \
+    return launch_gemm<BN_, false, BMN, E, false, false, CL_>(ta, tb, to, to2, tbh, p, st);                      \
   } while (0)
 #define B2C_DISPATCH_CL(BN_, CL_, DG)                                                              \
   if (bn == BN_ && cl == CL_ && !cta2 && !a_mn) {                                                  \
@@ -736,12 +784,12 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
       if (epi == EPI_BF16) B2C_LAUNCH_CL(BN_, false, EPI_BF16, CL_);                               \
       if (epi == EPI_SILU) B2C_LAUNCH_CL(BN_, false, EPI_SILU, CL_);                               \
       if (epi == EPI_RESID) B2C_LAUNCH_CL(BN_, false, EPI_RESID, CL_);                             \
-      return launch_gemm<BN_, false, false, EPI_GENERIC, false, true, CL_>(ta, tb, to, to2, p, st);         \
+      return launch_gemm<BN_, false, false, EPI_GENERIC, false, true, CL_>(ta, tb, to, to2, tbh, p, st);         \
     }                                                                                              \
     if constexpr (DG) {                                                                            \
       if (epi == EPI_BF16) B2C_LAUNCH_CL(BN_, true, EPI_BF16, CL_);                                \
       if (epi == EPI_SILU_BWD) B2C_LAUNCH_CL(BN_, true, EPI_SILU_BWD, CL_);                        \
-      return launch_gemm<BN_, false, true, EPI_GENERIC, false, true, CL_>(ta, tb, to, to2, p, st);          \
+      return launch_gemm<BN_, false, true, EPI_GENERIC, false, true, CL_>(ta, tb, to, to2, tbh, p, st);          \
     }                                                                                              \
   }
   B2C_DISPATCH_CL(128, 2, true)

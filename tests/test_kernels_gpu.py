@@ -394,6 +394,35 @@ def test_fused_adafactor_matches_hf():
             _close(o1.views[i]["row"], st["exp_avg_sq"], rel=1e-3, abs_=1e-12, name="sq")
 
 
+@pytest.mark.parametrize("M,N,K", [(23872, 256, 1024), (23872, 1024, 256), (19100, 256, 256), (40000, 384, 128)])
+def test_gemm_half_width_tail_tiles(ops, M, N, K):
+    """Benchmark-size problems whose last wave of tiles is less than half full: that wave runs as half-width tiles
+    (187 tiles on 148 SMs -> 148 full + 78 half).  Every epilogue family, forward and dgrad operand layouts."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().T + bias
+    _close(ops.gemm(a, w, M=M, N=N, K=K, bias=bias), ref, name="tail bf16")
+    u2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    h = ops.gemm(a, w, M=M, N=N, K=K, bias=bias, act=ops.ACT_SILU, out2=u2)
+    _close(u2, ref, name="tail pre-act")
+    _close(h, torch.nn.functional.silu(ref), name="tail silu")
+    x = torch.randn(M, N, device="cuda", generator=g)
+    want = x + 0.5 * ref
+    out = ops.gemm(a, w, M=M, N=N, K=K, bias=bias, resid=x, out_dtype=torch.float32, alpha=0.5)
+    _close(out, want, rel=5e-3, name="tail resid")
+    wt = w.t().contiguous()                                   # [K, N]: the MN-major B of a dgrad
+    _close(ops.gemm(a, wt, M=M, N=N, K=K, b_mn=True), a.float() @ wt.float(), name="tail dgrad")
+    aux = _bf(torch.randn(M, N, device="cuda", generator=g))
+    sg = torch.sigmoid(aux.float())
+    cs = torch.zeros(N, device="cuda")
+    du = ops.gemm(a, wt, M=M, N=N, K=K, b_mn=True, act=ops.ACT_SILU_BWD, aux=aux, colsum=cs)
+    want_du = (a.float() @ wt.float()) * (sg * (1 + aux.float() * (1 - sg)))
+    _close(du, want_du, name="tail silu bwd")
+    _close(cs, want_du.sum(0), rel=5e-3, abs_=0.5, name="tail colsum")
+
+
 # ----------------------------------------------------------------------------------------------- GEMM, CTA pairs
 @pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, -256), (512, 512, 256, -256), (1000, 1024, 256, -256),
                                       (777, 768, 320, -256), (300, 144, 144, -128), (23872, 256, 1024, -256),
