@@ -18,13 +18,18 @@
 //   warp 0     TMA producer (one elected lane) -> 128B-swizzled smem ring (mbarrier full/empty), runs ahead across tiles
 //   warp 1     TMEM allocator + MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16,
 //              accumulators DOUBLE-BUFFERED in TMEM (2 x BN columns): tile i+1's main loop overlaps tile i's epilogue
-//   warps 2-17 epilogue (16 warps; warp w owns TMEM lanes 32*(w%4).. and one quarter of the BN columns):
-//              tcgen05.ld (thread = row) -> release the TMEM buffer -> XOR-swizzled smem transpose (per warp, no CTA
-//              barrier) -> coalesced domain (lanes along columns): bias / SiLU / SiLU' / dropout / residual and
-//              128-byte coalesced global loads & stores (or red.global.add.v4.f32 for split-K / gradient accumulation)
-// The problems here are skinny (K = 144..2304) so a tile's main loop is only 3-16 k-blocks: the epilogue, not the MMA,
-// is the critical resource -- hence 16 epilogue warps (4 per scheduler: the per-element math is latency bound with
-// fewer), MUFU.TANH-based SiLU, compile-time epilogue variants and the overlap through TMEM.
+//   warps 2-17 epilogue (16 warps; warp w owns TMEM lanes 32*(w%4).. and one quarter of the BN columns), two families:
+//              ROW DOMAIN (bf16 outputs of the plain / SiLU epilogues): tcgen05.ld (thread = row) -> bias / SiLU / dropout on
+//              the thread's 32 consecutive columns -> bf16 -> 64B-swizzled 2 KB box in smem (a second box for the saved
+//              pre-activation) -> TMA store (clips at M / N).  Half the smem traffic of a transpose, no LDS / STG stream.
+//              COALESCED DOMAIN (fp32 residual outputs, SiLU-backward with its aux operand and fused bias-gradient column
+//              sums, split-K accumulation): tcgen05.ld -> release the TMEM buffer -> XOR-swizzled per-warp fp32 transpose ->
+//              lanes along columns: 128-byte coalesced global loads & stores (or red.global.add.v4.f32); the residual /
+//              aux operands are fetched with L1::no_allocate loads before the accumulator is awaited.
+// The problems here are skinny (K = 144..2304) so a tile's main loop is only 3-16 k-blocks and the kernel is bound by
+// SHARED-MEMORY BANDWIDTH (operand fills + MMA operand reads + epilogue staging; measured with in-kernel cycle stamps,
+// DESIGN.md section 4), not by the tensor pipe: hence the overlap through double-buffered TMEM, compile-time epilogue
+// variants, MUFU.TANH-based SiLU, and a tile schedule whose last, mostly empty wave runs as half-width tiles.
 #include <stdlib.h>
 
 #include "common.cuh"
