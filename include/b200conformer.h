@@ -115,13 +115,15 @@ int b2c_convmod_bn_apply(const void* y, const float* mean, const float* rstd, co
  * statistics the forward normalised with (batch stats in train mode, running stats -> rstd = 1/sqrt(var+eps) in eval).
  *  _bn_bwd_reduce: fp64 sums [2*d] (zeroed by the caller): S1 = sum dz, S2 = sum dz*yhat, dz = dc*SiLU'(z)
  *  _dw_bwd       : dy = BN'(dz) on the fly (bn_train selects the batch-stat formula), du bf16 [rows,2d] through the
- *                  depthwise conv and GLU; dwdw [d,k], dbdw, dbn_w, dbn_b fp32 are ACCUMULATED with atomics. */
+ *                  depthwise conv and GLU; dwdw [d,k], dbdw, dbn_w, dbn_b fp32 are ACCUMULATED with atomics, and so is
+ *                  dbias_u (fp32 [2d], optional): the column sums of du = the bias gradient of the pointwise conv
+ *                  that produced u (conformer.py:44-51). */
 int b2c_convmod_bn_bwd_reduce(const void* dc, const void* y, const float* mean, const float* rstd, const float* bn_w,
                               const float* bn_b, double* sums, int64_t rows, int d, void* stream);
 int b2c_convmod_dw_bwd(const void* dc, const void* y, const void* u, const float* mean, const float* rstd,
                        const float* bn_w, const float* bn_b, const double* sums, int bn_train, const float* wdw,
-                       void* du, float* dwdw, float* dbdw, float* dbn_w, float* dbn_b, int B, int T, int d, int k,
-                       void* stream);
+                       void* du, float* dwdw, float* dbdw, float* dbn_w, float* dbn_b, float* dbias_u, int B, int T, int d,
+                       int k, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Multi-head self-attention core, flash style: softmax(Q K^T * scale + key-length mask) V per (batch, head).

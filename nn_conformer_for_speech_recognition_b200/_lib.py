@@ -55,7 +55,7 @@ SIGNATURES = {
     "b2c_convmod_bn_finalize": [_P, _L, _F, _F, _P, _P, _P, _P, _I, _P],
     "b2c_convmod_bn_apply": [_P, _P, _P, _P, _P, _P, _L, _I, _P],
     "b2c_convmod_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
-    "b2c_convmod_dw_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "b2c_convmod_dw_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b2c_attention_bwd": [_P, _L, _L, _L, _P, _P, _P, _L, _P, _P, _P, _P, _I, _I, _I, _F, _F, c_uint64, _P],
     "b2c_attention_fwd": [_P, _L, _L, _L, _P, _P, _L, _P, _I, _I, _I, _F, _F, c_uint64, _P],
     "b2c_attention_rel_fwd": [_P, _L, _L, _L, _L, _P, _L, _L, _P, _P, _L, _P, _I, _I, _I, _F, _F, c_uint64, _P],

@@ -177,8 +177,8 @@ class _ConformerFn(torch.autograd.Function):
             du = ops.convmod_dw_bwd(dc, s["y"], s["u"], s["bmean"], s["brstd"], bn.weight, bn.bias, sums, s["bn_train"],
                                     P("conv_module.sequential.2.weight").view(d, k),
                                     G(li, "conv_module.sequential.2.weight"), G(li, "conv_module.sequential.2.bias"),
-                                    G(li, "conv_module.sequential.3.weight"), G(li, "conv_module.sequential.3.bias"), B, T)
-            ops.colsum(du, G(li, "conv_module.sequential.0.bias"))
+                                    G(li, "conv_module.sequential.3.weight"), G(li, "conv_module.sequential.3.bias"), B, T,
+                                    dbias_u=G(li, "conv_module.sequential.0.bias"))
             wgrad(du, s["a"], 2 * d, d, G(li, "conv_module.sequential.0.weight"))
             da = ops.gemm(du, w["conv_module.sequential.0.weight"], M=M, N=d, K=2 * d, b_mn=True)
             dyb = ops.layernorm_bwd(da, s["x"], P("conv_module.layer_norm.weight"), s["mean"], s["rstd"], dx, True,

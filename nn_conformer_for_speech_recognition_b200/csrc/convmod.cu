@@ -78,6 +78,7 @@ __device__ __forceinline__ void stage_glu(const __nv_bfloat16* __restrict__ u, f
 // depthwise taps of this CTA's 64 channels -> smem, tap-major [k][64] (coalesced global read, conflict-free float2 reads)
 constexpr int CM_WP = CM_CH + 2;   // tap-row pitch in shared memory: 66 floats (consecutive taps of a channel land 2 banks apart: the
                                    // transposing store is 2-way conflicted instead of 31-way; float2 reads stay 8-byte aligned)
+constexpr int CM_RS = CM_MAXK + 3;   // reduction slots per channel in the backward kernel: k taps, dbdw, d(pw1 bias) of both GLU halves
 constexpr int CM_TAPLD = (CM_CH * CM_MAXK + 255) / 256;    // tap elements per thread (256 threads)
 __device__ __forceinline__ void load_taps(const float* __restrict__ wdw, float (&tv)[CM_TAPLD], int c0, int d, int k) {
   const int nch = min(CM_CH, d - c0);
@@ -336,8 +337,8 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
                                                           const double* __restrict__ sums, double inv_count,
                                                           const float* __restrict__ wdw, __nv_bfloat16* __restrict__ du,
                                                           float* __restrict__ dwdw, float* __restrict__ dbdw,
-                                                          float* __restrict__ dbn_w, float* __restrict__ dbn_b, int T,
-                                                          int d, int k) {
+                                                          float* __restrict__ dbn_w, float* __restrict__ dbn_b,
+                                                          float* __restrict__ dbias_u, int T, int d, int k) {
   extern __shared__ float2 sbuf[];
   const int nrow = CM_TT + k - 1;
   float2* sG = sbuf;                                 // GLU(u)  [nrow][32]
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
   }
   __syncthreads();
 
+  float2 dua = make_float2(0.f, 0.f), dug = make_float2(0.f, 0.f);
   // ---- phase 1: dg = correlate(dy, reversed taps) for this warp's 16 frames, then du through the GLU ----
   {
     float2 w[CM_MAXK];                                // REVERSED taps: wr[j'] = w[k-1-j']
@@ -457,9 +459,11 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
           const int64_t row = static_cast<int64_t>(b) * T + t;
           const float2 av = unpack_bf16(ua[i]), bv = unpack_bf16(ug[i]);
           const float s0 = sigmoid_f(bv.x), s1 = sigmoid_f(bv.y);
-          *reinterpret_cast<uint32_t*>(du + row * 2 * d + ch) = pack_bf16(a[i].x * s0, a[i].y * s1);
-          *reinterpret_cast<uint32_t*>(du + row * 2 * d + d + ch) =
-              pack_bf16(a[i].x * av.x * s0 * (1.f - s0), a[i].y * av.y * s1 * (1.f - s1));
+          const float da0 = a[i].x * s0, da1 = a[i].y * s1;
+          const float dg0 = a[i].x * av.x * s0 * (1.f - s0), dg1 = a[i].y * av.y * s1 * (1.f - s1);
+          *reinterpret_cast<uint32_t*>(du + row * 2 * d + ch) = pack_bf16(da0, da1);
+          *reinterpret_cast<uint32_t*>(du + row * 2 * d + d + ch) = pack_bf16(dg0, dg1);
+          dua.x += da0; dua.y += da1; dug.x += dg0; dug.y += dg1;       // bias gradient of the pointwise conv that made u
         }
       }
     }
@@ -495,19 +499,23 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
   // in their place ([warp][tap][64 ch], conflict-free float2 stores -- the first version used 66 shared-memory
   // atomics per thread here), 256 threads add the 8 copies, then one global atomic per (channel, tap)
   __syncthreads();
-  float2* red2 = sbuf;                               // [8][CM_MAXK + 1][32] float2  (69.6 KB <= the two staged tiles)
+  float2* red2 = sbuf;                               // [8][CM_RS][32] float2  (73.7 KB <= the staged tiles + the old dw area)
 #pragma unroll
-  for (int j = 0; j < CM_MAXK; ++j) red2[(warp * (CM_MAXK + 1) + j) * 32 + lane] = acc[j];
-  red2[(warp * (CM_MAXK + 1) + CM_MAXK) * 32 + lane] = make_float2(dbs0, dbs1);
+  for (int j = 0; j < CM_MAXK; ++j) red2[(warp * CM_RS + j) * 32 + lane] = acc[j];
+  red2[(warp * CM_RS + CM_MAXK) * 32 + lane] = make_float2(dbs0, dbs1);
+  red2[(warp * CM_RS + CM_MAXK + 1) * 32 + lane] = dua;
+  red2[(warp * CM_RS + CM_MAXK + 2) * 32 + lane] = dug;
   __syncthreads();
   const float* red = reinterpret_cast<const float*>(sbuf);
-  for (int e = threadIdx.x; e < (CM_MAXK + 1) * CM_CH; e += blockDim.x) {
+  for (int e = threadIdx.x; e < CM_RS * CM_CH; e += blockDim.x) {
     const int j = e / CM_CH, c = e % CM_CH;
-    if (c0 + c >= d || (j >= k && j != CM_MAXK)) continue;
+    if (c0 + c >= d || (j >= k && j < CM_MAXK) || (j > CM_MAXK && dbias_u == nullptr)) continue;
     float sum = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) sum += red[(w * (CM_MAXK + 1) + j) * CM_CH + c];
+    for (int w = 0; w < 8; ++w) sum += red[(w * CM_RS + j) * CM_CH + c];
     if (j == CM_MAXK) atomicAdd(dbdw + c0 + c, sum);
+    else if (j == CM_MAXK + 1) atomicAdd(dbias_u + c0 + c, sum);
+    else if (j == CM_MAXK + 2) atomicAdd(dbias_u + d + c0 + c, sum);
     else atomicAdd(dwdw + static_cast<int64_t>(c0 + c) * k + j, sum);
   }
 }
@@ -622,7 +630,7 @@ extern "C" int b2c_convmod_bn_bwd_reduce(const void* dc, const void* y, const fl
 extern "C" int b2c_convmod_dw_bwd(const void* dc, const void* y, const void* u, const float* mean, const float* rstd,
                                   const float* bn_w, const float* bn_b, const double* sums, int bn_train,
                                   const float* wdw, void* du, float* dwdw, float* dbdw, float* dbn_w, float* dbn_b,
-                                  int B, int T, int d, int k, void* stream) {
+                                  float* dbias_u, int B, int T, int d, int k, void* stream) {
   B2C_REQUIRE(dc && y && u && mean && rstd && bn_w && bn_b && sums && wdw && du && dwdw && dbdw && dbn_w && dbn_b,
               "b2c_convmod_dw_bwd: null pointer");
   if (int rc = check_convmod(B, T, d, k, "b2c_convmod_dw_bwd")) return rc;
@@ -640,7 +648,7 @@ extern "C" int b2c_convmod_dw_bwd(const void* dc, const void* y, const void* u, 
   auto args = [&](auto kern) {
     kern<<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(dc), static_cast<const __nv_bfloat16*>(y),
                                   static_cast<const __nv_bfloat16*>(u), mean, rstd, bn_w, bn_b, sums, inv_count, wdw,
-                                  static_cast<__nv_bfloat16*>(du), dwdw, dbdw, dbn_w, dbn_b, T, d, k);
+                                  static_cast<__nv_bfloat16*>(du), dwdw, dbdw, dbn_w, dbn_b, dbias_u, T, d, k);
   };
   if (bn_train) args(convmod_bwd_kernel<true>); else args(convmod_bwd_kernel<false>);
   B2C_CUDA(cudaGetLastError());

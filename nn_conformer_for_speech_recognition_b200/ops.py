@@ -284,11 +284,14 @@ def convmod_bn_bwd_reduce(dc, y, mean, rstd, bn_w, bn_b):
     return sums
 
 
-def convmod_dw_bwd(dc, y, u, mean, rstd, bn_w, bn_b, sums, bn_train: bool, wdw, dwdw, dbdw, dbn_w, dbn_b, B: int, T: int):
+def convmod_dw_bwd(dc, y, u, mean, rstd, bn_w, bn_b, sums, bn_train: bool, wdw, dwdw, dbdw, dbn_w, dbn_b, B: int, T: int,
+                   dbias_u=None):
+    """dbias_u (fp32 [2d], optional): accumulates the column sums of du (bias gradient of the pointwise conv before the GLU)."""
     d, k = wdw.shape[0], wdw.shape[-1]
     du = torch.empty((B * T, 2 * d), device=u.device, dtype=torch.bfloat16)
     call("b2c_convmod_dw_bwd", ptr(dc), ptr(y), ptr(u), ptr(mean), ptr(rstd), ptr(bn_w), ptr(bn_b), ptr(sums),
-         int(bn_train), ptr(wdw), ptr(du), ptr(dwdw), ptr(dbdw), ptr(dbn_w), ptr(dbn_b), B, T, d, k, stream_ptr())
+         int(bn_train), ptr(wdw), ptr(du), ptr(dwdw), ptr(dbdw), ptr(dbn_w), ptr(dbn_b), ptr(dbias_u), B, T, d, k,
+         stream_ptr())
     return du
 
 

@@ -19,7 +19,7 @@ for _ in range(2):
     ops.gemm(a, w1, M=M, N=f, K=d, bias=b1, act=ops.ACT_SILU, out=out_f, out2=u2, drop_p=0.5, drop_seed=1)     # FFN-1 fwd (train)
     ops.gemm(hbuf, w2, M=M, N=d, K=f, bias=b2, resid=x, out_dtype=torch.float32, alpha=0.5, drop_p=0.5, drop_seed=2)  # FFN-2 fwd
     ops.gemm(a, wq, M=M, N=3 * d, K=d, bias=None)                                                             # QKV
-    ops.gemm(a, w2, M=M, N=f, K=d, b_mn=True, act=ops.ACT_SILU_BWD, aux=u2, out=out_f, drop_p=0.5, drop_seed=1, colsum=cs)  # dgrad SiLU'
+    ops.gemm(a, w2, M=M, N=f, K=d, b_mn=True, act=ops.ACT_SILU_BWD, aux=u2, out=out_f, alpha=2.0, colsum=cs)      # dgrad SiLU' (mask from u2)
     ops.gemm(hbuf, w1, M=M, N=d, K=f, b_mn=True)                                                             # dgrad K=1024
     ops.gemm(a, hbuf, M=d, N=f, K=M, a_mn=True, b_mn=True, out=dW, accumulate=True, split_k=37)              # wgrad
     y, mean, rstd = ops.layernorm_fwd(x, g, be, save_stats=True)
