@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
 }
 
 // pass 2: dy on the fly -> du (through depthwise conv + GLU), dwdw, dbdw (fp32 atomics), dbn_w/dbn_b (from sums)
-template <bool BN_TRAIN>
+// KT = compile-time tap count (31) or 0 = run-time k (loops sized for CM_MAXK, dead taps multiplied by zero)
+template <bool BN_TRAIN, int KT>
 __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16* __restrict__ dc,
                                                           const __nv_bfloat16* __restrict__ y,
                                                           const __nv_bfloat16* __restrict__ u,
@@ -338,7 +339,9 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
                                                           const float* __restrict__ wdw, __nv_bfloat16* __restrict__ du,
                                                           float* __restrict__ dwdw, float* __restrict__ dbdw,
                                                           float* __restrict__ dbn_w, float* __restrict__ dbn_b,
-                                                          float* __restrict__ dbias_u, int T, int d, int k) {
+                                                          float* __restrict__ dbias_u, int T, int d, int k_rt) {
+  const int k = KT ? KT : k_rt;
+  constexpr int NT = KT ? KT : CM_MAXK;
   extern __shared__ float2 sbuf[];
   const int nrow = CM_TT + k - 1;
   float2* sG = sbuf;                                 // GLU(u)  [nrow][32]
@@ -419,9 +422,9 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
   float2 dua = make_float2(0.f, 0.f), dug = make_float2(0.f, 0.f);
   // ---- phase 1: dg = correlate(dy, reversed taps) for this warp's 16 frames, then du through the GLU ----
   {
-    float2 w[CM_MAXK];                                // REVERSED taps: wr[j'] = w[k-1-j']
+    float2 w[NT];                                     // REVERSED taps: wr[j'] = w[k-1-j']
 #pragma unroll
-    for (int j = 0; j < CM_MAXK; ++j)
+    for (int j = 0; j < NT; ++j)
       w[j] = j < k ? *reinterpret_cast<const float2*>(sWt + (k - 1 - j) * CM_WP + lane * 2) : make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int grp = 0; grp < (CM_TT / 8) / CM_G; ++grp) {
@@ -442,13 +445,13 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
 #pragma unroll
       for (int i = 0; i < CM_G; ++i) a[i] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int r = 0; r < CM_G + CM_MAXK - 1; ++r) {
-        if (r < CM_G + k - 1) {
+      for (int r = 0; r < CM_G + NT - 1; ++r) {
+        if (KT || r < CM_G + k - 1) {
           const float2 dyr = sDY[(tl + r) * 32 + lane];
 #pragma unroll
           for (int i = 0; i < CM_G; ++i) {
             const int j = r - i;
-            if (j >= 0 && j < CM_MAXK) a[i] = ffma2(dyr, w[j], a[i]);
+            if (j >= 0 && j < NT) a[i] = ffma2(dyr, w[j], a[i]);
           }
         }
       }
@@ -470,9 +473,9 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
   }
 
   // ---- phase 2: dw[j] += dy[t] * g[t + j - h] over this warp's frames (taps are dead: registers are reused) ----
-  float2 acc[CM_MAXK];
+  float2 acc[NT];
 #pragma unroll
-  for (int j = 0; j < CM_MAXK; ++j) acc[j] = make_float2(0.f, 0.f);
+  for (int j = 0; j < NT; ++j) acc[j] = make_float2(0.f, 0.f);
   float dbs0 = 0.f, dbs1 = 0.f;
 #pragma unroll 1
   for (int grp = 0; grp < (CM_TT / 8) / CM_G; ++grp) {
@@ -484,13 +487,13 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
       dbs0 += dyc[i].x; dbs1 += dyc[i].y;
     }
 #pragma unroll
-    for (int r = 0; r < CM_G + CM_MAXK - 1; ++r) {
-      if (r < CM_G + k - 1) {
+    for (int r = 0; r < CM_G + NT - 1; ++r) {
+      if (KT || r < CM_G + k - 1) {
         const float2 gr = sG[(tl + r) * 32 + lane];
 #pragma unroll
         for (int i = 0; i < CM_G; ++i) {
           const int j = r - i;
-          if (j >= 0 && j < CM_MAXK) acc[j] = ffma2(dyc[i], gr, acc[j]);
+          if (j >= 0 && j < NT) acc[j] = ffma2(dyc[i], gr, acc[j]);
         }
       }
     }
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
   __syncthreads();
   float2* red2 = sbuf;                               // [8][CM_RS][32] float2  (73.7 KB <= the staged tiles + the old dw area)
 #pragma unroll
-  for (int j = 0; j < CM_MAXK; ++j) red2[(warp * CM_RS + j) * 32 + lane] = acc[j];
+  for (int j = 0; j < NT; ++j) red2[(warp * CM_RS + j) * 32 + lane] = acc[j];
   red2[(warp * CM_RS + CM_MAXK) * 32 + lane] = make_float2(dbs0, dbs1);
   red2[(warp * CM_RS + CM_MAXK + 1) * 32 + lane] = dua;
   red2[(warp * CM_RS + CM_MAXK + 2) * 32 + lane] = dug;
@@ -639,8 +642,12 @@ extern "C" int b2c_convmod_dw_bwd(const void* dc, const void* y, const void* u, 
                       CM_WP * k * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    B2C_CUDA(cudaFuncSetAttribute(convmod_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    B2C_CUDA(cudaFuncSetAttribute(convmod_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_bwd_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_bwd_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_bwd_kernel<true, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_bwd_kernel<false, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_bwd_kernel<true, 33>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2C_CUDA(cudaFuncSetAttribute(convmod_bwd_kernel<false, 33>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
   const double inv_count = 1.0 / (static_cast<double>(B) * T);
@@ -650,7 +657,9 @@ extern "C" int b2c_convmod_dw_bwd(const void* dc, const void* y, const void* u, 
                                   static_cast<const __nv_bfloat16*>(u), mean, rstd, bn_w, bn_b, sums, inv_count, wdw,
                                   static_cast<__nv_bfloat16*>(du), dwdw, dbdw, dbn_w, dbn_b, dbias_u, T, d, k);
   };
-  if (bn_train) args(convmod_bwd_kernel<true>); else args(convmod_bwd_kernel<false>);
+  if (k == 31)      { if (bn_train) args(convmod_bwd_kernel<true, 31>); else args(convmod_bwd_kernel<false, 31>); }
+  else if (k == 33) { if (bn_train) args(convmod_bwd_kernel<true, 33>); else args(convmod_bwd_kernel<false, 33>); }
+  else              { if (bn_train) args(convmod_bwd_kernel<true, 0>); else args(convmod_bwd_kernel<false, 0>); }
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
