@@ -53,10 +53,11 @@ __device__ __forceinline__ float tanh_approx(float x) {
 }
 __device__ __forceinline__ float sigmoid_f(float z) { return fmaf(0.5f, tanh_approx(0.5f * z), 0.5f); }
 __device__ __forceinline__ float silu_f(float z) { return z * sigmoid_f(z); }
-// d/dz [z*sigmoid(z)] = s * (1 + z*(1-s))
+// d/dz [z*sigmoid(z)] = s + z s (1 - s), s = (1 + t)/2, t = tanh(z/2)  =>  (1 + t + (z/2)(1 - t^2)) / 2: one MUFU, three FFMA
 __device__ __forceinline__ float silu_grad_f(float z) {
-  float s = sigmoid_f(z);
-  return s * (1.f + z * (1.f - s));
+  const float hz = 0.5f * z;
+  const float t = tanh_approx(hz);
+  return fmaf(0.5f, fmaf(hz, fmaf(-t, t, 1.f), t), 0.5f);
 }
 // packed fp32 FMA (FFMA2): d = a * b + c on two lanes of a 64-bit register pair -- half the issue slots of two FFMAs
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
