@@ -12,6 +12,8 @@
 // read consecutive 8-byte words), each warp then produces 16 frames for its 64 channels as two groups of 8 outputs
 // from a register sliding window (8+k-1 smem reads per 8 outputs instead of 8k), taps held in registers.
 // Frames past `lengths[b]` are NOT zeroed (conformer.py:85-88); only the utterance edges are zero padded.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "b200conformer.h"
 
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
 // ================================================================================================
 
 // pass 1: S1 = sum dz, S2 = sum dz*yhat per channel (fp64 atomics, once per CTA per channel) = dbeta, dgamma
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dc,
+__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dc,
                                                            const __nv_bfloat16* __restrict__ y,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ bn_w, const float* __restrict__ bn_b,
@@ -282,45 +284,56 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
   for (int i = threadIdx.x; i < 2 * d; i += 256) red_dyn[i] = 0.f;
   __syncthreads();
   if (tr < rpi) {
-    float m[8], q[8], g[8], bb[8], s1[8], s2[8];
+    // per channel only two folded constants stay in registers (z = y*A + C with A = rstd*gamma, C = beta - mean*A) and
+    // the sums are taken over dz and dz*y; sum(dz*yhat) = rstd * (sum(dz*y) - mean*sum(dz)) is formed once at the end:
+    // ~64 registers -> 4 CTAs per SM (the first version held 6 arrays of 8 and ran at 2 CTAs per SM, issue bound)
+    float A[8], C[8], s1[8], s3[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = tg * 8 + j;
-      m[j] = __ldg(mean + c); q[j] = __ldg(rstd + c); g[j] = __ldg(bn_w + c); bb[j] = __ldg(bn_b + c);
-      s1[j] = s2[j] = 0.f;
+    for (int j4 = 0; j4 < 2; ++j4) {
+      const int c = tg * 8 + j4 * 4;
+      const float4 q = __ldg(reinterpret_cast<const float4*>(rstd + c)), gw = __ldg(reinterpret_cast<const float4*>(bn_w + c));
+      const float4 gb = __ldg(reinterpret_cast<const float4*>(bn_b + c)), mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+      A[j4 * 4 + 0] = q.x * gw.x; A[j4 * 4 + 1] = q.y * gw.y; A[j4 * 4 + 2] = q.z * gw.z; A[j4 * 4 + 3] = q.w * gw.w;
+      C[j4 * 4 + 0] = gb.x - mu.x * A[j4 * 4 + 0]; C[j4 * 4 + 1] = gb.y - mu.y * A[j4 * 4 + 1];
+      C[j4 * 4 + 2] = gb.z - mu.z * A[j4 * 4 + 2]; C[j4 * 4 + 3] = gb.w - mu.w * A[j4 * 4 + 3];
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s3[j] = 0.f;
     const int64_t r_end = min(rows, (static_cast<int64_t>(blockIdx.x) + 1) * rows_per_block);
-    constexpr int UN = 4;
+    constexpr int UN = 2;
     for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + tr; r0 < r_end; r0 += static_cast<int64_t>(UN) * rpi) {
       uint4 vd[UN], vy[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
-        const int64_t r = r0 + static_cast<int64_t>(u) * rpi;
-        if (r < r_end) {
-          vd[u] = *reinterpret_cast<const uint4*>(dc + r * d + tg * 8);
-          vy[u] = *reinterpret_cast<const uint4*>(y + r * d + tg * 8);
-        }
+        const int64_t r = min(r0 + static_cast<int64_t>(u) * rpi, r_end - 1);          // clamped: loads stay unconditional
+        vd[u] = *reinterpret_cast<const uint4*>(dc + r * d + tg * 8);
+        vy[u] = *reinterpret_cast<const uint4*>(y + r * d + tg * 8);
       }
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
-        const int64_t r = r0 + static_cast<int64_t>(u) * rpi;
-        if (r >= r_end) break;
+        const float live = r0 + static_cast<int64_t>(u) * rpi < r_end ? 1.f : 0.f;
         const uint32_t wd[4] = {vd[u].x, vd[u].y, vd[u].z, vd[u].w}, wy[4] = {vy[u].x, vy[u].y, vy[u].z, vy[u].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 dcv = unpack_bf16(wd[j]), yv = unpack_bf16(wy[j]);
-          const float yh0 = (yv.x - m[2 * j]) * q[2 * j], yh1 = (yv.y - m[2 * j + 1]) * q[2 * j + 1];
-          const float dz0 = dcv.x * silu_grad_f(fmaf(yh0, g[2 * j], bb[2 * j]));
-          const float dz1 = dcv.y * silu_grad_f(fmaf(yh1, g[2 * j + 1], bb[2 * j + 1]));
+          const float dz0 = live * dcv.x * silu_grad_f(fmaf(yv.x, A[2 * j], C[2 * j]));
+          const float dz1 = live * dcv.y * silu_grad_f(fmaf(yv.y, A[2 * j + 1], C[2 * j + 1]));
           s1[2 * j] += dz0; s1[2 * j + 1] += dz1;
-          s2[2 * j] = fmaf(dz0, yh0, s2[2 * j]); s2[2 * j + 1] = fmaf(dz1, yh1, s2[2 * j + 1]);
+          s3[2 * j] = fmaf(dz0, yv.x, s3[2 * j]); s3[2 * j + 1] = fmaf(dz1, yv.y, s3[2 * j + 1]);
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&red_dyn[tg * 8 + j], s1[j]);
-      atomicAdd(&red_dyn[d + tg * 8 + j], s2[j]);
+    for (int j4 = 0; j4 < 2; ++j4) {
+      const int c = tg * 8 + j4 * 4;
+      const float4 q = __ldg(reinterpret_cast<const float4*>(rstd + c)), mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+      const float qq[4] = {q.x, q.y, q.z, q.w}, mm[4] = {mu.x, mu.y, mu.z, mu.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j4 * 4 + e;
+        atomicAdd(&red_dyn[c + e], s1[j]);
+        atomicAdd(&red_dyn[d + c + e], qq[e] * (s3[j] - mm[e] * s1[j]));
+      }
     }
   }
   __syncthreads();
@@ -619,7 +632,8 @@ extern "C" int b2c_convmod_bn_bwd_reduce(const void* dc, const void* y, const fl
   if (rows <= 0) return 0;
   B2C_REQUIRE(d <= 2048, "b2c_convmod_bn_bwd_reduce: d must be <= 2048");
   const int rpi = 256 / (d / 8);
-  int64_t nblk = static_cast<int64_t>(num_sms()) * 2;    // every CTA ends with 2*d fp64 atomics: keep the CTA count low
+  static const int per_sm = [] { const char* e = getenv("B2C_BN_RED_PER_SM"); return e ? atoi(e) : 2; }();
+  int64_t nblk = static_cast<int64_t>(num_sms()) * per_sm;   // 2 CTAs per SM by default: every CTA ends with 2*d fp64 atomics, more CTAs measured slower
   int64_t rpb = (rows + nblk - 1) / nblk;
   rpb = ((rpb + rpi - 1) / rpi) * rpi;
   nblk = (rows + rpb - 1) / rpb;
