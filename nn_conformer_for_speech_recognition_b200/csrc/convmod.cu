@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
 // ================================================================================================
 
 // pass 1: S1 = sum dz, S2 = sum dz*yhat per channel (fp64 atomics, once per CTA per channel) = dbeta, dgamma
-__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dc,
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dc,
                                                            const __nv_bfloat16* __restrict__ y,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ bn_w, const float* __restrict__ bn_b,
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const __nv_bfloat
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s3[j] = 0.f;
     const int64_t r_end = min(rows, (static_cast<int64_t>(blockIdx.x) + 1) * rows_per_block);
-    constexpr int UN = 2;
+    constexpr int UN = 5;                              // ~10 rows per thread: two batches of loads, two memory round trips
     for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + tr; r0 < r_end; r0 += static_cast<int64_t>(UN) * rpi) {
       uint4 vd[UN], vy[UN];
 #pragma unroll
@@ -632,8 +632,8 @@ extern "C" int b2c_convmod_bn_bwd_reduce(const void* dc, const void* y, const fl
   if (rows <= 0) return 0;
   B2C_REQUIRE(d <= 2048, "b2c_convmod_bn_bwd_reduce: d must be <= 2048");
   const int rpi = 256 / (d / 8);
-  static const int per_sm = [] { const char* e = getenv("B2C_BN_RED_PER_SM"); return e ? atoi(e) : 2; }();
-  int64_t nblk = static_cast<int64_t>(num_sms()) * per_sm;   // 2 CTAs per SM by default: every CTA ends with 2*d fp64 atomics, more CTAs measured slower
+  static const int per_sm = [] { const char* e = getenv("B2C_BN_RED_PER_SM"); return e ? atoi(e) : 1; }();
+  int64_t nblk = static_cast<int64_t>(num_sms()) * per_sm;   // 1 CTA per SM by default: every CTA ends with 2*d fp64 atomics and those dominate (12 / 14 / 18 us at 1 / 2 / 4 per SM)
   int64_t rpb = (rows + nblk - 1) / nblk;
   rpb = ((rpb + rpi - 1) / rpi) * rpi;
   nblk = (rows + rpb - 1) / rpb;
