@@ -33,7 +33,7 @@ def conformer_apply(model: Conformer, inp: torch.Tensor, lengths_i32: torch.Tens
     return _ConformerFn.apply(inp, lengths_i32, model, *params)
 
 
-_WGRAD_SIDE_STREAM = os.environ.get("B2C_WGRAD_STREAM", "1") != "0"
+_WGRAD_SIDE_STREAM = os.environ.get("B2C_WGRAD_STREAM", "0") == "1"   # measured neutral once every wgrad ran as one wave
 _SIDE = {}
 
 
@@ -114,9 +114,10 @@ class _ConformerFn(torch.autograd.Function):
             i = li * np_ + _LAYER_PARAMS.index(name)
             return arena[offs[i]:offs[i] + sizes[i]]
 
-        # Weight-gradient GEMMs have no consumer inside the backward pass: they go to a side stream, where their CTAs
-        # fill the SMs the dependent chain (dgrad GEMM -> LayerNorm backward -> cast ...) leaves idle in its tail waves
-        # and run next to the memory-bound kernels.  Operands stay referenced until the streams are joined again.
+        # Weight-gradient GEMMs have no consumer inside the backward pass: with B2C_WGRAD_STREAM=1 they go to a side stream,
+        # where their CTAs fill the SMs the dependent chain (dgrad GEMM -> LayerNorm backward -> cast ...) leaves idle in
+        # its tail waves (+2 % when the GEMMs still had ragged last waves; neutral since, hence off by default).
+        # Operands stay referenced until the streams are joined again.
         main = torch.cuda.current_stream()
         side = _side_stream(dev) if _WGRAD_SIDE_STREAM else None
         keep = []
