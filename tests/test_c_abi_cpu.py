@@ -80,3 +80,26 @@ def test_sources_avoid_banned_batch_memcpy():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 for b in banned:
                     assert b not in text, f"{f} mentions {b}"
+
+
+def test_dropout_keep_scale_host(lib):
+    """1 / keep-probability the fused dropout applies (8-bit decision per element): exact for p = 0.5."""
+    assert lib.b2c_dropout_keep_scale(0.0) == 1.0
+    assert lib.b2c_dropout_keep_scale(0.5) == 2.0
+    assert abs(lib.b2c_dropout_keep_scale(0.1) - 256.0 / (256 - (round(0.1 * 65536) >> 8))) < 1e-6
+    assert lib.b2c_dropout_keep_scale(0.25) == pytest.approx(4.0 / 3.0, rel=1e-6)
+
+
+def test_layer_eval_workspace_and_struct_layout(lib):
+    """b2c_conformer_layer_eval's workspace formula and the ctypes mirror of struct b2c_layer_weights (32 pointers)."""
+    from nn_conformer_for_speech_recognition_b200 import _lib
+    B, T, d, f, H = 64, 373, 256, 1024, 4
+    M, Hd = B * T, H * 64
+    al = lambda v: (v + 255) // 256 * 256                                # noqa: E731
+    want = al(M * d * 2) + al(M * f * 2) + al(M * 3 * Hd * 2) + al(M * Hd * 2) + al(M * 2 * d * 2) + al(M * d * 2)
+    assert lib.b2c_conformer_layer_eval_workspace(B, T, d, f, H) == want
+    assert ctypes.sizeof(_lib.FfnWeights) == 6 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_lib.LayerWeights) == 32 * ctypes.sizeof(ctypes.c_void_p)
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = hdr[hdr.index("typedef struct b2c_layer_weights {"):hdr.index("} b2c_layer_weights;")]
+    assert body.count("const float*") + body.count("const void*") == 20 and body.count("b2c_ffn_weights ffn") == 2

@@ -160,3 +160,14 @@ def test_nst_sweep_world2_gloo_restores_dataset_order():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res) and sorted(n for _, _, n in res) == [18, 19], res
+
+
+def test_plan_sweep_edge_cases():
+    from nn_conformer_for_speech_recognition_b200 import nst
+    assert nst.plan_sweep([], 8) == []
+    assert nst.plan_sweep([5, 7], 8, rank=3, world=4) == []                      # more ranks than utterances
+    one = nst.plan_sweep([5, 7, 6], 2, rank=0, world=1)
+    assert [b.indices for b in one] == [[0, 2], [1]] and [b.max_len for b in one] == [6, 7]
+    assert nst.merge_shards([{0: "a", 2: "c"}, {1: "b"}], 3) == ["a", "b", "c"]
+    with pytest.raises(ValueError):
+        nst.merge_shards([{0: "a"}], 2)
