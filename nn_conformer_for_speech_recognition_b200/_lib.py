@@ -161,12 +161,33 @@ def replay(rows, name: str, reps: int = 3):
     fn = getattr(load(), name)
     for args, _, _ in calls:
         fn(*args)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    # Replayed from ONE CUDA graph so that the timed region holds no Python / ctypes launch cost (a ~20 us kernel is
+    # about as long as one ctypes call: an eager loop can end up measuring the host).  Captured with capture_begin/end
+    # directly: torch.cuda.graph() would empty the allocator cache first and unmap buffers these launches point at.
+    graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin()
+            for args, _, _ in calls:                  # every entry point takes the stream as its last argument
+                fn(*(list(args[:-1]) + [side.cuda_stream]))
+            g.capture_end()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = g
+    except Exception:
+        graph = None
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        for args, _, _ in calls:
-            fn(*args)
+        if graph is not None:
+            graph.replay()
+        else:
+            for args, _, _ in calls:
+                fn(*args)
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (reps * len(calls))
