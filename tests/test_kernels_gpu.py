@@ -286,6 +286,35 @@ def test_attention_rel_fwd_bwd(ops, B, T, H, lens):
     _close(dpw, pf.grad, rel=3e-2, name="rel dPw")
 
 
+def test_attention_dropout_mask_is_the_same_in_forward_and_backward(ops):
+    """The backward kernel REGENERATES the probability-dropout mask from (seed, position).  With Q = K = 0 every
+    probability is 1/T, so one-hot V rows read the forward mask off `out`, and one-hot dO rows read the backward mask
+    off dV: the two must be identical (and about half the entries must survive at p = 0.5, scaled by 2)."""
+    B, T, H = 2, 128, 2
+    Hd = H * 64
+    qkv = torch.zeros(B * T, 3 * Hd, device="cuda", dtype=torch.bfloat16)
+    eye = torch.eye(64, device="cuda", dtype=torch.bfloat16)
+    for b in range(B):
+        for h in range(H):
+            qkv[b * T:b * T + 64, 2 * Hd + h * 64:2 * Hd + (h + 1) * 64] = eye        # V rows of keys 0..63 are one-hot
+    lengths = torch.full((B,), T, device="cuda", dtype=torch.int32)
+    out, lse = ops.attention_fwd(qkv, lengths, B, T, H, 0.125, save_lse=True, drop_p=0.5, drop_seed=77)
+    fwd = out.float().view(B, T, H, 64) * T                     # [b, i, h, j<64] = 2 * keep(i, j)
+    assert set(fwd.unique().round().tolist()) <= {0.0, 2.0}
+    assert 0.45 < (fwd != 0).float().mean().item() < 0.55
+    dout = torch.zeros(B * T, Hd, device="cuda", dtype=torch.bfloat16)
+    for b in range(B):
+        for h in range(H):
+            dout[b * T:b * T + 64, h * 64:(h + 1) * 64] = eye                        # dO rows of queries 0..63 are one-hot
+    dqkv = ops.attention_bwd(qkv, lengths, out, dout, lse, B, T, H, 0.125, 0.5, 77)
+    dv = dqkv[:, 2 * Hd:].float().view(B, T, H, 64) * T          # [b, j, h, i<64] = 2 * keep(i, j)
+    bwd = dv.permute(0, 3, 2, 1)                                 # -> [b, i<64, h, j]
+    assert torch.equal(bwd[:, :, :, :64] != 0, fwd[:, :64] != 0)
+    assert 0.45 < (bwd != 0).float().mean().item() < 0.55
+    out2 = ops.attention_fwd(qkv, lengths, B, T, H, 0.125, drop_p=0.5, drop_seed=78)
+    assert not torch.equal(out2 != 0, out != 0)                  # another seed, another mask
+
+
 def test_attention_zero_length_row_is_nan_like_torch(ops):
     qkv = _bf(torch.randn(2 * 64, 3 * 64, device="cuda"))
     lengths = torch.tensor([64, 0], device="cuda", dtype=torch.int32)
