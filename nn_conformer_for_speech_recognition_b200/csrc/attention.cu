@@ -35,6 +35,13 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col, int rows) {
   return static_cast<uint32_t>(blk * rows * 128 + row * 128 + ((((cc >> 3) ^ (row & 7)) << 4) | ((cc & 7) << 1)));
 }
 
+// p = 0.5 (the reference's dropout): ONE hash decides 32 consecutive keys of a query row, one bit each -- instead of
+// one hash per 4 keys.  `row_lin` = (b*H + h)*T + q, `key32` = first key of the aligned 32-key group.  Forward and
+// backward both call this, so the masks agree (tests: attention dropout mask, forward == backward).
+__device__ __forceinline__ uint32_t drop_bits32(const DropCfg& d, uint64_t row_lin, int T, int key32) {
+  return drop_hash32(d.seed ^ 0x94D049BB133111EBull, row_lin * static_cast<uint64_t>((T + 31) >> 5) + static_cast<uint64_t>(key32 >> 5));
+}
+
 struct AttnParams {
   const int32_t* lengths;
   __nv_bfloat16* out;
@@ -241,7 +248,11 @@ __global__ void __launch_bounds__(256, REL ? 1 : 2) attn_fwd_kernel(const __grid
           l_blk += pr[i];
         }
       }
-      if (drop.thresh16) {
+      if (drop.thresh16 == 32768u) {
+        const uint32_t bits = drop_bits32(drop, static_cast<uint64_t>(b * p.H + h) * p.T + q_idx, p.T, key0 + c);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pr[i] *= (bits >> i) & 1u ? 2.f : 0.f;
+      } else if (drop.thresh16) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           float sc[4];
@@ -376,7 +387,7 @@ template <bool REL>
 __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint32_t tm_s, uint32_t tm_dp, uint8_t* sP,
                                                    uint8_t* sdS, int row, int cq, int key0, int len, float lse_r,
                                                    float delta_r, uint64_t drop_row, int64_t rel_row, int q_idx,
-                                                   uint64_t* bar_sfree) {
+                                                   uint64_t* bar_sfree, uint64_t row_lin) {
   const DropCfg drop = drop_resolve(p.drop);
   const float inv_keep8 = 256.f / (256.f - static_cast<float>(drop.thresh16 >> 8));
   const int c = cq * 32;
@@ -390,6 +401,8 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
   tc_fence_before();
   mbar_arrive(bar_sfree);
   const bool full = key0 + c + 32 <= len;
+  const bool half_p = drop.thresh16 == 32768u;
+  const uint32_t bits = half_p ? drop_bits32(drop, row_lin, p.T, key0 + c) : 0u;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float pr[8], ds[8];
@@ -404,7 +417,12 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
     for (int i4 = 0; i4 < 8; i4 += 4) {
       const int i = g * 8 + i4;
       float dsc[4] = {1.f, 1.f, 1.f, 1.f};
-      if (drop.thresh16) drop_scale4(drop, drop_row + key0 + c + i, inv_keep8, dsc);
+      if (half_p) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dsc[e] = (bits >> (i + e)) & 1u ? 2.f : 0.f;
+      } else if (drop.thresh16) {
+        drop_scale4(drop, drop_row + key0 + c + i, inv_keep8, dsc);
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if constexpr (REL) vs[i + e] = __float_as_uint(__uint_as_float(vs[i + e]) + bb[i4 + e]);
@@ -633,7 +651,7 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
       attn_bwd_tile_math<REL>(p, tm_lane + TM_S, tm_lane + TM_DP, smem + OFF_P + bf * 32768, smem + OFF_DS + bf * 32768, row,
                               cq, key0, len, lse_r, delta_r, (static_cast<uint64_t>(b * p.H + h) * p.T + q_idx) * p.Tpad,
                               (REL && q_idx < p.T) ? (static_cast<int64_t>(row_base + q_idx) * p.H + h) * p.Rp : -1, q_idx,
-                              bar_sfree);
+                              bar_sfree, static_cast<uint64_t>(b * p.H + h) * p.T + q_idx);
       B2C_TM(i, 2)
       if (i > 0) drain_dq(i - 1);            // block i-1's products ran underneath this block's tile math
       B2C_TM(i, 3)
