@@ -144,8 +144,53 @@ __global__ void __launch_bounds__(AF_THREADS) adafactor_update_kernel(const AfTe
     scale = lr / fmaxf(1.f, rms / clip);
   }
   float ss = 0.f;
-  // (row, col) of this thread's element advance incrementally: no per-element 64-bit division
   const int icnt = static_cast<int>(cnt);
+  // 16-byte path: four elements of one row per thread and step (every large tensor has C % 4 == 0 and 16-byte aligned
+  // slices); the scalar loop below remains for the small odd-shaped ones
+  const bool vec = (C & 3) == 0 && ((reinterpret_cast<uintptr_t>(T.g + e0) | reinterpret_cast<uintptr_t>(T.p + e0) |
+                                     reinterpret_cast<uintptr_t>(T.m + e0)) & 15) == 0 &&
+                   (T.factored ? (reinterpret_cast<uintptr_t>(T.col) & 15) == 0 : (reinterpret_cast<uintptr_t>(T.row + e0) & 15) == 0);
+  if (vec) {
+    const int step = AF_THREADS * 4;
+    const int vstep_r = step / C, vstep_c = step % C;
+    int vr = static_cast<int>(threadIdx.x * 4) / C, vc = static_cast<int>(threadIdx.x * 4) % C;
+    for (int i = threadIdx.x * 4; i < icnt; i += step) {
+      const int64_t e = e0 + i;
+      const float4 g4 = *reinterpret_cast<const float4*>(T.g + e);
+      float u[4];
+      if (T.factored) {
+        const int row = ck.row0 + vr;
+        const int pslab = R == 1 ? row : row / R;
+        const float rs = rsqrtf(T.row[row] / T.rmean[pslab]);
+        const float4 c4 = *reinterpret_cast<const float4*>(T.col + static_cast<int64_t>(pslab) * C + vc);
+        u[0] = g4.x * rs * rsqrtf(c4.x); u[1] = g4.y * rs * rsqrtf(c4.y);
+        u[2] = g4.z * rs * rsqrtf(c4.z); u[3] = g4.w * rs * rsqrtf(c4.w);
+      } else {
+        float4 v4 = *reinterpret_cast<const float4*>(T.row + e);
+        if (!APPLY) {                                // second moment is updated once, in the first pass
+          v4.x = beta2t * v4.x + (1.f - beta2t) * (g4.x * g4.x + eps1); v4.y = beta2t * v4.y + (1.f - beta2t) * (g4.y * g4.y + eps1);
+          v4.z = beta2t * v4.z + (1.f - beta2t) * (g4.z * g4.z + eps1); v4.w = beta2t * v4.w + (1.f - beta2t) * (g4.w * g4.w + eps1);
+          *reinterpret_cast<float4*>(T.row + e) = v4;
+        }
+        u[0] = g4.x * rsqrtf(v4.x); u[1] = g4.y * rsqrtf(v4.y); u[2] = g4.z * rsqrtf(v4.z); u[3] = g4.w * rsqrtf(v4.w);
+      }
+      if (APPLY) {
+        float4 m4 = *reinterpret_cast<const float4*>(T.m + e);
+        float4 p4 = *reinterpret_cast<const float4*>(T.p + e);
+        m4.x = beta1 * m4.x + (1.f - beta1) * (scale * u[0]); m4.y = beta1 * m4.y + (1.f - beta1) * (scale * u[1]);
+        m4.z = beta1 * m4.z + (1.f - beta1) * (scale * u[2]); m4.w = beta1 * m4.w + (1.f - beta1) * (scale * u[3]);
+        p4.x -= m4.x; p4.y -= m4.y; p4.z -= m4.z; p4.w -= m4.w;
+        *reinterpret_cast<float4*>(T.m + e) = m4;
+        *reinterpret_cast<float4*>(T.p + e) = p4;
+      } else {
+        ss += u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3];
+      }
+      vr += vstep_r; vc += vstep_c;
+      if (vc >= C) { vc -= C; ++vr; }
+    }
+  }
+  // (row, col) of this thread's element advance incrementally: no per-element 64-bit division
+  if (!vec) {
   const int step_r = AF_THREADS / C, step_c = AF_THREADS % C;
   int rr = static_cast<int>(threadIdx.x) / C, c = static_cast<int>(threadIdx.x) % C;
   for (int i = threadIdx.x; i < icnt; i += AF_THREADS) {
@@ -173,6 +218,7 @@ __global__ void __launch_bounds__(AF_THREADS) adafactor_update_kernel(const AfTe
     }
     rr += step_r; c += step_c;
     if (c >= C) { c -= C; ++rr; }
+  }
   }
   if (!APPLY) {
     __shared__ float red[AF_THREADS / 32];
