@@ -14,10 +14,12 @@
 // Key blocks past lengths[b] are skipped entirely.  80 KB smem and 256 TMEM columns per CTA -> 2 CTAs per SM, so
 // one CTA's softmax overlaps the other's MMAs/TMA.
 //
-// Backward = two kernels that recompute S/P from the saved log-sum-exp (no T x T tensor ever reaches HBM):
-//   attn_bwd_dkv : CTA = (key block, head, utterance), loops over query blocks: dV += P^T dO, dK += dS^T Q
-//   attn_bwd_dq  : CTA = (query block, head, utterance), loops over key blocks:   dQ += dS K
-// with dS = P o (dP - delta) * scale, dP = dO V^T, delta = rowsum(dO o O) (attn_delta kernel).
+// Backward = attn_delta (delta = rowsum(dO o O)) + ONE kernel that recomputes S/P from the saved log-sum-exp (no
+// T x T tensor ever reaches HBM): CTA = (key block, head, utterance) loops over query blocks,
+//   dV += P^T dO, dK += dS^T Q accumulate in TMEM, dQ partials = dS K go to a per-key-block fp32 slab that
+//   attn_dq_cast sums, with dS = P o (dP - delta) * scale and dP = dO V^T.  See attn_bwd_kernel below.
+// The relative-position variant (REL) adds the shifted (q+v) Pw^T bias: fused in the forward, read back from a
+// materialised bias in the backward.
 #include "common.cuh"
 #include "b200conformer.h"
 

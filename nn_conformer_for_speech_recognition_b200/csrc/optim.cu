@@ -41,7 +41,53 @@ __global__ void __launch_bounds__(AF_THREADS) adafactor_stats_kernel(const AfTen
   const AfTensor T = tensors[ck.t];
   if (!T.factored) return;
   const int C = T.C, R = T.R;
-  if (C >= 32) {
+  const float* gbase = T.g + static_cast<int64_t>(ck.row0) * C;
+  if ((C & 127) == 0 && C <= 4 * AF_THREADS && (reinterpret_cast<uintptr_t>(gbase) & 15) == 0 &&
+      ck.row0 / R == (ck.row0 + ck.nrows - 1) / R) {
+    // the linear weights (C = 256 / 1024, one slab per chunk): ONE pass over g with 16-byte loads.  A thread owns four
+    // adjacent columns of every RPI-th row; a row's C/4 threads are whole warps, so the row sum is a shuffle reduction
+    // plus one atomic per warp (rowsum is zeroed with the rest of the workspace), the column sums stay in registers.
+    const int tid = threadIdx.x;
+    const int G = C >> 2, RPI = AF_THREADS / G;
+    const int tr = tid / G, tc = tid - tr * G;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tr < RPI) {
+      const float4* gp = reinterpret_cast<const float4*>(gbase) + tc;
+      const bool lane0 = (tid & 31) == 0;
+      constexpr int UN = 4;
+      for (int r = tr; r < ck.nrows; r += UN * RPI) {
+        float4 v[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int ru = r + u * RPI;
+          v[u] = ru < ck.nrows ? gp[static_cast<int64_t>(ru) * G] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int ru = r + u * RPI;
+          if (ru < ck.nrows) {                          // uniform over the warp
+            const float sx = fmaf(v[u].x, v[u].x, eps1), sy = fmaf(v[u].y, v[u].y, eps1);
+            const float sz = fmaf(v[u].z, v[u].z, eps1), sw = fmaf(v[u].w, v[u].w, eps1);
+            acc.x += sx; acc.y += sy; acc.z += sz; acc.w += sw;
+            const float rs = warp_sum((sx + sy) + (sz + sw));
+            if (lane0) atomicAdd(T.rowsum + ck.row0 + ru, rs);
+          }
+        }
+      }
+    }
+    __shared__ float4 cs[AF_THREADS];
+    cs[tid] = acc;
+    __syncthreads();
+    if (tid < G) {
+      float4 t = cs[tid];
+      for (int k = 1; k < RPI; ++k) {
+        const float4 o = cs[tid + k * G];
+        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+      }
+      float* dst = T.colsum + static_cast<int64_t>(ck.row0 / R) * C + 4 * tid;
+      atomicAdd(dst, t.x); atomicAdd(dst + 1, t.y); atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w);
+    }
+  } else if (C >= 32) {
     // wide rows: warp w takes rows w, w+8, ...; lanes stride the columns.  Row sums by warp shuffle; column sums are
     // kept per (warp, column) in registers only for C <= 32*8*... -> simpler: per-element atomics on the column sums
     // are avoided by letting each THREAD own columns c = tid, tid+256, ... across all rows of the chunk.
@@ -74,18 +120,30 @@ __global__ void __launch_bounds__(AF_THREADS) adafactor_stats_kernel(const AfTen
       if (lane == 0) T.rowsum[row] = acc;           // a row belongs to exactly one chunk: plain store
     }
   } else {
-    // narrow rows (conv kernels, C = 3..31): one thread per row
-    for (int r = threadIdx.x; r < ck.nrows; r += AF_THREADS) {
-      const int row = ck.row0 + r;
+    // narrow rows (conv kernels, C = 1..31): one thread per row.  When the 32 rows of a warp lie in one slab (pointwise
+    // convs: 256 rows of one column) the column sums are reduced in the warp first -- one atomic per warp instead of 32
+    // on the same address.
+    const int lane = threadIdx.x & 31;
+    for (int r0 = 0; r0 < ck.nrows; r0 += AF_THREADS) {
+      const int r = r0 + static_cast<int>(threadIdx.x);
+      const bool ok = r < ck.nrows;
+      const int row = ck.row0 + (ok ? r : ck.nrows - 1);
       const int pslab = row / R;
+      const int p0 = __shfl_sync(0xffffffffu, pslab, 0);
+      const bool uni = __all_sync(0xffffffffu, pslab == p0);
       float acc = 0.f;
       for (int c = 0; c < C; ++c) {
         const float gv = T.g[static_cast<int64_t>(row) * C + c];
-        const float s = gv * gv + eps1;
+        const float s = ok ? gv * gv + eps1 : 0.f;
         acc += s;
-        atomicAdd(T.colsum + static_cast<int64_t>(pslab) * C + c, s);
+        if (uni) {
+          const float t = warp_sum(s);
+          if (lane == 0) atomicAdd(T.colsum + static_cast<int64_t>(p0) * C + c, t);
+        } else if (ok) {
+          atomicAdd(T.colsum + static_cast<int64_t>(pslab) * C + c, s);
+        }
       }
-      T.rowsum[row] = acc;
+      if (ok) T.rowsum[row] = acc;
     }
   }
 }
@@ -112,6 +170,19 @@ __global__ void __launch_bounds__(AF_THREADS) adafactor_factors_kernel(const AfT
   const int64_t gstride = static_cast<int64_t>(gridDim.x) * AF_THREADS;
   for (int64_t i = gtid; i < static_cast<int64_t>(P) * C; i += gstride)
     T.col[i] = beta2t * T.col[i] + om * (T.colsum[i] / R);
+  if (R <= 8) {                                        // stacks of tiny slabs (3x3 / 7x7 conv kernels): a thread per slab
+    for (int64_t pslab = gtid; pslab < P; pslab += gstride) {
+      float acc = 0.f;
+      for (int r = 0; r < R; ++r) {
+        const int64_t i = pslab * R + r;
+        const float v = beta2t * T.row[i] + om * (T.rowsum[i] / C);
+        T.row[i] = v;
+        acc += v;
+      }
+      T.rmean[pslab] = acc / R;
+    }
+    return;
+  }
   const int lane = threadIdx.x & 31;
   const int64_t gwarp = gtid >> 5, nwarps = gstride >> 5;
   for (int64_t pslab = gwarp; pslab < P; pslab += nwarps) {

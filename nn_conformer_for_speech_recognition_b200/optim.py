@@ -19,6 +19,7 @@ _TENSOR_DT = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("row", "<u8"),
 _CHUNK_DT = np.dtype([("t", "<i4"), ("row0", "<i4"), ("nrows", "<i4"), ("pad", "<i4")])
 assert _TENSOR_DT.itemsize == 96 and _CHUNK_DT.itemsize == 16
 _CHUNK_ELEMS = 16384
+_CHUNK_ELEMS_NARROW = 2048      # rows shorter than a warp run one thread per row: keep the per-thread loops short
 
 
 class Adafactor:
@@ -76,7 +77,7 @@ class Adafactor:
             ocol += al(P * C) if f else 0
             ows += al(P * R) + al(P * C) + al(P) + 4
             rows = P * R
-            per = max(1, _CHUNK_ELEMS // C)
+            per = max(1, (_CHUNK_ELEMS if C >= 32 else _CHUNK_ELEMS_NARROW) // C)
             for r0 in range(0, rows, per):
                 chunks.append((i, r0, min(per, rows - r0), 0))
         self._tab_host = torch.from_numpy(tab.view(np.uint8).reshape(-1)).pin_memory()

@@ -397,7 +397,7 @@ def test_fused_adafactor_matches_hf():
     from nn_conformer_for_speech_recognition_b200.optim import Adafactor
     torch.manual_seed(0)
     shapes = [(256,), (1024, 256), (256, 1024), (512, 256, 1), (256, 1, 31), (512, 1, 7, 7), (128, 64, 3, 3), (144,),
-              (256, 2304), (3, 5)]
+              (256, 2304), (3, 5), (4, 8, 128), (2, 256, 128), (70, 384)]
     ours = [torch.nn.Parameter(torch.randn(s, device="cuda") * 0.1) for s in shapes]
     ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
     o1 = Adafactor(ours, lr=2e-5, beta1=0.9)
@@ -409,8 +409,6 @@ def test_fused_adafactor_matches_hf():
         o1.step()
         o2.step()
         for i, (a, b_) in enumerate(zip(ours, ref)):
-            upd_ref = (b_.detach() - (a.detach() * 0 + b_.detach())).abs().max()     # placeholder to keep shapes in scope
-            del upd_ref
             err = (a.detach() - b_.detach()).abs().max().item()
             assert err <= 2e-7 + 1e-3 * 2e-5, f"step {step} tensor {shapes[i]}: |dp| {err:.3e}"
     for i, b_ in enumerate(ref):
