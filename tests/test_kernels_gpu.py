@@ -450,6 +450,25 @@ def test_gemm_half_width_tail_tiles(ops, M, N, K):
     _close(cs, want_du.sum(0), rel=5e-3, abs_=0.5, name="tail colsum")
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(300, 144, 576, 256), (300, 144, 576, 128), (1000, 1000, 256, 256), (1000, 1000, 256, 128),
+                                      (33, 40, 64, 128), (4100, 520, 128, 0), (23872, 1024, 256, 2256)])
+def test_gemm_silu_backward_row_domain_ragged(ops, M, N, K, bn):
+    """SiLU-backward dgrad whose saved pre-activation arrives as TMA boxes one chunk ahead: shapes where some of a
+    warp's 32-column chunks lie past N (their loads / waits are skipped, buffer parities must stay in step), rows past
+    M, the 1/keep factor and the fused bias gradient.  A strided aux (a column slice of a wider buffer) as well."""
+    g = torch.Generator(device="cuda").manual_seed(M * 3 + N)
+    dy = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(K, N, device="cuda", generator=g) / math.sqrt(K))
+    wide = _bf(torch.randn(M, N + 24, device="cuda", generator=g))
+    u = wide[:, 8:8 + N]                                       # pitch N + 24 elements, 16-byte aligned start
+    cs = torch.zeros(N, device="cuda")
+    out = ops.gemm(dy, w, M=M, N=N, K=K, b_mn=True, act=ops.ACT_SILU_BWD, aux=u, alpha=2.0, colsum=cs, block_n=bn)
+    s = torch.sigmoid(u.float())
+    want = 2.0 * (dy.float() @ w.float()) * (s * (1 + u.float() * (1 - s)))
+    _close(out, want, name="silu bwd ragged")
+    _close(cs, want.sum(0), rel=5e-3, abs_=0.5, name="silu bwd ragged colsum")
+
+
 # ----------------------------------------------------------------------------------------------- GEMM, CTA pairs
 @pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, -256), (512, 512, 256, -256), (1000, 1024, 256, -256),
                                       (777, 768, 320, -256), (300, 144, 144, -128), (23872, 256, 1024, -256),
