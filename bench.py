@@ -234,6 +234,14 @@ def main():
     ap.add_argument("--no-instrument", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    # stdout carries exactly ONE JSON line: anything native libraries write to fd 1 (NCCL prints its version banner
+    # there when NCCL_DEBUG is set) is routed to stderr, and the line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     cfg = CONFIGS[args.model]
     T = int(round(args.seconds * 100))
@@ -255,7 +263,7 @@ def main():
                     config=dict(workload=workload, ref_sample=base["sample"]), cpu_baseline=base,
                     e2e=dict(value=base["value"], unit="audio-s/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     gpu_launches=0)
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -500,7 +508,7 @@ def main():
             except Exception as e:      # the baseline is reported, never required for our arm
                 line["cpu_baseline"] = dict(value=None, unit="audio-s/s", cores=os.cpu_count(), kind="port",
                                             sample=f"failed: {type(e).__name__}: {e}")
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
