@@ -13,6 +13,7 @@ from ._lib import B2CError  # noqa: F401
 from .conformer import Conformer, ConformerLayer  # noqa: F401
 from .convsubsampling import ConvSubSampling  # noqa: F401
 from .encoder import ConformerEncoder, Linear  # noqa: F401
+from .prefetch import HostPrefetcher  # noqa: F401
 from .patch import conformer_from_torchaudio, convsub_from_reference, patch_asrnn  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,67 @@
+"""Host -> device input pipeline: the next batch crosses PCIe on a copy stream while the current step computes.
+
+The reference feeds its model straight from the DataLoader (`/root/reference/lib/standard/runner.py:140-146`:
+`x = x.to(device)` in front of every step, so the copy and the step serialise).  A 64 x 15 s batch of 80-bin features is
+30.7 MB = ~0.55 ms of PCIe time against a 16.7 ms training step (3 %) or a 3.9 ms inference batch (14 %): worth hiding.
+
+    pre = HostPrefetcher(x_host.shape, device)
+    pre.submit(x_host)                 # pinned host tensor
+    for ...:
+        x = pre.get()                  # device tensor; the current stream waits for its copy
+        pre.submit(next_host_batch)    # overlaps the step launched below
+        step(x)
+
+Two device buffers alternate.  A buffer is refilled only after the work that was enqueued on the consumer stream up to
+the NEXT `get()` has finished with it (event recorded there), so `x` stays valid until the second `get()` after it.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class HostPrefetcher:
+    def __init__(self, shape, device, dtype=torch.float32, depth: int = 2):
+        if torch.device(device).type != "cuda":
+            raise ValueError("HostPrefetcher needs a CUDA device (there is no CPU fallback)")
+        if depth < 2:
+            raise ValueError("depth must be >= 2 (one buffer in use, one in flight)")
+        self.bufs = [torch.empty(shape, device=device, dtype=dtype) for _ in range(depth)]
+        self.stream = torch.cuda.Stream(device=device)
+        self.ready = [torch.cuda.Event() for _ in range(depth)]        # copy into buffer i finished
+        self.free = [None] * depth                                     # consumer finished with buffer i
+        self.head = 0                                                  # next buffer to fill
+        self.tail = 0                                                  # next buffer to hand out
+        self.in_flight = 0
+        self.last = None                                               # buffer handed out by the previous get()
+
+    def submit(self, host: torch.Tensor) -> None:
+        """Start copying `host` (pinned memory for a truly asynchronous copy) into the next free device buffer."""
+        if self.in_flight >= len(self.bufs) - (1 if self.last is not None else 0):
+            raise RuntimeError("HostPrefetcher: every buffer is in use; call get() before submitting more")
+        if host.shape != self.bufs[0].shape or host.dtype != self.bufs[0].dtype:
+            raise ValueError(f"HostPrefetcher: expected {tuple(self.bufs[0].shape)} {self.bufs[0].dtype}, "
+                             f"got {tuple(host.shape)} {host.dtype}")
+        i = self.head
+        if self.free[i] is not None:
+            self.stream.wait_event(self.free[i])
+        with torch.cuda.stream(self.stream):
+            self.bufs[i].copy_(host, non_blocking=True)
+            self.ready[i].record(self.stream)
+        self.head = (i + 1) % len(self.bufs)
+        self.in_flight += 1
+
+    def get(self) -> torch.Tensor:
+        """Oldest submitted batch as a device tensor; the current stream waits for its copy."""
+        if self.in_flight == 0:
+            raise RuntimeError("HostPrefetcher: get() without a submitted batch")
+        cur = torch.cuda.current_stream(self.bufs[0].device)
+        if self.last is not None:                   # everything enqueued so far may have read the previous buffer
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.free[self.last] = ev
+        i = self.tail
+        cur.wait_event(self.ready[i])
+        self.tail = (i + 1) % len(self.bufs)
+        self.in_flight -= 1
+        self.last = i
+        return self.bufs[i]
