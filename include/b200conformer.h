@@ -28,10 +28,26 @@ enum { B2C_ACT_NONE = 0, B2C_ACT_SILU = 1, B2C_ACT_SILU_BWD = 2 };
 
 const char* b2c_last_error(void);
 int b2c_version(void);
-/* Dropout masks are a pure function of (seed, element index, epoch).  The epoch is a device-side counter this call
- * increments (one tiny launch): call it once at the start of every training step -- forward and backward of the step
- * then regenerate identical masks, and a replayed CUDA graph still draws fresh masks each step. */
+/* Dropout (torchaudio conformer.py:74,106,108,152,153; asrnn.py:210).  Masks are a pure function of
+ * (seed, element index, epoch word); the epoch word is read by the KERNELS, so a replayed CUDA graph still draws fresh
+ * masks each step.  There is one step counter per device:
+ *   _bump      counter += 1                                  (one tiny launch)
+ *   _snapshot  counter += 1; *dst = counter                  dst = a device word owned by ONE training forward call
+ *   _set       counter = value                               (tests: makes mask sequences reproducible)
+ *   _use       host-side, thread-local: kernels launched by this thread from now on read `epoch_word` instead of the
+ *              device counter (NULL restores the counter).  A forward installs its snapshot for its own launches and
+ *              its backward installs the same word again, so interleaved forward/backward pairs regenerate the masks
+ *              each forward really used.
+ *   _export_mask  debug: out fp32 [rows, cols] = the scale (0 or 1/keep) the kernels apply at a site with this
+ *              (drop_p, drop_seed) under the currently installed epoch word.  kind 0: elementwise sites (GEMM residual
+ *              epilogues, b2c_scale_cast, b2c_layernorm_bwd_cast; element index = r*cols + c).  kind 1: attention
+ *              probabilities, rows = (b*H + h)*T + q, cols = T keys. */
 int b2c_dropout_epoch_bump(void* stream);
+int b2c_dropout_epoch_snapshot(uint64_t* dst, void* stream);
+int b2c_dropout_epoch_set(uint64_t value, void* stream);
+int b2c_dropout_epoch_use(const uint64_t* epoch_word);
+int b2c_dropout_export_mask(int kind, float drop_p, uint64_t drop_seed, int64_t rows, int64_t cols, float* out,
+                            void* stream);
 /* fails (returns <0) unless the current CUDA device is compute capability 10.x -- there is no fallback path */
 int b2c_device_check(void);
 

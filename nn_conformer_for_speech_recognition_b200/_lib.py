@@ -68,6 +68,10 @@ SIGNATURES = {
     "b2c_specaug_apply": [_P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _F, _I, _I, _I, _P],
     "b2c_adafactor_step": [_P, _I, _P, _I, _P, _P, _F, _F, _F, _F, _F, _P],
     "b2c_dropout_epoch_bump": [_P],
+    "b2c_dropout_epoch_snapshot": [_P, _P],
+    "b2c_dropout_epoch_set": [c_uint64, _P],
+    "b2c_dropout_epoch_use": [_P],
+    "b2c_dropout_export_mask": [_I, _F, c_uint64, _L, _L, _P, _P],
     "b2c_cast_f32_bf16": [_P, _P, _L, _P],
     "b2c_multi_cast_f32_bf16": [_P, _I, _L, _P],
     "b2c_scale_cast": [_P, _P, _L, _L, _F, _F, c_uint64, _P, _P],
@@ -84,7 +88,7 @@ HOST_SIGNATURES = {
 
 _lib = None
 LAUNCHES = 0          # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 2, "b2c_convsub_compose_bwd": 2, "b2c_attention_bwd": 4, "b2c_attention_rel_bwd": 4, "b2c_conformer_layer_eval": 20, "b2c_adafactor_step": 5, "b2c_version": 0, "b2c_device_check": 0}
+_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 2, "b2c_convsub_compose_bwd": 2, "b2c_attention_bwd": 4, "b2c_attention_rel_bwd": 4, "b2c_conformer_layer_eval": 20, "b2c_adafactor_step": 5, "b2c_version": 0, "b2c_device_check": 0, "b2c_dropout_epoch_use": 0}
 
 
 def load() -> ctypes.CDLL:
@@ -211,3 +215,33 @@ def require_device() -> None:
 
 def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
+
+
+class epoch_scope:
+    """`with epoch_scope(word):` -- kernels launched inside read the dropout epoch from `word` (a 1-element int64 device
+    tensor written by b2c_dropout_epoch_snapshot) instead of the device counter.  None = no-op."""
+
+    current = None                       # innermost installed word (scopes nest; single-threaded launch path)
+
+    def __init__(self, word):
+        self.word = word
+
+    def __enter__(self):
+        if self.word is not None:
+            self.prev = epoch_scope.current
+            epoch_scope.current = self.word
+            load().b2c_dropout_epoch_use(self.word.data_ptr())
+        return self
+
+    def __exit__(self, *exc):
+        if self.word is not None:
+            epoch_scope.current = self.prev
+            load().b2c_dropout_epoch_use(None if self.prev is None else self.prev.data_ptr())
+        return False
+
+
+def epoch_snapshot(device):
+    """New per-call epoch word: bumps the device's step counter and copies it (one capturable launch)."""
+    word = torch.empty(1, device=device, dtype=torch.int64)
+    call("b2c_dropout_epoch_snapshot", word.data_ptr(), stream_ptr())
+    return word

@@ -24,11 +24,15 @@ def conformer_apply(model: Conformer, inp: torch.Tensor, lengths_i32: torch.Tens
     params = [_get(layer, n) for layer in model.conformer_layers for n in model.layer_params]
     need_grad = torch.is_grad_enabled() and (inp.requires_grad or any(p.requires_grad for p in params))
     drop_p = model.dropout_p if model.training else 0.0
-    if drop_p > 0.0:            # one device-side tick per training forward: fresh masks even when a CUDA graph replays
-        _lib.call("b2c_dropout_epoch_bump", _lib.stream_ptr())
     if not need_grad:
         x = inp.detach().reshape(B * T, d).to(torch.float32).clone(memory_format=torch.contiguous_format)
-        y = run_layers(model, x, lengths_i32, B, T, None, model.training, drop_p, model.next_seed())
+        if drop_p > 0.0:
+            # train mode without autograd (torch.no_grad(): MC-dropout, noisy-student inference): torchaudio still applies
+            # dropout there, so run the dropout-enabled pipeline and drop what it saves for a backward pass
+            with _lib.epoch_scope(_lib.epoch_snapshot(inp.device)):
+                y = run_layers(model, x, lengths_i32, B, T, [], True, drop_p, model.next_seed())
+        else:
+            y = run_layers(model, x, lengths_i32, B, T, None, model.training, 0.0, model.next_seed())
         return y.view(B, T, d)
     return _ConformerFn.apply(inp, lengths_i32, model, *params)
 
@@ -60,9 +64,16 @@ class _ConformerFn(torch.autograd.Function):
         state: List[dict] = []
         drop_p = model.dropout_p if model.training else 0.0
         seed = model.next_seed()
+        # one epoch word per CALL (device step counter + 1, copied by a capturable launch): forward and backward of this
+        # call read the same word even when other training forwards run in between (advisor finding, round 1)
+        ctx.epoch = _lib.epoch_snapshot(inp.device) if drop_p > 0.0 else None
         # gradients are wanted: always run the two-pass conv-module chain so `y` exists for the backward pass
-        y = run_layers(model, x, lengths_i32, B, T, state, model.training, drop_p, seed, force_two_pass=True)
+        with _lib.epoch_scope(ctx.epoch):
+            y = run_layers(model, x, lengths_i32, B, T, state, model.training, drop_p, seed, force_two_pass=True)
         ctx.model, ctx.state, ctx.lengths = model, state, lengths_i32
+        if getattr(model, "_debug_keep_state", False):          # tests: saved activations / seed / epoch of this call
+            model._debug_state = dict(state=list(state), seed=seed, epoch=ctx.epoch, drop_p=drop_p)
+        ctx.weights = model._cache.bf16          # the operands this forward used (static buffers; no re-cast in backward)
         ctx.dims = (B, T, d)
         ctx.drop_p, ctx.seed = drop_p, seed
         ctx.in_dtype = inp.dtype
@@ -70,6 +81,11 @@ class _ConformerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        with _lib.epoch_scope(ctx.epoch):
+            return _ConformerFn._backward(ctx, dy)
+
+    @staticmethod
+    def _backward(ctx, dy):
         model: Conformer = ctx.model
         B, T, d = ctx.dims
         M = B * T
@@ -79,7 +95,7 @@ class _ConformerFn(torch.autograd.Function):
         scale = 1.0 / math.sqrt(dh)
         drop_p, seed = ctx.drop_p, ctx.seed
         keep_scale = float(_lib.load().b2c_dropout_keep_scale(drop_p)) if drop_p > 0 else 1.0
-        weights = model._cache.get()
+        weights = ctx.weights
         dev = dy.device
         dx = dy.reshape(M, d).to(torch.float32).contiguous()
         if dx.data_ptr() == dy.data_ptr():

@@ -130,56 +130,109 @@ def _get(module: nn.Module, dotted: str) -> torch.Tensor:
 
 
 class _WeightCache:
-    """bf16 copies of the GEMM weights (one multi-tensor cast launch), refreshed when a Parameter changes."""
+    """bf16 copies of the GEMM weights in STATIC device buffers, refreshed IN PLACE by one multi-tensor cast launch.
+
+    Refresh policy: eagerly, when a Parameter's version changed since the last refresh; ALWAYS while the current stream
+    is being captured into a CUDA graph -- the refresh kernels are then part of the graph, so every replay re-derives the
+    bf16 operands from the fp32 masters the optimizer has just updated (no Python runs at replay time, a host-side
+    version check cannot)."""
 
     def __init__(self, owner: "Conformer"):
         self.owner = owner
         self.key = None
+        self.ptrs = None
         self.bf16: List[dict] = []
         self.table = None
         self.max_n = 0
+        self.stage: List[dict] = []       # padded fp32 staging buffers (head_dim < 64 / rel_att only)
+
+    def _names(self):
+        return _BF16_WEIGHTS + ["self_attn.in_proj_bias"] + (_REL_PARAMS if self.owner.rel_att else [])
 
     def _signature(self):
         sig = []
         for layer in self.owner.conformer_layers:
-            for name in _BF16_WEIGHTS + ["self_attn.in_proj_bias"] + (_REL_PARAMS if self.owner.rel_att else []):
+            for name in self._names():
                 p = _get(layer, name)
                 sig.append((p.data_ptr(), p._version))
         return tuple(sig)
 
+    @property
+    def padded(self) -> bool:
+        return self.owner.head_dim != HEAD_PAD or self.owner.rel_att
+
+    def _allocate(self, dev):
+        """(Re)build the static buffers and the cast table; runs when the parameters' storage moved (.to(), first use)."""
+        o = self.owner
+        H, d = o.num_heads, o.input_dim
+        nslab = 4 if o.rel_att else 3
+        self.bf16, self.stage, entries = [], [], []
+        bf = torch.bfloat16
+        for layer in o.conformer_layers:
+            out, stg = {}, {}
+            for name in _BF16_WEIGHTS + (["self_attn.linear_pos.weight"] if o.rel_att else []):
+                p = _get(layer, name)
+                src = p
+                if self.padded and name == "self_attn.in_proj_weight":
+                    # heads zero-padded to 64; rel_att: a 4th slab repeats W_q -- the GEMM then emits [q+u | k | v | q+v]
+                    src = stg[name] = torch.zeros(nslab * H * HEAD_PAD, d, device=dev, dtype=torch.float32)
+                elif self.padded and name == "self_attn.out_proj.weight":
+                    src = stg[name] = torch.zeros(d, H * HEAD_PAD, device=dev, dtype=torch.float32)
+                elif name == "self_attn.linear_pos.weight":
+                    src = stg[name] = torch.zeros(H * HEAD_PAD, d, device=dev, dtype=torch.float32)
+                t = torch.empty(src.shape[:2] if src.dim() == 3 else src.shape, device=dev, dtype=bf)
+                out[name] = t
+                entries.append((src.data_ptr(), t.data_ptr(), src.numel()))
+            if self.padded:
+                out["in_bias"] = stg["in_bias"] = torch.zeros(nslab * H * HEAD_PAD, device=dev, dtype=torch.float32)
+            else:
+                out["in_bias"] = _get(layer, "self_attn.in_proj_bias")
+            self.bf16.append(out)
+            self.stage.append(stg)
+        self.table = torch.tensor([v for e in entries for v in e], dtype=torch.int64).to(dev)
+        self.ntab = len(entries)
+        self.max_n = max(e[2] for e in entries)
+        self._structs = None
+
+    def _refresh(self):
+        """fp32 masters -> bf16 operands, in place (capturable: device-side copies and ONE multi-tensor cast launch)."""
+        o = self.owner
+        if self.padded:
+            H, dh, d = o.num_heads, o.head_dim, o.input_dim
+            nslab = 4 if o.rel_att else 3
+            with torch.no_grad():
+                for layer, stg in zip(o.conformer_layers, self.stage):
+                    w = stg["self_attn.in_proj_weight"].view(nslab, H, HEAD_PAD, d)
+                    w[:3, :, :dh].copy_(_get(layer, "self_attn.in_proj_weight").view(3, H, dh, d))
+                    stg["self_attn.out_proj.weight"].view(d, H, HEAD_PAD)[:, :, :dh].copy_(
+                        _get(layer, "self_attn.out_proj.weight").view(d, H, dh))
+                    b = stg["in_bias"].view(nslab, H, HEAD_PAD)
+                    b[:3, :, :dh].copy_(_get(layer, "self_attn.in_proj_bias").view(3, H, dh))
+                    if o.rel_att:
+                        w[3].copy_(w[0])
+                        b[3].copy_(b[0])
+                        b[0, :, :dh].add_(_get(layer, "self_attn.pos_bias_u"))
+                        b[3, :, :dh].add_(_get(layer, "self_attn.pos_bias_v"))
+                        stg["self_attn.linear_pos.weight"].view(H, HEAD_PAD, d)[:, :dh].copy_(
+                            _get(layer, "self_attn.linear_pos.weight").view(H, dh, d))
+        _lib.call("b2c_multi_cast_f32_bf16", self.table.data_ptr(), self.ntab, self.max_n, _lib.stream_ptr())
+
     def get(self) -> List[dict]:
         sig = self._signature()
-        if sig == self.key:
-            return self.bf16
-        o = self.owner
-        dev = next(o.parameters()).device
-        if o.head_dim != HEAD_PAD or o.rel_att:
-            self._build_padded(dev)
-        else:
-            rebuild = self.table is None or [s[0] for s in sig] != [s[0] for s in (self.key or ())]
-            if rebuild:
-                self.bf16, entries = [], []
-                for layer in o.conformer_layers:
-                    d = {}
-                    for name in _BF16_WEIGHTS:
-                        p = _get(layer, name)
-                        t = torch.empty(p.shape[:2] if p.dim() == 3 else p.shape, device=dev, dtype=torch.bfloat16)
-                        d[name] = t
-                        entries.append((p.data_ptr(), t.data_ptr(), p.numel()))
-                    d["in_bias"] = _get(layer, "self_attn.in_proj_bias")
-                    self.bf16.append(d)
-                flat = torch.tensor([v for e in entries for v in e], dtype=torch.int64)
-                self.table = flat.to(dev)
-                self.ntab = len(entries)
-                self.max_n = max(e[2] for e in entries)
-            _lib.call("b2c_multi_cast_f32_bf16", self.table.data_ptr(), self.ntab, self.max_n, _lib.stream_ptr())
-        self.key = sig
+        ptrs = tuple(s[0] for s in sig)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if ptrs != self.ptrs:
+            self._allocate(next(self.owner.parameters()).device)
+            self.ptrs, self.key = ptrs, None
+        if capturing or sig != self.key:
+            self._refresh()
+            self.key = sig
         return self.bf16
 
     def layer_structs(self):
-        """ctypes `b2c_layer_weights` per layer for the one-call-per-layer eval path (rebuilt with the bf16 copies)."""
+        """ctypes `b2c_layer_weights` per layer for the one-call-per-layer eval path (pointers are static)."""
         weights = self.get()
-        if getattr(self, "_structs_key", None) != self.key:
+        if self._structs is None:
             out = []
             for layer, w in zip(self.owner.conformer_layers, weights):
                 P = lambda name: _get(layer, name).data_ptr()                       # noqa: E731
@@ -201,45 +254,8 @@ class _WeightCache:
                 lw.pw2_w, lw.pw2_b = B("conv_module.sequential.5.weight"), P("conv_module.sequential.5.bias")
                 lw.final_ln_w, lw.final_ln_b = P("final_layer_norm.weight"), P("final_layer_norm.bias")
                 out.append(lw)
-            self._structs, self._structs_key = out, self.key
+            self._structs = out
         return self._structs
-
-    def _build_padded(self, dev):
-        """head_dim < 64 (Conformer-S: 36): zero-pad every head to 64 in the in/out projections so the attention
-        kernel sees head dim 64.  Weight preparation only (runs when parameters change), done with torch indexing."""
-        o = self.owner
-        H, dh, d = o.num_heads, o.head_dim, o.input_dim
-        self.bf16 = []
-        for layer in o.conformer_layers:
-            out = {}
-            for name in _BF16_WEIGHTS:
-                p = _get(layer, name).detach()
-                if name == "self_attn.in_proj_weight":
-                    # rel_att: a 4th slab repeats W_q -- the GEMM then emits [q+u | k | v | q+v] through the bias below
-                    nslab = 4 if o.rel_att else 3
-                    w = torch.zeros(nslab, H, HEAD_PAD, d, device=dev, dtype=torch.float32)
-                    w[:3, :, :dh] = p.view(3, H, dh, d)
-                    if o.rel_att:
-                        w[3] = w[0]
-                    p = w.view(nslab * H * HEAD_PAD, d)
-                elif name == "self_attn.out_proj.weight":
-                    w = torch.zeros(d, H, HEAD_PAD, device=dev, dtype=torch.float32)
-                    w[:, :, :dh] = p.view(d, H, dh)
-                    p = w.view(d, H * HEAD_PAD)
-                elif p.dim() == 3:
-                    p = p[:, :, 0]
-                out[name] = ops.cast_bf16(p.contiguous())
-            b = torch.zeros(4 if o.rel_att else 3, H, HEAD_PAD, device=dev, dtype=torch.float32)
-            b[:3, :, :dh] = _get(layer, "self_attn.in_proj_bias").detach().view(3, H, dh)
-            if o.rel_att:
-                b[3] = b[0]
-                b[0, :, :dh] += _get(layer, "self_attn.pos_bias_u").detach()
-                b[3, :, :dh] += _get(layer, "self_attn.pos_bias_v").detach()
-                wp = torch.zeros(H, HEAD_PAD, d, device=dev, dtype=torch.float32)
-                wp[:, :dh] = _get(layer, "self_attn.linear_pos.weight").detach().view(H, dh, d)
-                out["self_attn.linear_pos.weight"] = ops.cast_bf16(wp.view(H * HEAD_PAD, d))
-            out["in_bias"] = b.view(-1)
-            self.bf16.append(out)
 
 
 class Conformer(nn.Module):

@@ -48,20 +48,22 @@ class ConvSubSampling(nn.Module):
         self.out_nodes = out_nodes
         self.C2p = ((out_nodes + 15) // 16) * 16          # UMMA N granularity; extra channels are zero and sliced off
         self._key = None
+        self._ptrs = None
         self._composed = None
 
-    # -- composed weights, cached until a parameter changes --------------------------------------
+    # -- composed weights: static buffers, recomposed in place when a parameter changed -- and ALWAYS while the stream
+    #    is being captured, so a replayed CUDA graph recomposes from the parameters the optimizer has just updated
     def composed(self):
         ps = (self.conv_sub_1.weight, self.conv_sub_1.bias, self.conv_sub_2.weight, self.conv_sub_2.bias)
         key = tuple((p.data_ptr(), p._version) for p in ps)
-        if key != self._key:
-            Wc, bc = ops.convsub_compose(*(p.detach() for p in ps), self.s1, self.KP)
-            if self.C2p != self.out_nodes:
-                Wp = torch.zeros((self.C2p, self.KP), device=Wc.device, dtype=Wc.dtype)
-                bp = torch.zeros(self.C2p, device=bc.device, dtype=bc.dtype)
-                Wp[:self.out_nodes], bp[:self.out_nodes] = Wc, bc
-                Wc, bc = Wp, bp
-            self._composed = (Wc, bc)
+        ptrs = tuple(k[0] for k in key)
+        if self._composed is None or ptrs != self._ptrs:
+            dev = ps[0].device
+            self._composed = (torch.zeros((self.C2p, self.KP), device=dev, dtype=torch.bfloat16),
+                              torch.zeros(self.C2p, device=dev, dtype=torch.float32))
+            self._ptrs, self._key = ptrs, None
+        if key != self._key or torch.cuda.is_current_stream_capturing():
+            ops.convsub_compose(*(p.detach() for p in ps), self.s1, self.KP, out=self._composed)   # rows >= out_nodes stay zero
             self._key = key
         return self._composed
 

@@ -37,13 +37,6 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col, int rows) {
   return static_cast<uint32_t>(blk * rows * 128 + row * 128 + ((((cc >> 3) ^ (row & 7)) << 4) | ((cc & 7) << 1)));
 }
 
-// p = 0.5 (the reference's dropout): ONE hash decides 32 consecutive keys of a query row, one bit each -- instead of
-// one hash per 4 keys.  `row_lin` = (b*H + h)*T + q, `key32` = first key of the aligned 32-key group.  Forward and
-// backward both call this, so the masks agree (tests: attention dropout mask, forward == backward).
-__device__ __forceinline__ uint32_t drop_bits32(const DropCfg& d, uint64_t row_lin, int T, int key32) {
-  return drop_hash32(d.seed ^ 0x94D049BB133111EBull, row_lin * static_cast<uint64_t>((T + 31) >> 5) + static_cast<uint64_t>(key32 >> 5));
-}
-
 struct AttnParams {
   const int32_t* lengths;
   __nv_bfloat16* out;

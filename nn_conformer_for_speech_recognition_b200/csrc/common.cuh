@@ -100,7 +100,9 @@ struct DropCfg {
   float inv_keep;
   float inv_keep8;           // 256 / (256 - (thresh16 >> 8)): scale of the 8-bit-per-decision variants
 };
-const uint64_t* dropout_epoch_ptr();       // host.cpp: lazily allocated per-process device word
+uint64_t* dropout_epoch_ptr();             // dropout.cu: the CURRENT DEVICE's step counter (lazily allocated, one per device)
+const uint64_t* dropout_epoch_current();   // the word kernels launched by this thread read: the one installed with
+                                           // b2c_dropout_epoch_use (a per-call snapshot), else the device counter
 __host__ __device__ __forceinline__ uint64_t drop_mix_seed(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -110,7 +112,7 @@ __host__ __device__ __forceinline__ uint64_t drop_mix_seed(uint64_t z) {
 inline DropCfg make_drop(float p, uint64_t seed) {
   DropCfg d;
   d.seed = drop_mix_seed(seed);
-  d.epoch = p > 0.f ? dropout_epoch_ptr() : nullptr;
+  d.epoch = p > 0.f ? dropout_epoch_current() : nullptr;
   d.thresh16 = p > 0.f ? static_cast<uint32_t>(p * 65536.0 + 0.5) : 0u;
   if (d.thresh16 > 65535u) d.thresh16 = 65535u;
   d.inv_keep = p > 0.f ? 65536.f / static_cast<float>(65536u - d.thresh16) : 1.f;
@@ -148,6 +150,12 @@ __device__ __forceinline__ void drop_scale4g(const DropCfg& d, uint64_t idx4, fl
   s1 = ((h >> 8) & 0xFFu) >= t8 ? k : 0.f;
   s2 = ((h >> 16) & 0xFFu) >= t8 ? k : 0.f;
   s3 = (h >> 24) >= t8 ? k : 0.f;
+}
+// attention probabilities at p = 0.5 (the reference's dropout): ONE hash decides 32 consecutive keys of a query row, one
+// bit each.  `row_lin` = (b*H + h)*T + q, `key32` = first key of the aligned 32-key group.  Forward, backward and the
+// mask export (b2c_dropout_export_mask) all call this, so the masks agree.
+__device__ __forceinline__ uint32_t drop_bits32(const DropCfg& d, uint64_t row_lin, int T, int key32) {
+  return drop_hash32(d.seed ^ 0x94D049BB133111EBull, row_lin * static_cast<uint64_t>((T + 31) >> 5) + static_cast<uint64_t>(key32 >> 5));
 }
 // scales for elements idx (even) and idx+1
 __device__ __forceinline__ void drop_scale2(const DropCfg& d, uint64_t idx_even, float& s0, float& s1) {

@@ -147,18 +147,6 @@ int get_tensor_map_2d_sw(CUtensorMap* out, const void* base, int elem_bytes, uin
   return 0;
 }
 
-static uint64_t* g_epoch = nullptr;
-const uint64_t* dropout_epoch_ptr() {
-  static std::once_flag once;
-  std::call_once(once, [] {
-    if (cudaMalloc(&g_epoch, sizeof(uint64_t)) == cudaSuccess) cudaMemset(g_epoch, 0, sizeof(uint64_t));
-    else g_epoch = nullptr;
-  });
-  return g_epoch;
-}
-
-__global__ void epoch_bump_kernel(uint64_t* e) { *e += 1; }
-
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -175,14 +163,6 @@ extern "C" const char* b2c_last_error(void) { return b2c::g_err; }
 
 extern "C" int b2c_version(void) { return B2C_VERSION; }
 
-extern "C" int b2c_dropout_epoch_bump(void* stream) {
-  uint64_t* e = const_cast<uint64_t*>(b2c::dropout_epoch_ptr());
-  B2C_REQUIRE(e != nullptr, "b2c_dropout_epoch_bump: could not allocate the epoch word");
-  b2c::epoch_bump_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(e);
-  B2C_CUDA(cudaGetLastError());
-  return 0;
-}
-
 extern "C" int b2c_device_check(void) {
   int dev = 0;
   B2C_CUDA(cudaGetDevice(&dev));
@@ -193,9 +173,3 @@ extern "C" int b2c_device_check(void) {
   return 0;
 }
 
-extern "C" float b2c_dropout_keep_scale(float p) {      // mirrors make_drop(): 8-bit keep decision per element
-  if (!(p > 0.f)) return 1.f;
-  uint32_t t16 = static_cast<uint32_t>(p * 65536.0 + 0.5);
-  if (t16 > 65535u) t16 = 65535u;
-  return 256.f / (256.f - static_cast<float>(t16 >> 8));
-}

@@ -19,32 +19,40 @@ from typing import Optional
 import torch
 from torch import nn
 
-from . import ops, specaugment
+from . import _lib, ops, specaugment
 from .conformer import Conformer
 from .convsubsampling import ConvSubSampling
 
 
 class _BridgeFn(torch.autograd.Function):
-    """y[M,d] = a[M,K] W^T + b on the tcgen05 GEMM; a is the bf16 token-major conv-subsampling output."""
+    """y[M,d] = dropout(a[M,K] W^T + b) on the tcgen05 GEMM; a is the bf16 token-major conv-subsampling output.  The
+    dropout is the reference's `self.dropout(x)` between bridge and Conformer stack (asrnn.py:210), fused as the GEMM's
+    epilogue; the backward regenerates the same mask (same seed, same per-call epoch word) while casting dy."""
 
     @staticmethod
-    def forward(ctx, a, weight, bias, w_bf16):
+    def forward(ctx, a, weight, bias, w_bf16, drop_p, drop_seed):
         M, K = a.shape
         ctx.save_for_backward(a, w_bf16)
         ctx.shapes = (M, K, weight.shape[0])
-        return ops.gemm(a, w_bf16, M=M, N=weight.shape[0], K=K, bias=bias, out_dtype=torch.float32)
+        ctx.drop = (drop_p, drop_seed)
+        ctx.epoch = _lib.epoch_snapshot(a.device) if drop_p > 0.0 else None
+        with _lib.epoch_scope(ctx.epoch):
+            return ops.gemm(a, w_bf16, M=M, N=weight.shape[0], K=K, bias=bias, out_dtype=torch.float32, drop_p=drop_p,
+                            drop_seed=drop_seed)
 
     @staticmethod
     def backward(ctx, dy):
         a, w_bf16 = ctx.saved_tensors
         M, K, N = ctx.shapes
+        drop_p, drop_seed = ctx.drop
         db = torch.zeros(N, device=dy.device, dtype=torch.float32)
-        dyb = ops.scale_cast(dy.contiguous().view(M, N), 1.0, colsum=db)
+        with _lib.epoch_scope(ctx.epoch):
+            dyb = ops.scale_cast(dy.contiguous().view(M, N), 1.0, drop_p, drop_seed, colsum=db)
         dW = torch.zeros((N, K), device=dy.device, dtype=torch.float32)
         ops.gemm(dyb, a, M=N, N=K, K=M, a_mn=True, b_mn=True, out=dW, accumulate=True,
                  split_k=max(1, min(16, ((M + 63) // 64) // 4)))
         da = ops.gemm(dyb, w_bf16, M=M, N=K, K=N, b_mn=True) if ctx.needs_input_grad[0] else None
-        return da, dW, db, None
+        return da, dW, db, None, None, None
 
 
 class _LinearFn(torch.autograd.Function):
@@ -93,9 +101,11 @@ class Linear(nn.Linear):
 class ConformerEncoder(nn.Module):
     def __init__(self, hp, input_dim: int, num_heads: int, ffn_dim: int, num_layers: int,
                  depthwise_conv_kernel_size: int, dropout: float = 0.0, conv_out_nodes: int = 128,
-                 specaug_mode: str = "reference"):
+                 specaug_mode: str = "reference", bridge_dropout: Optional[float] = None):
         super().__init__()
         self.hp = hp
+        # `self.dropout(x)` between bridge and Conformer stack (asrnn.py:210): the reference uses hp.dropout for both
+        self.bridge_dropout_p = float(dropout if bridge_dropout is None else bridge_dropout)
         self.conv_sub_sampling = ConvSubSampling(hp, 1, conv_out_nodes)
         cs = self.conv_sub_sampling
         self.freq_out = (hp.input_rows - cs.kc) // cs.stride + 1
@@ -113,14 +123,22 @@ class ConformerEncoder(nn.Module):
         return l2.clamp(min=0)
 
     def _bridge_weight(self):
+        """bf16 bridge weight in the kernel's token-major feature order, in a STATIC buffer.  Refreshed when the Parameter
+        changed and always while the stream is being captured (a replayed graph must re-derive it from the fp32 master
+        the optimizer updates -- same policy as conformer._WeightCache)."""
         w = self.bridge.weight
         key = (w.data_ptr(), w._version)
-        if key != self._bridge_key:
+        if self._bridge_bf16 is None or self._bridge_bf16.device != w.device or key[0] != (self._bridge_key or (None,))[0]:
+            self._bridge_f32 = torch.empty(w.shape, device=w.device, dtype=torch.float32)
+            self._bridge_bf16 = torch.empty(w.shape, device=w.device, dtype=torch.bfloat16)
+            self._bridge_key = None
+        if key != self._bridge_key or torch.cuda.is_current_stream_capturing():
             # the module stores the weight with the reference's NCHW flatten order (feature = c*F' + f'); the kernel's
-            # token-major rows are ordered f'*C + c, so permute once per weight update (weight prep, not data path)
+            # token-major rows are ordered f'*C + c: permuting copy + cast (weight prep, two launches)
             C, Fo = self.conv_sub_sampling.out_nodes, self.freq_out
-            wp = w.detach().view(-1, C, Fo).permute(0, 2, 1).reshape(w.shape[0], Fo * C).contiguous()
-            self._bridge_bf16 = ops.cast_bf16(wp)
+            with torch.no_grad():
+                self._bridge_f32.view(-1, Fo, C).copy_(w.detach().view(-1, C, Fo).permute(0, 2, 1))
+            ops.cast_bf16(self._bridge_f32, self._bridge_bf16)
             self._bridge_key = key
         return self._bridge_bf16
 
@@ -135,12 +153,15 @@ class ConformerEncoder(nn.Module):
         tok = self.conv_sub_sampling.forward_tokens(x)                  # (B, T', F', C) bf16
         B, To, Fo, C = tok.shape
         w_bf16 = self._bridge_weight()
+        drop_p = self.bridge_dropout_p if self.training else 0.0
+        drop_seed = (self.conformers.next_seed() ^ 0x5DEECE66D) if drop_p > 0.0 else 0
         if torch.is_grad_enabled() and (self.bridge.weight.requires_grad or tok.requires_grad):
             wp_view = self.bridge.weight.view(-1, C, Fo).permute(0, 2, 1).reshape(self.bridge.weight.shape[0], Fo * C)
-            h = _BridgeFn.apply(tok.view(B * To, Fo * C), wp_view, self.bridge.bias, w_bf16)
+            h = _BridgeFn.apply(tok.view(B * To, Fo * C), wp_view, self.bridge.bias, w_bf16, drop_p, drop_seed)
         else:
-            h = ops.gemm(tok.view(B * To, Fo * C), w_bf16, M=B * To, N=self.bridge.weight.shape[0], K=Fo * C,
-                         bias=self.bridge.bias, out_dtype=torch.float32)
+            with _lib.epoch_scope(_lib.epoch_snapshot(tok.device) if drop_p > 0.0 else None):
+                h = ops.gemm(tok.view(B * To, Fo * C), w_bf16, M=B * To, N=self.bridge.weight.shape[0], K=Fo * C,
+                             bias=self.bridge.bias, out_dtype=torch.float32, drop_p=drop_p, drop_seed=drop_seed)
         out_lens = self.output_lengths(input_lens)
         y, _ = self.conformers(h.view(B, To, -1), out_lens)
         return y, out_lens

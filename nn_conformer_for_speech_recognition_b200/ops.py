@@ -194,13 +194,17 @@ def attention_rel_bwd(qkv, pw, lengths_i32, att, datt, lse, B: int, T: int, H: i
     return dqkv, dpw
 
 
-def convsub_compose(W1, b1, W2, b2, s1: int, KP: int, want_f32: bool = False):
+def convsub_compose(W1, b1, W2, b2, s1: int, KP: int, want_f32: bool = False, out=None):
+    """out = (Wc bf16 [>=C2, KP], bc fp32 [>=C2]): write into these (static) buffers instead of allocating."""
     _lib.require_device()
     C1, _, k1, _ = W1.shape
     C2, _, k2, _ = W2.shape
-    Wc = torch.empty((C2, KP), device=W1.device, dtype=torch.bfloat16)
+    if out is not None:
+        Wc, bc = out
+    else:
+        Wc = torch.empty((C2, KP), device=W1.device, dtype=torch.bfloat16)
+        bc = torch.empty(C2, device=W1.device, dtype=torch.float32)
     Wc32 = torch.empty((C2, KP), device=W1.device, dtype=torch.float32) if want_f32 else None
-    bc = torch.empty(C2, device=W1.device, dtype=torch.float32)
     call("b2c_convsub_compose", ptr(W1), ptr(b1), ptr(W2), ptr(b2), C1, C2, k1, s1, k2, ptr(Wc), ptr(Wc32), ptr(bc), KP,
          stream_ptr())
     return (Wc, bc, Wc32) if want_f32 else (Wc, bc)

@@ -125,8 +125,12 @@ class SpecAugPlan:
     """Pre-drawn SpecAugment for a CUDA-graph-captured step.
 
     `draw(...)` runs on the host BEFORE the replay (same draws, same order, same global `random` stream as
-    `SpecAugment`) and writes the parameters into a pinned buffer; `apply(x)` only enqueues a pinned->device copy and the
-    kernel, so it can be captured once and replayed with new parameters every step.
+    `SpecAugment`), writes the parameters into a pinned block and enqueues its host->device copy on the current
+    stream; `apply(x)` is only the kernel launch, so it can be captured once and replayed with new parameters every
+    step.  The pinned block is DOUBLE-BUFFERED: in a device-resident loop nothing synchronises host and device, so the
+    host can be drawing step n+1 while step n's copy has not executed yet -- `draw` alternates two pinned slots and
+    waits for the copy that last read the slot it is about to overwrite (an event recorded behind that copy).  The
+    device block needs no second copy: the stream orders copy(n+1) behind the kernel of step n.
     """
 
     def __init__(self, hp, B: int, device, mode: str = "reference"):
@@ -136,7 +140,9 @@ class SpecAugPlan:
             Mt = min(Mt, floor(hp.pm))
         self.n_warp, self.n_f, self.n_t = hp.warping_ntimes, hp.frequency_mask_ntimes, Mt
         n = B + 2 * self.n_warp * B + 2 * self.n_f + 2 * self.n_t * B
-        self.host = torch.zeros(max(n, 1), dtype=torch.int32).pin_memory()
+        self.hosts = [torch.zeros(max(n, 1), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.copied = [None, None]                       # event behind the last copy that read hosts[i]
+        self.slot = 0
         self.dev = torch.zeros(max(n, 1), dtype=torch.int32, device=device)
         o = 0
         self.sl = {}
@@ -145,13 +151,21 @@ class SpecAugPlan:
             self.sl[name] = (o, o + cnt)
             o += cnt
 
+    @property
+    def host(self):
+        """the pinned slot written by the latest draw()"""
+        return self.hosts[self.slot ^ 1]
+
     def draw(self, F: int, tau):
         hp, B = self.hp, self.B
         tau = _tau_list(tau)
         warps = [_draw_warp(hp, B, tau) for _ in range(self.n_warp)]
         fmasks = [_draw_fmask(hp, F) for _ in range(self.n_f)]
         tmasks = [_draw_tmask(hp, B, tau) for _ in range(self.n_t)]
-        h = self.host
+        i = self.slot
+        if self.copied[i] is not None:
+            self.copied[i].synchronize()                 # the copy issued two draws ago has read this slot
+        h = self.hosts[i]
 
         def put(name, values):
             a, b = self.sl[name]
@@ -162,11 +176,15 @@ class SpecAugPlan:
         put("w0", [w[1] for w in warps])
         put("fm", fmasks)
         put("tm", tmasks)
+        self.dev.copy_(h, non_blocking=True)             # ordered behind the previous step's kernel on this stream
+        ev = torch.cuda.Event()
+        ev.record()
+        self.copied[i] = ev
+        self.slot = i ^ 1
 
     def apply(self, x4: torch.Tensor) -> torch.Tensor:
-        """x4 (B,1,F,T) fp32 on the GPU -> (B,1,F,T); capturable."""
+        """x4 (B,1,F,T) fp32 on the GPU -> (B,1,F,T); one kernel launch, capturable."""
         x = x4[:, 0] if x4.dim() == 4 else x4
-        self.dev.copy_(self.host, non_blocking=True)
         d = self.dev
 
         def view(name, shape):
