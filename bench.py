@@ -245,14 +245,29 @@ class Rig:
                 self.opt = opt = Adafactor(params, lr=2e-5, beta1=0.9, scale_parameter=False, relative_step=False)
                 use_graph = False
 
+            from nn_conformer_for_speech_recognition_b200.ctc import ctc_loss_from_logits
+            fused_ctc = self.fused_ctc = getattr(args, "ctc", "fused") == "fused"
+            tgt_i32 = tgt.to(torch.int32)
+            out_lens_i32 = torch.full((B,), self.Tp, device=dev, dtype=torch.int32)
+            tgt_lens_i32 = torch.full((B,), TGT_LEN, device=dev, dtype=torch.int32)
+
+            def loss_of(y):
+                if fused_ctc:     # csrc/ctc.cu: log_softmax + CTC + d/dlogits (asrnn.py:254-256, runner.py:35,143)
+                    return ctc_loss_from_logits(head(y), tgt_i32, out_lens_i32, tgt_lens_i32, blank=0, zero_infinity=True)
+                logp = head(y).log_softmax(-1).transpose(0, 1)
+                return torch.nn.functional.ctc_loss(logp, tgt, out_lens_host, tgt_lens_host, blank=0, zero_infinity=True)
+            self.loss_of = loss_of
+
             class EncStep(nn.Module):
-                """encoder forward as a Module so torch.cuda.make_graphed_callables can capture its forward AND backward"""
+                """forward as a Module so torch.cuda.make_graphed_callables can capture its forward AND backward: the encoder
+                and -- with the fused CTC -- the head projection and the loss (everything but the optimizer)"""
                 def __init__(self):
                     super().__init__()
-                    self.enc = enc
+                    self.enc, self.head = enc, head
 
                 def forward(self, xin):
-                    return self.enc(xin, lens, SpecAugment=True, specaug_plan=plan)[0]
+                    y = self.enc(xin, lens, SpecAugment=True, specaug_plan=plan)[0]
+                    return loss_of(y) if fused_ctc else y
 
             enc_step = EncStep()
             if use_graph:
@@ -264,13 +279,12 @@ class Rig:
             sync = self.sync
 
             def device_step(xin):
-                """One training step.  The encoder (every kernel of this repo's hot path, INCLUDING the bf16 / composed /
-                permuted weight preparation) is graph-replayed; the CTC head is torch (not hot path) and stays eager
-                because torch's CTC copies its length lists host->device internally."""
+                """One training step.  Encoder, head projection and fused CTC loss (every kernel of this repo, INCLUDING the
+                bf16 / composed / permuted weight preparation) are graph-replayed, forward and backward; the gradient
+                exchange (N > 1) and the fused Adafactor run eagerly behind them."""
                 opt.zero_grad(set_to_none=True)
-                y = enc_step(xin)
-                logp = head(y).log_softmax(-1).transpose(0, 1)
-                loss = torch.nn.functional.ctc_loss(logp, tgt, out_lens_host, tgt_lens_host, blank=0, zero_infinity=True)
+                out = enc_step(xin)
+                loss = out if fused_ctc else loss_of(out)
                 loss.backward()
                 if sync is not None:
                     sync.finish()
@@ -375,8 +389,7 @@ class Rig:
         if self.mode == "train":
             self.opt.zero_grad(set_to_none=True)
             y_i = self.enc(self.x_static, self.lens, SpecAugment=True, specaug_plan=self.plan)[0]
-            torch.nn.functional.ctc_loss(self.head(y_i).log_softmax(-1).transpose(0, 1), self.tgt, [self.Tp] * self.B,
-                                         [TGT_LEN] * self.B, blank=0, zero_infinity=True).backward()
+            self.loss_of(y_i).backward()
             self.opt.step()
         else:
             with torch.no_grad():
@@ -543,6 +556,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=15.0)
     ap.add_argument("--ref-batch", type=int, default=8, help="utterances per step of the CPU reference arm")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "hf"])
+    ap.add_argument("--ctc", default="fused", choices=["fused", "torch"], help="fused = csrc/ctc.cu (default); torch = ATen log_softmax + ctc_loss")
     ap.add_argument("--nst-utts", type=int, default=1250, help="C5 secondary: utterances per GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -603,8 +617,9 @@ def main():
     audio_s = B * args.seconds * world
     value = audio_s / (m["ms"] / 1e3)
     e2e_val = audio_s / (m["e2e_ms"] / 1e3)
-    details = dict(head="Linear(d,1024) on the tcgen05 GEMM; log_softmax + CTC via torch (not hot path, SURVEY 8f#2)",
-                   launch=(("CUDA graph replay (encoder fwd+bwd incl. weight preparation captured; CTC head + optimizer eager)"
+    details = dict(head=("Linear(d,1024) on the tcgen05 GEMM + fused log_softmax/CTC kernels (csrc/ctc.cu)" if getattr(rig, "fused_ctc", False)
+                         else "Linear(d,1024) on the tcgen05 GEMM; log_softmax + CTC via torch"),
+                   launch=(("CUDA graph replay (encoder + head + CTC fwd+bwd incl. weight preparation captured; optimizer eager)"
                             if args.mode == "train" else "CUDA graph replay") if rig.graphed else "eager launches"))
     if args.mode == "train":
         details.update(optimizer=f"Adafactor[{args.optimizer}] lr 2e-5 beta1 0.9 (runner.py:36)",

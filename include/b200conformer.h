@@ -283,6 +283,21 @@ int b2c_colsum_bf16(const void* a, int64_t ld, int64_t rows, int64_t cols, float
 /* pads / unpads per-head columns:  dst[r, h*dst_dh + c] = src[r, h*src_dh + c] (zero fill), nblk = blocks per row */
 int b2c_repack_heads(const void* src, void* dst, int64_t rows, int nblk, int src_dh, int dst_dh, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused log-softmax + CTC loss (+ gradient w.r.t. the logits): `nn.LogSoftmax(-1)` at asrnn.py:44,254-256 followed by
+ * `CTCLoss(blank=hp.blank_idx, zero_infinity=True)` at runner.py:35,143 (reduction 'mean': nll_b / max(S_b, 1), averaged
+ * over the batch; infinite losses and their gradients zeroed when zero_infinity).
+ *   logits fp32 [B, T, V] batch-major (row = b*T + t); log-softmaxed input gives the same result (log_softmax is idempotent)
+ *   targets int32 [B, Smax] (labels beyond target_lens[b] ignored), input_lens / target_lens int32 [B]
+ *   loss fp32 [1], nll fp32 [B] (optional), grad_logits fp32 [B, T, V] = d loss / d logits * (*grad_out)
+ *   phases: 1 forward only (state posteriors stay in `workspace`), 2 gradient only (same workspace), 3 both
+ *   grad_out: DEVICE scalar or NULL (= 1).  workspace: b2c_ctc_workspace(B, T, Smax) bytes.
+ * ------------------------------------------------------------------------------------------------------- */
+size_t b2c_ctc_workspace(int B, int T, int Smax);
+int b2c_ctc_loss(const float* logits, const int32_t* targets, const int32_t* input_lens, const int32_t* target_lens, int B,
+                 int T, int V, int Smax, int blank, int zero_infinity, int phases, const float* grad_out, float* loss,
+                 float* nll, float* grad_logits, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,10 +77,12 @@ SIGNATURES = {
     "b2c_scale_cast": [_P, _P, _L, _L, _F, _F, c_uint64, _P, _P],
     "b2c_colsum_bf16": [_P, _L, _L, _L, _P, _P],
     "b2c_repack_heads": [_P, _P, _L, _I, _I, _I, _P],
+    "b2c_ctc_loss": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, ctypes.c_size_t, _P],
 }
 HOST_SIGNATURES = {
     "b2c_dropout_keep_scale": ([c_float], c_float),
     "b2c_conformer_layer_eval_workspace": ([_I, _I, _I, _I, _I], ctypes.c_size_t),
+    "b2c_ctc_workspace": ([_I, _I, _I], ctypes.c_size_t),
     "b2c_last_error": ([], c_char_p),
     "b2c_mt19937_seed_host": ([POINTER(c_uint32), c_uint64], None),
     "b2c_mt19937_randint_host": ([POINTER(c_uint32), c_int64, c_int64], c_int64),
@@ -88,7 +90,7 @@ HOST_SIGNATURES = {
 
 _lib = None
 LAUNCHES = 0          # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 2, "b2c_convsub_compose_bwd": 2, "b2c_attention_bwd": 4, "b2c_attention_rel_bwd": 4, "b2c_conformer_layer_eval": 20, "b2c_adafactor_step": 5, "b2c_version": 0, "b2c_device_check": 0, "b2c_dropout_epoch_use": 0}
+_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 2, "b2c_convsub_compose_bwd": 2, "b2c_attention_bwd": 4, "b2c_attention_rel_bwd": 4, "b2c_conformer_layer_eval": 20, "b2c_adafactor_step": 5, "b2c_ctc_loss": 3, "b2c_version": 0, "b2c_device_check": 0, "b2c_dropout_epoch_use": 0}
 
 
 def load() -> ctypes.CDLL:
