@@ -227,6 +227,9 @@ class Rig:
         self.x_static = self.x_host.to(dev)
         self.sync = dp.GradSync(enc, head, world=world) if (world > 1 and mode == "train") else None
         if self.sync is not None:
+            # the stack's gradient arena is all-reduced in 4 spans of layers from INSIDE the backward pass (captured into the
+            # backward graph as a parallel branch), overlapping the backward kernels of the layers below
+            self.sync.attach(enc.conformers, groups=int(os.environ.get("B2C_DP_GROUPS", "4")))
             self.sync.broadcast_parameters()
         self.plan = plan = SpecAugPlan(hp, B, dev, mode="paper")
         tgt_lens_host, out_lens_host = [TGT_LEN] * B, [self.Tp] * B
@@ -384,6 +387,8 @@ class Rig:
         from nn_conformer_for_speech_recognition_b200 import conformer as _cf
         saved = _cf._LAYER_CALLS
         _cf._LAYER_CALLS = False               # per-launch events need per-launch calls (eval normally makes one C call per layer)
+        gs = getattr(self.enc.conformers, "_grad_sync", None)
+        self.enc.conformers._grad_sync = None  # this step runs on rank 0 ALONE: no collective may be issued from its backward
         prof = _lib.profile_begin()
         self.host_prepare()
         if self.mode == "train":
@@ -396,6 +401,7 @@ class Rig:
                 self.enc(self.x_static, self.lens)
         rows = _lib.profile_end(prof)
         _cf._LAYER_CALLS = saved
+        self.enc.conformers._grad_sync = gs
         return rows
 
     def gemm_roofline(self, rows, pk):
@@ -687,7 +693,12 @@ def main():
                                             sample=f"failed: {type(e).__name__}: {e}")
         emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # The backward CUDA graphs hold captured NCCL collectives; tearing the communicator down underneath them can block
+        # (observed: destroy_process_group() never returned at N = 2).  All results are out: meet once more, then leave.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -136,6 +136,15 @@ class _ConformerFn(torch.autograd.Function):
         # Operands stay referenced until the streams are joined again.
         main = torch.cuda.current_stream()
         side = _side_stream(dev) if _WGRAD_SIDE_STREAM else None
+        # data-parallel training: dp.GradSync.attach() asks for the arena to be all-reduced in `groups` spans of layers
+        gsync = getattr(model, "_grad_sync", None)
+        group_lo = {}
+        if gsync is not None and gsync.world > 1:
+            ng, Lr = model._grad_sync_groups, model.num_layers
+            bounds = [round(i * Lr / ng) for i in range(ng + 1)]
+            group_lo = {bounds[i]: bounds[i + 1] for i in range(ng)}      # first layer of a group -> one past its last
+        else:
+            gsync = None
         keep = []
 
         def wgrad(dyb, act, Mo, No, out):
@@ -225,10 +234,19 @@ class _ConformerFn(torch.autograd.Function):
             # ---- 1. FFN1
             ffn_bwd("ffn1", 0, dyb, None)
             ctx.state[li] = None                  # free this layer's saved activations
+            if gsync is not None and li in group_lo:
+                # every gradient of layers [li, group end) is final: hand the arena span to the gradient exchange now, so
+                # the all-reduce runs (NCCL stream / parallel graph branch) under the backward kernels of the layers below
+                if side is not None:
+                    main.wait_stream(side)
+                hi_layer = group_lo[li]
+                gsync.reduce_span(arena[offs[li * np_]:offs[hi_layer * np_]])
 
         if side is not None:
             main.wait_stream(side)
             keep.clear()
+        if gsync is not None:
+            gsync.join()                          # the reduced spans are visible to the stream before the gradients are handed out
         grads = []
         for li, layer in enumerate(model.conformer_layers):
             for n in _LAYER_PARAMS:

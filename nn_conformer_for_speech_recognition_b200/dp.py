@@ -2,10 +2,9 @@
 gloo in the CPU tests).  The path shards by utterance: inference and NST pseudo-labelling use
 NO collective; a training step has exactly one exchange -- the gradient all-reduce (mean) -- issued in buckets.
 
-`GradSync.finish()` is called between backward and the optimizer step.  Gradients are packed into flat buckets of
-about `bucket_mb` MB, each bucket is all-reduced asynchronously (NCCL runs them on its own stream, overlapping the
-packing of the next bucket), then unpacked.  BatchNorm statistics stay local to each rank, as in the single-device
-reference; parameters and buffers are broadcast from rank 0 once.
+See `GradSync`: the Conformer stack's gradient arena is all-reduced in layer-group spans from INSIDE the backward pass
+(overlapping the rest of it); `GradSync.finish()`, called between backward and the optimizer step, handles the few
+remaining gradients in packed buckets.
 """
 from __future__ import annotations
 
@@ -39,56 +38,77 @@ def make_buckets(sizes: List[int], bucket_elems: int) -> List[List[int]]:
 
 
 class GradSync:
+    """Gradient exchange of a training step: exactly one all-reduce (mean) per gradient element, issued as early as possible.
+
+    * The Conformer stack computes all of its ~500 parameter gradients into ONE fp32 arena (autograd.py), last layer first.
+      `attach(conformer, groups)` makes its backward pass hand the arena span of every finished group of layers to
+      `reduce_span`, which all-reduces it IN PLACE and asynchronously -- NCCL works on the spans of layers 12-15 while the
+      backward kernels of layers 0-11 still run (and, when the backward pass is captured into a CUDA graph, the collectives
+      are captured with it as a parallel branch).  The backward pass joins them before it returns.
+    * Everything else (conv-subsampling, bridge, head: their gradients are the LAST the backward pass produces) goes through
+      `finish()`: packed into flat buckets, all-reduced, unpacked with one multi-tensor copy.  The parameter list of that
+      path is fixed at construction time (no per-step grouping by storage).
+    BatchNorm statistics stay local to each rank, as in the single-device reference; parameters and buffers are broadcast
+    from rank 0 once."""
+
     def __init__(self, *modules, world: int = None, bucket_mb: float = 32.0):
         self.params = [p for m in modules for p in m.parameters() if p.requires_grad]
         self.buffers = [b for m in modules for b in m.buffers()]
         self.world = world if world is not None else dist.get_world_size()
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
-        self.buckets = make_buckets([p.numel() for p in self.params], self.bucket_elems)
         self.avg = dist.get_backend() == "nccl"
+        self.op = dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM
+        self.pending = []
+        self.in_backward_ids = set()           # parameters whose gradients are reduced inside the Conformer backward
+        self.loose = list(self.params)
+        self.buckets = make_buckets([p.numel() for p in self.loose], self.bucket_elems)
+
+    def attach(self, conformer, groups: int = 4):
+        """Reduce the Conformer stack's gradient arena from inside its backward pass, in `groups` spans of layers."""
+        conformer._grad_sync = self
+        conformer._grad_sync_groups = max(1, min(groups, conformer.num_layers))
+        self.in_backward_ids = {id(p) for p in conformer.parameters()}
+        self.loose = [p for p in self.params if id(p) not in self.in_backward_ids]
+        self.buckets = make_buckets([p.numel() for p in self.loose], self.bucket_elems)
+        return self
 
     def broadcast_parameters(self, src: int = 0):
         for t in self.params + self.buffers:
             dist.broadcast(t.data, src)
 
-    def finish(self):
-        """All-reduce (mean) every gradient; returns when the results are visible to the current stream.
-
-        Gradients that are views of ONE buffer (the Conformer stack returns all of its ~500 parameter gradients as slices
-        of a single fp32 arena, autograd.py) are reduced IN PLACE as one flat span: no packing, no per-parameter
-        unpacking copies (those were ~500 launches = a tenth of the step at world size 2).  Everything else goes
-        through the bucketed pack / all-reduce / multi-tensor unpack path."""
+    # ---- called by autograd._ConformerFn.backward --------------------------------------------------------------------
+    def reduce_span(self, flat: torch.Tensor):
         if self.world == 1:
             return
-        op = dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM
-        by_storage = {}
-        for p in self.params:
-            g = p.grad
-            if g is None:
+        self.pending.append((dist.all_reduce(flat, op=self.op, async_op=True), flat))
+
+    def join(self):
+        for work, flat in self.pending:
+            work.wait()
+            if not self.avg:
+                flat.div_(self.world)
+        self.pending = []
+
+    # ---- called between backward and the optimizer step ---------------------------------------------------------------
+    def finish(self):
+        """All-reduce (mean) the gradients the backward pass has not already reduced; returns when the results are visible
+        to the current stream."""
+        if self.world == 1:
+            return
+        self.join()
+        pending = []
+        for idx in self.buckets:
+            grads = [self.loose[i].grad for i in idx if self.loose[i].grad is not None]
+            if not grads:
                 continue
-            by_storage.setdefault(g.untyped_storage().data_ptr(), []).append(g)
-        pending, loose = [], []
-        for grads in by_storage.values():
-            g0 = grads[0]
-            if len(grads) >= 8 and all(g.is_contiguous() and g.dtype == g0.dtype for g in grads):
-                lo = min(g.storage_offset() for g in grads)
-                hi = max(g.storage_offset() + g.numel() for g in grads)
-                if hi - lo <= 1.25 * sum(g.numel() for g in grads):         # dense enough: reduce the span itself
-                    flat = torch.empty(0, device=g0.device, dtype=g0.dtype).set_(g0.untyped_storage(), lo, (hi - lo,))
-                    pending.append((dist.all_reduce(flat, op=op, async_op=True), flat, None))
-                    continue
-            loose += grads
-        for idx in make_buckets([g.numel() for g in loose], self.bucket_elems):
-            grads = [loose[i] for i in idx]
             flat = torch.cat([g.reshape(-1) for g in grads])
-            pending.append((dist.all_reduce(flat, op=op, async_op=True), flat, grads))
+            pending.append((dist.all_reduce(flat, op=self.op, async_op=True), flat, grads))
         for work, flat, grads in pending:
             work.wait()
             if not self.avg:
                 flat.div_(self.world)
-            if grads is not None:
-                outs, off = [], 0
-                for g in grads:
-                    outs.append(flat[off:off + g.numel()].view_as(g))
-                    off += g.numel()
-                torch._foreach_copy_(grads, outs)
+            outs, off = [], 0
+            for g in grads:
+                outs.append(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+            torch._foreach_copy_(grads, outs)

@@ -53,7 +53,7 @@ def _worker(rank, world, port, q):
         ref = p.data.clone()
         dist.broadcast(ref, 0)
         same_params &= bool(torch.equal(ref, p.data))
-    # gradients living in ONE arena (what the Conformer stack's backward returns): reduced in place as a single span
+    # gradients living in ONE arena (what the Conformer stack's backward returns): reduced in place, span by span
     deep = torch.nn.Sequential(*[torch.nn.Linear(4, 4) for _ in range(6)])
     with torch.no_grad():
         for p in deep.parameters():
@@ -68,17 +68,32 @@ def _worker(rank, world, port, q):
         p.grad = view
         local2.append(view.clone())
         off += p.numel()
-    sync2 = dp.GradSync(deep, world=world)
+    # the protocol autograd._ConformerFn.backward follows: attach() -> reduce_span() per finished group of layers (async, in
+    # place, no packing) -> join() before the gradients are handed out; finish() then only handles the OTHER parameters
+    extra = torch.nn.Linear(3, 2)
+    extra(torch.ones(1, 3) * (rank + 1)).sum().backward()
+    local3 = [p.grad.clone() for p in extra.parameters()]
+    deep.num_layers = 6
+    sync2 = dp.GradSync(deep, extra, world=world).attach(deep, groups=2)
+    assert [id(p) for p in sync2.loose] == [id(p) for p in extra.parameters()]
     calls = []
     orig = dist.all_reduce
     dist.all_reduce = lambda t, **kw: (calls.append(t.numel()), orig(t, **kw))[1]
+    half = n // 2
+    sync2.reduce_span(arena[4 + half:4 + n])                    # the later layers finish first
+    sync2.reduce_span(arena[4:4 + half])
+    sync2.join()
     sync2.finish()
     dist.all_reduce = orig
     g2 = [[torch.zeros_like(g) for _ in range(world)] for g in local2]
     for g, out in zip(local2, g2):
         dist.all_gather(out, g)
     ok &= all(torch.allclose(p.grad, sum(out) / world, atol=1e-6) for p, out in zip(deep.parameters(), g2))
-    ok &= calls == [n]                                          # one collective over the span, no packing
+    g3 = [[torch.zeros_like(g) for _ in range(world)] for g in local3]
+    for g, out in zip(local3, g3):
+        dist.all_gather(out, g)
+    ok &= all(torch.allclose(p.grad, sum(out) / world, atol=1e-6) for p, out in zip(extra.parameters(), g3))
+    ok &= calls == [n - half, half, sum(p.numel() for p in extra.parameters())]   # two spans in place + one packed bucket
     q.put((rank, ok, same_params))
     dist.destroy_process_group()
 
