@@ -298,6 +298,26 @@ int b2c_ctc_loss(const float* logits, const int32_t* targets, const int32_t* inp
                  int T, int V, int Smax, int blank, int zero_infinity, int phases, const float* grad_out, float* loss,
                  float* nll, float* grad_logits, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * BatchNorm1d over token rows (+ the SiLU in front of it): tail of the reference's projection block
+ * `projection_fc -> swish -> projection_batch_norm` (asrnn.py:73-89,217).  Linear + SiLU = b2c_gemm_bf16 with act = SILU and
+ * out2 = z (saved pre-activation); h bf16 [rows, C] is its output.
+ *   _stats       stats fp64 [2C] (zeroed by the caller) += per-channel sum, sum of squares of h; b2c_convmod_bn_finalize turns
+ *                them into mean / rstd and updates the running statistics
+ *   _apply       y fp32 [rows, C] = (h - mean) * rstd * gamma + beta
+ *   _bwd_reduce  sums fp64 [2C] (zeroed) += sum dy (= dbeta), sum dy * hhat (= dgamma)
+ *   _bwd_apply   dz bf16 = BN'(dy) * SiLU'(z)  (train = 1: batch-statistics formula, 0: gamma * rstd * dy);
+ *                colsum fp32 [C] (optional) += column sums of dz (the Linear's bias gradient)
+ * ------------------------------------------------------------------------------------------------------- */
+int b2c_bn1d_stats(const void* h, double* stats, int64_t rows, int C, void* stream);
+int b2c_bn1d_apply(const void* h, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
+                   int64_t rows, int C, void* stream);
+int b2c_bn1d_bwd_reduce(const float* dy, const void* h, const float* mean, const float* rstd, double* sums, int64_t rows,
+                        int C, void* stream);
+int b2c_bn1d_bwd_apply(const float* dy, const void* h, const void* z, const float* mean, const float* rstd,
+                       const float* gamma, const double* sums, int train, void* dz, float* colsum, int64_t rows, int C,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif
