@@ -278,6 +278,9 @@ int b2c_multi_cast_f32_bf16(const void* table_dev, int n_tensors, int64_t max_n,
  * colsum (optional fp32 [cols]) += column sums of dst: the bias gradient of the linear layer that produced y */
 int b2c_scale_cast(const float* src, void* dst, int64_t rows, int64_t cols, float alpha, float drop_p,
                    uint64_t drop_seed, float* colsum, void* stream);
+/* out = x + e (fp32, n % 4 == 0): `x = x + rel_pos_emb` of the reference's own positional variant
+ * (unused_lib/conformer.py:101-103, table from unused_lib/relativepositionalembeddings.py:26-32) */
+int b2c_add_f32(const float* x, const float* e, float* out, int64_t n, void* stream);
 /* out fp32 [cols] += column sums of a bf16 [rows, ld] matrix (bias gradients) */
 int b2c_colsum_bf16(const void* a, int64_t ld, int64_t rows, int64_t cols, float* out, void* stream);
 /* pads / unpads per-head columns:  dst[r, h*dst_dh + c] = src[r, h*src_dh + c] (zero fill), nblk = blocks per row */

@@ -16,6 +16,7 @@ from .ctc import CTCLoss, ctc_loss_from_logits  # noqa: F401
 from .ctc import CTCLoss, ctc_loss_from_logits  # noqa: F401
 from .encoder import ConformerEncoder, Linear  # noqa: F401
 from .prefetch import HostPrefetcher  # noqa: F401
+from .relpos import RelativePositionalEmbeddings  # noqa: F401
 from .patch import conformer_from_torchaudio, convsub_from_reference, patch_asrnn  # noqa: F401
 
 __version__ = "0.1.0"

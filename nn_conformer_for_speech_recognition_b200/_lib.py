@@ -73,6 +73,7 @@ SIGNATURES = {
     "b2c_dropout_epoch_use": [_P],
     "b2c_dropout_export_mask": [_I, _F, c_uint64, _L, _L, _P, _P],
     "b2c_cast_f32_bf16": [_P, _P, _L, _P],
+    "b2c_add_f32": [_P, _P, _P, _L, _P],
     "b2c_multi_cast_f32_bf16": [_P, _I, _L, _P],
     "b2c_scale_cast": [_P, _P, _L, _L, _F, _F, c_uint64, _P, _P],
     "b2c_colsum_bf16": [_P, _L, _L, _L, _P, _P],

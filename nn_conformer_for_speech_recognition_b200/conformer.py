@@ -268,8 +268,12 @@ class Conformer(nn.Module):
 
     def __init__(self, input_dim: int, num_heads: int, ffn_dim: int, num_layers: int,
                  depthwise_conv_kernel_size: int, dropout: float = 0.0, use_group_norm: bool = False,
-                 convolution_first: bool = False, rel_att: bool = False):
+                 convolution_first: bool = False, rel_att: bool = False, pos_table: Optional[torch.Tensor] = None):
         super().__init__()
+        # pos_table: the reference's own positional variant (unused_lib/conformer.py:101-103): a table from
+        # relpos.RelativePositionalEmbeddings, one row per flattened token, ADDED to the attention branch's input in front
+        # of its LayerNorm in every layer (a constant: not a parameter, not in the state_dict)
+        self.pos_table = None if pos_table is None else pos_table.detach().to(torch.float32).contiguous()
         if input_dim % num_heads != 0:
             raise AssertionError("embed_dim must be divisible by num_heads")
         self.conformer_layers = nn.ModuleList([
@@ -356,7 +360,7 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
     dev = x.device
     save = train_state is not None
     bf = torch.bfloat16
-    if not save and not bn_train and not force_two_pass and not model.rel_att and _LAYER_CALLS:
+    if not save and not bn_train and not force_two_pass and not model.rel_att and model.pos_table is None and _LAYER_CALLS:
         # eval: ONE C call per layer (b2c_conformer_layer_eval enqueues the same 20 launches): the per-launch Python /
         # ctypes cost otherwise exceeds the GPU time of a layer in the eager inference / NST sweep path
         import ctypes
@@ -409,8 +413,17 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
         pw = None
         if rel:            # Pw = linear_pos(PE): [Rp, H*64] projected relative embeddings of this layer
             pw = ops.gemm(pe, w["self_attn.linear_pos.weight"], M=pe.shape[0], N=Hd, K=d)
+        x_att = x                              # input of the attention LayerNorm (the residual below stays x)
+        if model.pos_table is not None:        # x + E, unused_lib/conformer.py:101
+            E = model.pos_table
+            if E.shape[-1] != d or E.shape[0] < M:
+                raise ValueError(f"pos_table must be (>= {M}, {d}); got {tuple(E.shape)}")
+            if E.device != dev:
+                E = model.pos_table = E.to(dev)
+            x_att = torch.empty_like(x)
+            _lib.call("b2c_add_f32", x.data_ptr(), E.data_ptr(), x_att.data_ptr(), M * d, _lib.stream_ptr())
         if save:
-            a, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, save_stats=True)
+            a, mean, rstd = ops.layernorm_fwd(x_att, ln_w, ln_b, save_stats=True)
             qkv = ops.gemm(a, w["self_attn.in_proj_weight"], M=M, N=nq * Hd, K=d, bias=w["in_bias"])
             if rel:
                 att, lse = ops.attention_rel_fwd(qkv, pw, lengths_i32, B, T, H, scale, save_lse=True, drop_p=drop_p,
@@ -419,10 +432,10 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
                 att, lse = ops.attention_fwd(qkv, lengths_i32, B, T, H, scale, save_lse=True, drop_p=drop_p, drop_seed=sd + 4)
             x_out = ops.gemm(att, w["self_attn.out_proj.weight"], M=M, N=d, K=Hd, bias=P("self_attn.out_proj.bias"),
                              resid=x, out_dtype=torch.float32, drop_p=drop_p, drop_seed=sd + 5)
-            st["attn"] = dict(x=x, a=a, mean=mean, rstd=rstd, qkv=qkv, att=att, lse=lse, pw=pw)
+            st["attn"] = dict(x=x_att, a=a, mean=mean, rstd=rstd, qkv=qkv, att=att, lse=lse, pw=pw)
             x = x_out
         else:
-            ops.layernorm_fwd(x, ln_w, ln_b, out=a_buf)
+            ops.layernorm_fwd(x_att, ln_w, ln_b, out=a_buf)
             ops.gemm(a_buf, w["self_attn.in_proj_weight"], M=M, N=nq * Hd, K=d, bias=w["in_bias"], out=qkv_buf)
             att = (ops.attention_rel_fwd(qkv_buf, pw, lengths_i32, B, T, H, scale) if rel
                    else ops.attention_fwd(qkv_buf, lengths_i32, B, T, H, scale))

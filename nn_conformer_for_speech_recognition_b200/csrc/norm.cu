@@ -424,6 +424,32 @@ extern "C" int b2c_layernorm_bwd_cast(const void* dy, int dy_dtype, const float*
   return layernorm_bwd_launch(dy, dy_dtype, x, gamma, mean, rstd, dx, dx_accumulate, dgamma, dbeta, rows, d, &c, stream);
 }
 
+namespace b2c {
+// out[i] = x[i] + e[i]  (fp32, float4): `x = x + rel_pos_emb` in front of the attention LayerNorm of the reference's own
+// positional variant (/root/reference/unused_lib/conformer.py:101-103; table = RelativePositionalEmbeddings, one row per
+// flattened token).  n elements; e holds at least n.
+__global__ void __launch_bounds__(256) add_f32_kernel(const float4* __restrict__ x, const float4* __restrict__ e,
+                                                     float4* __restrict__ out, int64_t n4) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 a = x[i], b = e[i];
+    out[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+}  // namespace b2c
+extern "C" int b2c_add_f32(const float* x, const float* e, float* out, int64_t n, void* stream) {
+  B2C_REQUIRE(x && e && out && n > 0 && n % 4 == 0, "b2c_add_f32: null pointer or n not a multiple of 4");
+  B2C_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+              "b2c_add_f32: pointers must be 16-byte aligned");
+  const int64_t n4 = n / 4;
+  const int grid = static_cast<int>(n4 / 256 + 1 < 8 * 148 ? n4 / 256 + 1 : 8 * 148);
+  b2c::add_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(x),
+                                                                         reinterpret_cast<const float4*>(e),
+                                                                         reinterpret_cast<float4*>(out), n4);
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
 extern "C" int b2c_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
   B2C_REQUIRE(src && dst, "b2c_cast_f32_bf16: null pointer");
   if (n <= 0) return 0;

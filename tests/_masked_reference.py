@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 
 
-def layer_forward(x, P, lengths, masks, num_heads, bn_train=True, bn_eps=1e-5):
+def layer_forward(x, P, lengths, masks, num_heads, bn_train=True, bn_eps=1e-5, pos=None):
     """x (B,T,d) fp64; P: dict of the layer's parameters/buffers (torchaudio state_dict keys without the layer prefix);
     masks: dict with optional scale tensors 'ffn1_h' (B,T,f), 'ffn1_o' (B,T,d), 'attn' (B,H,T,T), 'attn_o', 'conv_o',
     'ffn2_h', 'ffn2_o'.  Returns the layer output (B,T,d)."""
@@ -30,7 +30,8 @@ def layer_forward(x, P, lengths, masks, num_heads, bn_train=True, bn_eps=1e-5):
         return F.linear(h, P[pre + ".sequential.4.weight"], P[pre + ".sequential.4.bias"]) * m(pre + "_o")
 
     x = x + 0.5 * ffn(x, "ffn1")                                               # conformer.py:185-187
-    a = F.layer_norm(x, (d,), P["self_attn_layer_norm.weight"], P["self_attn_layer_norm.bias"])
+    xa = x if pos is None else x + pos[:B * T].view(B, T, d)        # unused_lib/conformer.py:101: x + rel_pos_emb in front of the LN
+    a = F.layer_norm(xa, (d,), P["self_attn_layer_norm.weight"], P["self_attn_layer_norm.bias"])
     qkv = F.linear(a, P["self_attn.in_proj_weight"], P["self_attn.in_proj_bias"])
     q, k, v = (t.view(B, T, H, dh).transpose(1, 2) for t in qkv.split(d, dim=-1))
     s = q @ k.transpose(-1, -2) / math.sqrt(dh)

@@ -212,3 +212,49 @@ def test_train_mode_without_autograd_still_applies_dropout():
         y_nodrop, _ = m(x, lens)
     assert (y_ng - y_g.detach()).abs().max().item() <= 5e-3
     assert (y_ng - y_nodrop).abs().mean().item() > 0.05         # dropout really was applied
+
+
+@gpu
+def test_reference_positional_table_added_in_front_of_the_attention_layernorm():
+    """The reference's own positional variant (unused_lib/conformer.py:101-103): `x + RelativePositionalEmbeddings(...)()` in
+    front of the attention LayerNorm, one table row per flattened token.  `Conformer(..., pos_table=E)` vs the fp64 layer
+    restatement with the same addition: forward and all gradients (bf16 tolerance of the module tests)."""
+    torch.manual_seed(21)
+    d, h, f, L, k, B, T = 128, 2, 256, 2, 31, 2, 140
+    lens = [140, 101]
+    E = b2c.RelativePositionalEmbeddings((B * T, d), True)().detach()
+    m = b2c.Conformer(d, h, f, L, k, 0.0, pos_table=E).cuda().train()
+    assert "pos_table" not in m.state_dict()
+    x = torch.randn(B, T, d)
+    w = torch.randn(B, T, d, dtype=torch.float64) * (torch.arange(T)[None, :, None] < torch.tensor(lens)[:, None, None])
+    sd0 = {kk: v.detach().cpu().clone() for kk, v in m.state_dict().items()}
+    xg = x.cuda().requires_grad_(True)
+    y, _ = m(xg, torch.tensor(lens).cuda())
+    (y.double() * w.cuda()).sum().backward()
+    xr = x.double().requires_grad_(True)
+    params, yr = [], xr
+    for li in range(L):
+        P = {kk: (v.requires_grad_(True) if v.is_floating_point() and "running" not in kk else v)
+             for kk, v in _layer_params(sd0, li).items()}
+        params.append(P)
+        yr = layer_forward(yr, P, lens, {}, h, pos=E.double())
+    (yr * w).sum().backward()
+    valid = (torch.arange(T)[None, :] < torch.tensor(lens)[:, None])
+    diff = (y.detach().cpu().double() - yr.detach())[valid].abs()
+    assert diff.max().item() <= 3e-2 and diff.mean().item() <= 5e-3
+    # and it is NOT a no-op: without the table the output differs
+    m2 = b2c.Conformer(d, h, f, L, k, 0.0).cuda().train()
+    m2.load_state_dict(m.state_dict())
+    y2, _ = m2(x.cuda(), torch.tensor(lens).cuda())
+    assert (y2 - y).abs().mean().item() > 0.05
+    _cmp_grad(xg.grad, xr.grad, "d loss / d x", 0.999, 3e-2, 1.0)
+    for li in range(L):
+        scale = float(params[li]["conv_module.sequential.2.weight"].grad.norm())
+        for name, pr in params[li].items():
+            if pr.is_floating_point() and pr.requires_grad:
+                _cmp_grad(dict(m.named_parameters())[f"conformer_layers.{li}.{name}"].grad, pr.grad, f"layer {li} {name}", 0.999, 3e-2, scale)
+    # eval path too (per-launch pipeline; the one-call-per-layer entry point has no table argument)
+    m.eval()
+    with torch.no_grad():
+        ye, _ = m(x.cuda(), torch.tensor(lens).cuda())
+    assert torch.isfinite(ye).all()

@@ -136,3 +136,23 @@ def test_encoder_output_lengths_formula():
     lens = torch.tensor([1500, 1000, 11, 10, 0])
     assert enc.output_lengths(lens).tolist() == [373, 248, 1, 0, 0]
     assert enc.bridge.weight.shape == (64, 128 * 18)
+
+
+def test_relative_positional_embeddings_table_is_bit_exact_with_the_reference():
+    """SURVEY 8 row a7 (the reference's own piece): `RelativePositionalEmbeddings(shape, relative)()` -- same constructor,
+    same call, bit-identical table (fixtures generated by running unused_lib/relativepositionalembeddings.py:17-32,
+    tests/golden/make_golden_relpos.py), `requires_grad` following `relative`, half-split sin|cos (not interleaved)."""
+    import hashlib
+    import numpy as np
+    from nn_conformer_for_speech_recognition_b200.relpos import RelativePositionalEmbeddings
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "relpos_table.npz"))
+    for shape in [(12, 16), (80, 256), (3, 5, 8)]:
+        t = RelativePositionalEmbeddings(shape, True)()
+        assert t.requires_grad and tuple(t.shape) == shape
+        assert np.array_equal(t.detach().numpy(), g["t_" + "x".join(map(str, shape))])
+    big = RelativePositionalEmbeddings((1280, 512), False)()
+    assert not big.requires_grad
+    assert hashlib.sha256(big.contiguous().numpy().tobytes()).digest() == bytes(g["sha_1280x512"])
+    t = RelativePositionalEmbeddings((4, 8))().detach()
+    assert torch.equal(t[0], torch.tensor([0., 0., 0., 0., 1., 1., 1., 1.]))          # p = 0: sin half zero, cos half one
+    assert abs(float(t[1, 0]) - float(torch.sin(torch.tensor(1.0)))) < 1e-7 and abs(float(t[1, 4]) - float(torch.cos(torch.tensor(1.0)))) < 1e-7
