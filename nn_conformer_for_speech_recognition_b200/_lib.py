@@ -224,6 +224,27 @@ def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 
 
+NVTX = os.environ.get("B2C_NVTX", "0") == "1"
+
+
+class nvtx:
+    """`with nvtx("layer3.mhsa"):` -- an NVTX range around the launches of one module stage when B2C_NVTX=1 (visible in
+    Nsight Systems / ncu --nvtx filters); a no-op otherwise (tracing hooks the reference lacks)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class epoch_scope:
     """`with epoch_scope(word):` -- kernels launched inside read the dropout epoch from `word` (a 1-element int64 device
     tensor written by b2c_dropout_epoch_snapshot) instead of the device counter.  None = no-op."""

@@ -81,7 +81,7 @@ class _ConformerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        with _lib.epoch_scope(ctx.epoch):
+        with _lib.epoch_scope(ctx.epoch), _lib.nvtx("conformer.backward"):
             return _ConformerFn._backward(ctx, dy)
 
     @staticmethod

@@ -406,7 +406,10 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
             return x_in
 
         # ---- 1. x += 0.5 * FFN1(x)                                                   conformer.py:185-187
-        x = ffn(x, "ffn1", 0)
+        with _lib.nvtx(f"layer{li}.ffn1"):
+            x = ffn(x, "ffn1", 0)
+        _nv = _lib.nvtx(f"layer{li}.mhsa")
+        _nv.__enter__()
 
         # ---- 2. x += out_proj(Attn(in_proj(LN(x))))                                  conformer.py:192-202
         ln_w, ln_b = P("self_attn_layer_norm.weight"), P("self_attn_layer_norm.bias")
@@ -442,7 +445,10 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
             ops.gemm(att, w["self_attn.out_proj.weight"], M=M, N=d, K=Hd, bias=P("self_attn.out_proj.bias"),
                      resid=x, out=x)
 
+        _nv.__exit__()
         # ---- 3. x += conv_module(x)                                                  conformer.py:168-174,77-88
+        _nv = _lib.nvtx(f"layer{li}.conv_module")
+        _nv.__enter__()
         bn = layer.conv_module.sequential[3]
         ln_w, ln_b = P("conv_module.layer_norm.weight"), P("conv_module.layer_norm.bias")
         wdw = P("conv_module.sequential.2.weight").view(d, k)
@@ -476,8 +482,10 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
             ops.gemm(c, w["conv_module.sequential.5.weight"], M=M, N=d, K=d, bias=P("conv_module.sequential.5.bias"),
                      resid=x, out=x)
 
+        _nv.__exit__()
         # ---- 4. x += 0.5 * FFN2(x)                                                   conformer.py:206-209
-        x = ffn(x, "ffn2", 12)
+        with _lib.nvtx(f"layer{li}.ffn2"):
+            x = ffn(x, "ffn2", 12)
 
         # ---- 5. x = LN(x)                                                            conformer.py:211
         ln_w, ln_b = P("final_layer_norm.weight"), P("final_layer_norm.bias")

@@ -84,6 +84,7 @@ template <bool REL>
 __global__ void __launch_bounds__(256, REL ? 1 : 2) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                                    const __grid_constant__ CUtensorMap tmPW,
                                                                    const AttnParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -102,8 +103,6 @@ __global__ void __launch_bounds__(256, REL ? 1 : 2) attn_fwd_kernel(const __grid
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid & 127, half = tid >> 7;
   const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
-  const int len = min(p.lengths[b], p.T);
-  const int nkb = (len + AT_BK - 1) / AT_BK;
   const int row_base = b * p.T;
 
   if (tid == 0) {
@@ -118,6 +117,9 @@ __global__ void __launch_bounds__(256, REL ? 1 : 2) attn_fwd_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  pdl_wait();                    // barrier init + TMEM allocation above overlapped the previous kernel's tail
+  const int len = min(p.lengths[b], p.T);
+  const int nkb = (len + AT_BK - 1) / AT_BK;
 
   // REL: relative positions of key block j start at r_lo = T-128-q0 + 128 j (negative / past-the-end rows: TMA zero fill)
   auto load_pw = [&](int j) {
@@ -346,30 +348,38 @@ struct AttnBwdParams {
   int64_t Rp;
 };
 
-// delta[b,h,t] = sum_c dO[row, h*64+c] * O[row, h*64+c]
+// delta[b,h,t] = sum_c dO[row, h*64+c] * O[row, h*64+c].  Eight lanes share one (row, head): each reads ONE 16-byte piece of
+// O and of dO (a warp instruction covers 4 x 128 contiguous bytes), three shuffles finish the dot product.
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
                                                         const __nv_bfloat16* __restrict__ dout, int64_t ld_out,
                                                         float* __restrict__ delta, int B, int T, int H) {
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;     // (row, h)
-  if (idx >= static_cast<int64_t>(B) * T * H) return;
+  pdl_trigger();
+  pdl_wait();
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int part = static_cast<int>(g & 7);
+  const int64_t idx = g >> 3;                                                          // (row, h)
+  const bool live = idx < static_cast<int64_t>(B) * T * H;
   const int h = static_cast<int>(idx % H);
-  const int64_t row = idx / H;
-  const uint4* po = reinterpret_cast<const uint4*>(o + row * ld_out + h * AT_DH);
-  const uint4* pd = reinterpret_cast<const uint4*>(dout + row * ld_out + h * AT_DH);
+  const int64_t row = live ? idx / H : 0;
   float acc = 0.f;
-#pragma unroll
-  for (int i = 0; i < AT_DH / 8; ++i) {
-    const uint4 a = po[i], b = pd[i];
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  if (live) {
+    const uint4 a = *reinterpret_cast<const uint4*>(o + row * ld_out + h * AT_DH + part * 8);
+    const uint4 d = *reinterpret_cast<const uint4*>(dout + row * ld_out + h * AT_DH + part * 8);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 x = unpack_bf16(aw[j]), y = unpack_bf16(bw[j]);
+      const float2 x = unpack_bf16(aw[j]), y = unpack_bf16(dw[j]);
       acc = fmaf(x.x, y.x, acc);
       acc = fmaf(x.y, y.y, acc);
     }
   }
-  const int b_ = static_cast<int>(row / T), t = static_cast<int>(row % T);
-  delta[(static_cast<int64_t>(b_) * H + h) * T + t] = acc;
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (live && part == 0) {
+    const int b_ = static_cast<int>(row / T), t = static_cast<int>(row % T);
+    delta[(static_cast<int64_t>(b_) * H + h) * T + t] = acc;
+  }
 }
 
 // Thread (row = tid & 127, column quarter cq = tid >> 7) turns 32 columns of its S row and dP row (TMEM) into
@@ -462,6 +472,8 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
                                                           const __grid_constant__ CUtensorMap tmDQ,
                                                           const __grid_constant__ CUtensorMap tmDKV,
                                                           const AttnBwdParams p, float* __restrict__ dq_f32) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -703,6 +715,8 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
 // dQ = sum over key blocks of the fp32 partial slabs [nkb][rows, H*64] -> the Q slab of dqkv (bf16, pitch ld)
 __global__ void __launch_bounds__(256) attn_dq_cast_kernel(const float* __restrict__ dq, __nv_bfloat16* __restrict__ dqkv,
                                                           int64_t rows, int cols, int64_t ld, int q_col, int nkb) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   const int64_t n = rows * cols;
   if (i >= n) return;
@@ -759,8 +773,8 @@ static int attention_fwd_launch(const void* qkv, int64_t ld, int64_t k_off, int6
   p.Tpad = (T + 3) & ~3;
   p.drop = make_drop(drop_p, drop_seed);
   dim3 grid((T + AT_BQ - 1) / AT_BQ, H, B);
-  if (rel) attn_fwd_kernel<true><<<grid, 256, ATTN_FWD_REL_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, tp, p);
-  else attn_fwd_kernel<false><<<grid, 256, ATTN_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, tp, p);
+  if (rel) B2C_CUDA(launch_k(attn_fwd_kernel<true>, dim3(grid), dim3(256), ATTN_FWD_REL_SMEM, static_cast<cudaStream_t>(stream), tm, tp, p));
+  else B2C_CUDA(launch_k(attn_fwd_kernel<false>, dim3(grid), dim3(256), ATTN_FWD_SMEM, static_cast<cudaStream_t>(stream), tm, tp, p));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -803,8 +817,8 @@ static int attention_bwd_launch(const void* qkv, int64_t ld, int64_t k_off, int6
   }
   const int64_t rows = static_cast<int64_t>(B) * T;
   const int64_t n = rows * H;
-  attn_delta_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), ld_out, delta, B, T, H);
+  B2C_CUDA(launch_k(attn_delta_kernel, dim3(static_cast<unsigned>((n * 8 + 255) / 256)), dim3(256), 0, st, 
+      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), ld_out, delta, B, T, H));
   AttnBwdParams p;
   p.lengths = lengths; p.lse = lse; p.delta = delta; p.dqkv = static_cast<__nv_bfloat16*>(dqkv); p.ld = ld;
   p.B = B; p.T = T; p.H = H;
@@ -824,11 +838,11 @@ static int attention_bwd_launch(const void* qkv, int64_t ld, int64_t k_off, int6
   if (int rc = get_tensor_map_3d(&tdkv, dqkv, 2, static_cast<uint64_t>(ld), static_cast<uint64_t>(T), static_cast<uint64_t>(B),
                                  static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(T) * ld * 2, 64, 128, true))
     return rc;
-  if (rel) attn_bwd_kernel<true><<<grid, 544, ATTN_BWD_SMEM, st>>>(tq, td, tdq, tdkv, p, dq_f32);
-  else attn_bwd_kernel<false><<<grid, 544, ATTN_BWD_SMEM, st>>>(tq, td, tdq, tdkv, p, dq_f32);
+  if (rel) B2C_CUDA(launch_k(attn_bwd_kernel<true>, dim3(grid), dim3(544), ATTN_BWD_SMEM, st, tq, td, tdq, tdkv, p, dq_f32));
+  else B2C_CUDA(launch_k(attn_bwd_kernel<false>, dim3(grid), dim3(544), ATTN_BWD_SMEM, st, tq, td, tdq, tdkv, p, dq_f32));
   const int64_t n8 = rows * H * AT_DH / 8;
-  attn_dq_cast_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, st>>>(dq_f32, static_cast<__nv_bfloat16*>(dqkv),
-                                                                               rows, H * AT_DH, ld, 0, (T + AT_BK - 1) / AT_BK);
+  B2C_CUDA(launch_k(attn_dq_cast_kernel, dim3(static_cast<unsigned>((n8 + 255) / 256)), dim3(256), 0, st, dq_f32, static_cast<__nv_bfloat16*>(dqkv),
+                                                                               rows, H * AT_DH, ld, 0, (T + AT_BK - 1) / AT_BK));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

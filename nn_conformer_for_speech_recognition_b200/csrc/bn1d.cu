@@ -18,6 +18,8 @@ namespace b2c {
 
 __global__ void __launch_bounds__(256) bn1d_stats_kernel(const __nv_bfloat16* __restrict__ h, double* __restrict__ stats,
                                                         int64_t rows, int C, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float red[];                       // [2][C]
   const int cg = C >> 3, rpi = 256 / cg;
   const int tr = threadIdx.x / cg, tg = threadIdx.x - tr * cg;
@@ -52,6 +54,8 @@ __global__ void __launch_bounds__(256) bn1d_apply_kernel(const __nv_bfloat16* __
                                                         const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ y, int64_t rows,
                                                         int C) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t n8 = rows * (C >> 3);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -76,6 +80,8 @@ __global__ void __launch_bounds__(256) bn1d_bwd_reduce_kernel(const float* __res
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              double* __restrict__ sums, int64_t rows, int C,
                                                              int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float red[];                       // [2][C]
   const int cg = C >> 3, rpi = 256 / cg;
   const int tr = threadIdx.x / cg, tg = threadIdx.x - tr * cg;
@@ -120,6 +126,8 @@ __global__ void __launch_bounds__(256) bn1d_bwd_apply_kernel(const float* __rest
                                                             const double* __restrict__ sums, double inv_count, int train,
                                                             __nv_bfloat16* __restrict__ dz, float* __restrict__ colsum,
                                                             int64_t rows, int C, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float red[];                       // [C]
   const int cg = C >> 3, rpi = 256 / cg;
   const int tr = threadIdx.x / cg, tg = threadIdx.x - tr * cg;
@@ -189,8 +197,8 @@ extern "C" int b2c_bn1d_stats(const void* h, double* stats, int64_t rows, int C,
   B2C_BN1D_CHECK("b2c_bn1d_stats");
   int64_t rpb;
   const int grid = bn1d_grid(rows, C, &rpb);
-  bn1d_stats_kernel<<<grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(h), stats, rows, C, static_cast<int>(rpb));
+  B2C_CUDA(launch_k(bn1d_stats_kernel, dim3(grid), dim3(256), 2 * C * sizeof(float), static_cast<cudaStream_t>(stream), 
+      static_cast<const __nv_bfloat16*>(h), stats, rows, C, static_cast<int>(rpb)));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -201,8 +209,8 @@ extern "C" int b2c_bn1d_apply(const void* h, const float* mean, const float* rst
   B2C_BN1D_CHECK("b2c_bn1d_apply");
   const int64_t n8 = rows * (C / 8);
   const int grid = static_cast<int>(n8 / 256 + 1 < 8 * 148 ? n8 / 256 + 1 : 8 * 148);
-  bn1d_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(h), mean, rstd,
-                                                                         gamma, beta, y, rows, C);
+  B2C_CUDA(launch_k(bn1d_apply_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(h), mean, rstd,
+                                                                         gamma, beta, y, rows, C));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -213,8 +221,8 @@ extern "C" int b2c_bn1d_bwd_reduce(const float* dy, const void* h, const float* 
   B2C_BN1D_CHECK("b2c_bn1d_bwd_reduce");
   int64_t rpb;
   const int grid = bn1d_grid(rows, C, &rpb);
-  bn1d_bwd_reduce_kernel<<<grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      dy, static_cast<const __nv_bfloat16*>(h), mean, rstd, sums, rows, C, static_cast<int>(rpb));
+  B2C_CUDA(launch_k(bn1d_bwd_reduce_kernel, dim3(grid), dim3(256), 2 * C * sizeof(float), static_cast<cudaStream_t>(stream), 
+      dy, static_cast<const __nv_bfloat16*>(h), mean, rstd, sums, rows, C, static_cast<int>(rpb)));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -226,9 +234,9 @@ extern "C" int b2c_bn1d_bwd_apply(const float* dy, const void* h, const void* z,
   B2C_BN1D_CHECK("b2c_bn1d_bwd_apply");
   int64_t rpb;
   const int grid = bn1d_grid(rows, C, &rpb);
-  bn1d_bwd_apply_kernel<<<grid, 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  B2C_CUDA(launch_k(bn1d_bwd_apply_kernel, dim3(grid), dim3(256), C * sizeof(float), static_cast<cudaStream_t>(stream), 
       dy, static_cast<const __nv_bfloat16*>(h), static_cast<const __nv_bfloat16*>(z), mean, rstd, gamma, sums,
-      1.0 / static_cast<double>(rows), train, static_cast<__nv_bfloat16*>(dz), colsum, rows, C, static_cast<int>(rpb));
+      1.0 / static_cast<double>(rows), train, static_cast<__nv_bfloat16*>(dz), colsum, rows, C, static_cast<int>(rpb)));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

@@ -36,8 +36,37 @@ int get_tensor_map_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64
                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, bool swizzle128);
 
 int num_sms();
+bool pdl_enabled();       // host.cpp: programmatic dependent launch on unless B2C_PDL=0
 
 #ifdef __CUDACC__
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The step is ~750 short kernels in one stream / CUDA graph; between two
+// dependent kernels the GPU otherwise drains completely, then pays the launch latency and the next kernel's prologue
+// (barrier init, TMEM allocation, descriptor prefetch) with every SM idle.  Every kernel of this library is launched with
+// programmaticStreamSerializationAllowed: its CTAs become resident while the previous kernel's last wave still runs, execute
+// their prologue, and block in pdl_wait() until the previous grid has COMPLETED and its memory is visible.
+// Contract for every kernel launched through launch_k():
+//   pdl_trigger() first (lets the NEXT kernel start being scheduled as soon as all CTAs of this one have started), and
+//   pdl_wait() before the first global-memory access that is not a kernel parameter / tensor map.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------------------------
 // small device utilities
 // ----------------------------------------------------------------------------------------------

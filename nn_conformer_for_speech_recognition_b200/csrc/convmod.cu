@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(256, 3) convmod_fwd_kernel(const __nv_bfloat16
                                                           const float* __restrict__ bn_var, float eps,
                                                           __nv_bfloat16* __restrict__ out, double* __restrict__ stats,
                                                           int T, int d, int k_rt) {
+  pdl_trigger();
+  pdl_wait();
   const int k = KT ? KT : k_rt;
   constexpr int NTAP = KT ? KT : CM_MAXK;
   extern __shared__ float2 sG[];                 // [(CM_TT + k - 1)][32] float2, then taps [k][64] float
@@ -202,6 +204,8 @@ __global__ void __launch_bounds__(256, 3) convmod_fwd_kernel(const __nv_bfloat16
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, float eps, float momentum,
                                    float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int d) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d) return;
   const double mu = stats[c] / count;
@@ -222,6 +226,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
                                                       const float* __restrict__ rstd, const float* __restrict__ bn_w,
                                                       const float* __restrict__ bn_b, __nv_bfloat16* __restrict__ out,
                                                       int64_t rows, int d, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = d >> 3, rpi = 256 / cg;                 // channel groups per row, rows per CTA step
   const int tr = threadIdx.x / cg, tg = threadIdx.x - tr * cg;
   if (tr >= rpi) return;
@@ -276,6 +282,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const __nv_bfloat
                                                            const float* __restrict__ bn_w, const float* __restrict__ bn_b,
                                                            double* __restrict__ sums, int64_t rows, int d,
                                                            int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   // thread = fixed group of 8 channels walking down this CTA's rows (16-byte loads, 2 x 4 rows in flight); the CTA's
   // partial sums meet in shared memory and leave as one fp64 atomic per channel
   extern __shared__ float red_dyn[];                     // [2][d]
@@ -353,6 +361,8 @@ __global__ void __launch_bounds__(256, 2) convmod_bwd_kernel(const __nv_bfloat16
                                                           float* __restrict__ dwdw, float* __restrict__ dbdw,
                                                           float* __restrict__ dbn_w, float* __restrict__ dbn_b,
                                                           float* __restrict__ dbias_u, int T, int d, int k_rt) {
+  pdl_trigger();
+  pdl_wait();
   const int k = KT ? KT : k_rt;
   constexpr int NT = KT ? KT : CM_MAXK;
   extern __shared__ float2 sbuf[];
@@ -570,9 +580,9 @@ extern "C" int b2c_convmod_eval_fwd(const void* u, const float* wdw, const float
   const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) + CM_WP * k * sizeof(float);
   if (int rc = convmod_fwd_attr()) return rc;
 #define B2C_CM_FWD(KT_)                                                                                          \
-  convmod_fwd_kernel<0, KT_><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(                           \
+  B2C_CUDA(launch_k(convmod_fwd_kernel<0, KT_>, dim3(grid), dim3(256), smem, static_cast<cudaStream_t>(stream),                            \
       static_cast<const __nv_bfloat16*>(u), wdw, bdw, bn_w, bn_b, bn_mean, bn_var, eps, static_cast<__nv_bfloat16*>(out), \
-      nullptr, T, d, k)
+      nullptr, T, d, k))
   if (k == 31) B2C_CM_FWD(31); else if (k == 33) B2C_CM_FWD(33); else B2C_CM_FWD(0);
 #undef B2C_CM_FWD
   B2C_CUDA(cudaGetLastError());
@@ -587,9 +597,9 @@ extern "C" int b2c_convmod_dw_fwd(const void* u, const float* wdw, const float* 
   const size_t smem = static_cast<size_t>(CM_TT + k - 1) * 32 * sizeof(float2) + CM_WP * k * sizeof(float);
   if (int rc = convmod_fwd_attr()) return rc;
 #define B2C_CM_FWD(KT_)                                                                                          \
-  convmod_fwd_kernel<1, KT_><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(                           \
+  B2C_CUDA(launch_k(convmod_fwd_kernel<1, KT_>, dim3(grid), dim3(256), smem, static_cast<cudaStream_t>(stream),                            \
       static_cast<const __nv_bfloat16*>(u), wdw, bdw, nullptr, nullptr, nullptr, nullptr, 0.f,                   \
-      static_cast<__nv_bfloat16*>(y), stats, T, d, k)
+      static_cast<__nv_bfloat16*>(y), stats, T, d, k))
   if (k == 31) B2C_CM_FWD(31); else if (k == 33) B2C_CM_FWD(33); else B2C_CM_FWD(0);
 #undef B2C_CM_FWD
   B2C_CUDA(cudaGetLastError());
@@ -600,8 +610,8 @@ extern "C" int b2c_convmod_bn_finalize(const double* stats, int64_t count, float
                                        float* rstd, float* running_mean, float* running_var, int d, void* stream) {
   B2C_REQUIRE(stats && mean && rstd && d > 0 && count > 0, "b2c_convmod_bn_finalize: bad argument");
   B2C_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "b2c_convmod_bn_finalize: running stats mismatch");
-  bn_finalize_kernel<<<(d + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, static_cast<double>(count), eps, momentum, mean, rstd, running_mean, running_var, d);
+  B2C_CUDA(launch_k(bn_finalize_kernel, dim3((d + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), 
+      stats, static_cast<double>(count), eps, momentum, mean, rstd, running_mean, running_var, d));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -617,9 +627,9 @@ extern "C" int b2c_convmod_bn_apply(const void* y, const float* mean, const floa
   int64_t rpb = (rows + nblk - 1) / nblk;
   rpb = ((rpb + rpi - 1) / rpi) * rpi;
   nblk = (rows + rpb - 1) / rpb;
-  bn_apply_kernel<<<static_cast<unsigned>(nblk), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  B2C_CUDA(launch_k(bn_apply_kernel, dim3(static_cast<unsigned>(nblk)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(y), mean, rstd, bn_w, bn_b, static_cast<__nv_bfloat16*>(out), rows, d,
-      static_cast<int>(rpb));
+      static_cast<int>(rpb)));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -637,9 +647,9 @@ extern "C" int b2c_convmod_bn_bwd_reduce(const void* dc, const void* y, const fl
   int64_t rpb = (rows + nblk - 1) / nblk;
   rpb = ((rpb + rpi - 1) / rpi) * rpi;
   nblk = (rows + rpb - 1) / rpb;
-  bn_bwd_reduce_kernel<<<static_cast<unsigned>(nblk), 256, 2 * d * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  B2C_CUDA(launch_k(bn_bwd_reduce_kernel, dim3(static_cast<unsigned>(nblk)), dim3(256), 2 * d * sizeof(float), static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dc), static_cast<const __nv_bfloat16*>(y), mean, rstd, bn_w, bn_b, sums, rows, d,
-      static_cast<int>(rpb));
+      static_cast<int>(rpb)));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -666,14 +676,17 @@ extern "C" int b2c_convmod_dw_bwd(const void* dc, const void* y, const void* u, 
   }
   const double inv_count = 1.0 / (static_cast<double>(B) * T);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  auto args = [&](auto kern) {
-    kern<<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(dc), static_cast<const __nv_bfloat16*>(y),
+  auto args = [&](auto kern) -> int {
+    B2C_CUDA(launch_k(kern, dim3(grid), dim3(256), smem, st, static_cast<const __nv_bfloat16*>(dc), static_cast<const __nv_bfloat16*>(y),
                                   static_cast<const __nv_bfloat16*>(u), mean, rstd, bn_w, bn_b, sums, inv_count, wdw,
-                                  static_cast<__nv_bfloat16*>(du), dwdw, dbdw, dbn_w, dbn_b, dbias_u, T, d, k);
+                                  static_cast<__nv_bfloat16*>(du), dwdw, dbdw, dbn_w, dbn_b, dbias_u, T, d, k));
+    return 0;
   };
-  if (k == 31)      { if (bn_train) args(convmod_bwd_kernel<true, 31>); else args(convmod_bwd_kernel<false, 31>); }
-  else if (k == 33) { if (bn_train) args(convmod_bwd_kernel<true, 33>); else args(convmod_bwd_kernel<false, 33>); }
-  else              { if (bn_train) args(convmod_bwd_kernel<true, 0>); else args(convmod_bwd_kernel<false, 0>); }
+  int rc;
+  if (k == 31)      rc = bn_train ? args(convmod_bwd_kernel<true, 31>) : args(convmod_bwd_kernel<false, 31>);
+  else if (k == 33) rc = bn_train ? args(convmod_bwd_kernel<true, 33>) : args(convmod_bwd_kernel<false, 33>);
+  else              rc = bn_train ? args(convmod_bwd_kernel<true, 0>) : args(convmod_bwd_kernel<false, 0>);
+  if (rc) return rc;
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

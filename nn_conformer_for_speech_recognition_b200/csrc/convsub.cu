@@ -61,6 +61,8 @@ __device__ __forceinline__ uint32_t pow2_cols(int n) {
 }
 
 __global__ void __launch_bounds__(256) convsub_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ConvSubParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(256) convsub_fwd_kernel(const __grid_constant_
 
 // dWc[c, kk] += sum over this CTA's tiles of dout[m, c] * patch[m, kk]   (M-dim = c, N-dim = kk, reduction = frames)
 __global__ void __launch_bounds__(256) convsub_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, const ConvSubParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -224,6 +228,8 @@ constexpr int CS_SPLIT = 8;
 __global__ void __launch_bounds__(256) compose_w_kernel(const float* __restrict__ W1, const float* __restrict__ W2, int C1,
                                                         int C2, int k1, int s1, int k2, int kc, int KP,
                                                         __nv_bfloat16* __restrict__ Wc, float* __restrict__ Wc_f32) {
+  pdl_trigger();
+  pdl_wait();
   const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
   const int idx = gidx / CS_SPLIT, part = gidx % CS_SPLIT;    // (o, kk) over C2 x KP; part = which slice of the channels
   const bool live = idx < C2 * KP;
@@ -254,6 +260,8 @@ __global__ void __launch_bounds__(256) compose_w_kernel(const float* __restrict_
 
 __global__ void compose_b_kernel(const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
                                  int C1, int C2, int k2, float* __restrict__ bc) {
+  pdl_trigger();
+  pdl_wait();
   const int o = blockIdx.x, lane = threadIdx.x;               // one warp per output channel
   float acc = 0.f;
   const int n = C1 * k2 * k2;
@@ -266,6 +274,8 @@ __global__ void __launch_bounds__(256) compose_bwd_w1_kernel(const float* __rest
                                                              const float* __restrict__ W2, int C1, int C2, int k1, int s1,
                                                              int k2, int kc, int KP, float* __restrict__ dW1,
                                                              float* __restrict__ db1) {
+  pdl_trigger();
+  pdl_wait();
   const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
   const int idx = gidx / CS_SPLIT, part = gidx % CS_SPLIT;    // (c, p, q) plus one extra slot per c for db1; part = slice of o
   const int per_c = k1 * k1 + 1;
@@ -294,6 +304,8 @@ __global__ void __launch_bounds__(256) compose_bwd_w1_kernel(const float* __rest
 __global__ void compose_bwd_w2_kernel(const float* __restrict__ dWc, const float* __restrict__ dbc,
                                       const float* __restrict__ W1, const float* __restrict__ b1, int C1, int C2, int k1,
                                       int s1, int k2, int kc, int KP, float* __restrict__ dW2, float* __restrict__ db2) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // (o, c, u, v)
   if (idx >= static_cast<int64_t>(C2) * C1 * k2 * k2) return;
   const int v = idx % k2, u = (idx / k2) % k2;
@@ -328,9 +340,9 @@ extern "C" int b2c_convsub_compose(const float* W1, const float* b1, const float
   const int kc = k1 + (k2 - 1) * s1;
   B2C_REQUIRE(KP >= kc * kc, "b2c_convsub_compose: KP too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  compose_w_kernel<<<(C2 * KP * CS_SPLIT + 255) / 256, 256, 0, st>>>(W1, W2, C1, C2, k1, s1, k2, kc, KP,
-                                                         static_cast<__nv_bfloat16*>(Wc), Wc_f32);
-  compose_b_kernel<<<C2, 32, 0, st>>>(b1, W2, b2, C1, C2, k2, bc);
+  B2C_CUDA(launch_k(compose_w_kernel, dim3((C2 * KP * CS_SPLIT + 255) / 256), dim3(256), 0, st, W1, W2, C1, C2, k1, s1, k2, kc, KP,
+                                                         static_cast<__nv_bfloat16*>(Wc), Wc_f32));
+  B2C_CUDA(launch_k(compose_b_kernel, dim3(C2), dim3(32), 0, st, b1, W2, b2, C1, C2, k2, bc));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -350,7 +362,7 @@ extern "C" int b2c_convsub_fwd(const float* x, const void* Wc, const float* bc, 
     configured = smem;
   }
   dim3 grid(p.tiles_t, p.Fo, B);
-  convsub_fwd_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(tm, p);
+  B2C_CUDA(launch_k(convsub_fwd_kernel, dim3(grid), dim3(256), smem, static_cast<cudaStream_t>(stream), tm, p));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -375,7 +387,7 @@ extern "C" int b2c_convsub_wgrad(const float* x, const void* dout, float* dWc, i
   int gx = num_sms() * 2 / (C2 / 128);
   if (gx > p.total_tiles) gx = p.total_tiles;
   dim3 grid(gx, C2 / 128);
-  convsub_wgrad_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(tm, p);
+  B2C_CUDA(launch_k(convsub_wgrad_kernel, dim3(grid), dim3(256), smem, static_cast<cudaStream_t>(stream), tm, p));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -387,10 +399,10 @@ extern "C" int b2c_convsub_compose_bwd(const float* dWc, const float* dbc, const
   const int kc = k1 + (k2 - 1) * s1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n1 = C1 * (k1 * k1 + 1);
-  compose_bwd_w1_kernel<<<(n1 * CS_SPLIT + 255) / 256, 256, 0, st>>>(dWc, dbc, W2, C1, C2, k1, s1, k2, kc, KP, dW1, db1);
+  B2C_CUDA(launch_k(compose_bwd_w1_kernel, dim3((n1 * CS_SPLIT + 255) / 256), dim3(256), 0, st, dWc, dbc, W2, C1, C2, k1, s1, k2, kc, KP, dW1, db1));
   const int64_t n2 = static_cast<int64_t>(C2) * C1 * k2 * k2;
-  compose_bwd_w2_kernel<<<static_cast<unsigned>((n2 + 127) / 128), 128, 0, st>>>(dWc, dbc, W1, b1, C1, C2, k1, s1, k2,
-                                                                                  kc, KP, dW2, db2);
+  B2C_CUDA(launch_k(compose_bwd_w2_kernel, dim3(static_cast<unsigned>((n2 + 127) / 128)), dim3(128), 0, st, dWc, dbc, W1, b1, C1, C2, k1, s1, k2,
+                                                                                  kc, KP, dW2, db2));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

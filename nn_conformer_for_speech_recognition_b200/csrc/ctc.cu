@@ -54,12 +54,15 @@ struct CtcParams {
   float* grad;               // [B, T, V]
   const float* grad_out;     // [1] device scalar, or nullptr = 1
   int B, T, V, Smax, SP, blank, zero_infinity;
+  int stage_lp;              // 1: the lattice kernel stages an utterance's emissions in shared memory
 };
 
 __device__ __forceinline__ int ext_label(const int32_t* tgt, int s, int blank) { return (s & 1) ? tgt[s >> 1] : blank; }
 
 // ---- pass 1: row log-sum-exp + gather of the extended labels' log-probabilities --------------------------------------
 __global__ void __launch_bounds__(256) ctc_rows_kernel(const CtcParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   if (row >= static_cast<int64_t>(p.B) * p.T) return;
@@ -92,6 +95,8 @@ __global__ void __launch_bounds__(256) ctc_rows_kernel(const CtcParams p) {
 
 // ---- pass 2: alpha and beta recursions of one utterance, concurrently ------------------------------------------------
 __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];                       // [2 halves][2 rows][SP]
   const int b = blockIdx.x;
   const int SP = p.SP;
@@ -110,7 +115,19 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcParams p) {
     else skip = s + 2 < S1 && tgt[(s >> 1) + 1] != lab;
   }
   float* buf = sm + half * 2 * SP;
-  const float* lp = p.lpc + static_cast<int64_t>(b) * p.T * SP + s;
+  // The emissions of this utterance ([len][SP] floats, 95 KB at T = 373, S' <= 64) are staged in shared memory by ONE
+  // cooperative, coalesced sweep: read from global inside the recursion, every time step exposed a full memory latency
+  // (~1 k cycles cold) to a loop whose arithmetic is ~100 cycles.  `stage` is false when they do not fit.
+  float* slp = sm + 4 * SP;
+  const bool stage = p.stage_lp != 0;
+  const float* lpg = p.lpc + static_cast<int64_t>(b) * p.T * SP;
+  if (stage) {
+    const float4* src = reinterpret_cast<const float4*>(lpg);
+    float4* dst4 = reinterpret_cast<float4*>(slp);
+    for (int i = threadIdx.x; i < len * SP / 4; i += blockDim.x) dst4[i] = src[i];
+    __syncthreads();
+  }
+  const float* lp = (stage ? slp : lpg) + s;
   float* dst = (half ? p.lb : p.la) + static_cast<int64_t>(b) * p.T * SP + s;
   const int bar_id = 1 + half;
   const int nthr = (SP + 31) & ~31;                   // threads of one half, rounded up to whole warps (SP % 32 == 0)
@@ -133,7 +150,7 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcParams p) {
       const float* prev = buf + ((i - 1) & 1) * SP;
       float* cur = buf + (i & 1) * SP;
       const float e = e_next;
-      if (live && i + 1 < len) e_next = lp[static_cast<int64_t>(half ? t - 1 : t + 1) * SP];   // prefetch the next step's emission
+      if (live && i + 1 < len) e_next = lp[static_cast<int64_t>(half ? t - 1 : t + 1) * SP];   // the next step's emission
       float nv = CTC_NEG_INF;
       if (live) {
         const float a0 = prev[s];
@@ -184,6 +201,8 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcParams p) {
 
 // ---- pass 3: gradient w.r.t. the logits ----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ctc_grad_kernel(const CtcParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   if (row >= static_cast<int64_t>(p.B) * p.T) return;
@@ -226,7 +245,8 @@ using namespace b2c;
 
 extern "C" size_t b2c_ctc_workspace(int B, int T, int Smax) {
   const size_t SP = static_cast<size_t>((2 * Smax + 1 + 31) & ~31);
-  return (static_cast<size_t>(B) * T * (1 + 3 * SP) + B) * sizeof(float);
+  const size_t rows = static_cast<size_t>(B) * T, rows4 = (rows + 3) & ~static_cast<size_t>(3);   // keeps lpc / la / lb 16-byte aligned
+  return (rows4 + rows * 3 * SP + B) * sizeof(float);
 }
 
 // phases: 1 = forward (row pass + lattice: loss, nll, state posteriors kept in the workspace), 2 = gradient pass only (the
@@ -247,22 +267,33 @@ extern "C" int b2c_ctc_loss(const float* logits, const int32_t* targets, const i
   const int SP = (2 * Smax + 1 + 31) & ~31;
   B2C_REQUIRE(2 * SP <= 1024, "b2c_ctc_loss: targets longer than 255 labels are not supported");
   B2C_REQUIRE(workspace_bytes >= b2c_ctc_workspace(B, T, Smax), "b2c_ctc_loss: workspace too small");
+  B2C_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "b2c_ctc_loss: workspace must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CtcParams p;
   float* w = static_cast<float*>(workspace);
   const size_t rows = static_cast<size_t>(B) * T;
   p.logits = logits; p.targets = targets; p.in_lens = input_lens; p.tgt_lens = target_lens;
-  p.lse = w; p.lpc = w + rows; p.la = p.lpc + rows * SP; p.lb = p.la + rows * SP;
+  p.lse = w; p.lpc = w + ((rows + 3) & ~static_cast<size_t>(3)); p.la = p.lpc + rows * SP; p.lb = p.la + rows * SP;
   p.nll = nll ? nll : p.lb + rows * SP;
   p.loss = loss; p.grad = grad_logits; p.grad_out = grad_out;
   p.B = B; p.T = T; p.V = V; p.Smax = Smax; p.SP = SP; p.blank = blank; p.zero_infinity = zero_infinity;
+  p.stage_lp = 0;
   const unsigned row_blocks = static_cast<unsigned>((rows + 7) / 8);
   if (phases & 1) {
     B2C_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
-    ctc_rows_kernel<<<row_blocks, 256, 0, st>>>(p);
-    ctc_lattice_kernel<<<B, 2 * SP, 4 * SP * sizeof(float), st>>>(p);
+    B2C_CUDA(launch_k(ctc_rows_kernel, dim3(row_blocks), dim3(256), 0, st, p));
+    size_t lat_smem = 4 * SP * sizeof(float);
+    const size_t want = lat_smem + static_cast<size_t>(T) * SP * sizeof(float);
+    p.stage_lp = want <= 200 * 1024 ? 1 : 0;
+    if (p.stage_lp) lat_smem = want;
+    static size_t configured = 0;
+    if (lat_smem > 48 * 1024 && lat_smem > configured) {
+      B2C_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 4096));
+      configured = 200 * 1024 + 4096;
+    }
+    B2C_CUDA(launch_k(ctc_lattice_kernel, dim3(B), dim3(2 * SP), lat_smem, st, p));
   }
-  if (phases & 2) ctc_grad_kernel<<<row_blocks, 256, 0, st>>>(p);
+  if (phases & 2) B2C_CUDA(launch_k(ctc_grad_kernel, dim3(row_blocks), dim3(256), 0, st, p));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

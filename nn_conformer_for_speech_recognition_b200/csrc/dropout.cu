@@ -38,16 +38,22 @@ uint64_t* dropout_epoch_ptr() {
 const uint64_t* dropout_epoch_current() { return g_epoch_use ? g_epoch_use : dropout_epoch_ptr(); }
 
 __global__ void epoch_bump_kernel(uint64_t* e, uint64_t* snap) {
+  pdl_trigger();
+  pdl_wait();
   const uint64_t v = *e + 1;
   *e = v;
   if (snap) *snap = v;
 }
-__global__ void epoch_set_kernel(uint64_t* e, uint64_t v) { *e = v; }
+__global__ void epoch_set_kernel(uint64_t* e, uint64_t v) {
+  pdl_trigger();
+  pdl_wait(); *e = v; }
 
 // kind 0: elementwise sites -- the scale drop_scale4g applies to element (r, c) of a [rows, cols] tensor
 //         (GEMM residual epilogues, scale_cast, layernorm_bwd_cast; index = r*cols + c)
 // kind 1: attention probabilities -- rows = B*H*T query rows (row_lin = (b*H + h)*T + q), cols = T keys
 __global__ void export_mask_kernel(int kind, DropCfg drop, int64_t rows, int64_t cols, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   drop = drop_resolve(drop);
   const int64_t cp = (cols + 3) & ~static_cast<int64_t>(3);      // the attention kernels' even row pitch (Tpad)
   const int64_t n4 = rows * (cp >> 2);
@@ -77,7 +83,7 @@ using namespace b2c;
 extern "C" int b2c_dropout_epoch_bump(void* stream) {
   uint64_t* e = dropout_epoch_ptr();
   B2C_REQUIRE(e != nullptr, "b2c_dropout_epoch_bump: could not allocate the epoch word");
-  epoch_bump_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(e, nullptr);
+  B2C_CUDA(launch_k(epoch_bump_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), e, nullptr));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -85,7 +91,7 @@ extern "C" int b2c_dropout_epoch_bump(void* stream) {
 extern "C" int b2c_dropout_epoch_snapshot(uint64_t* dst, void* stream) {
   uint64_t* e = dropout_epoch_ptr();
   B2C_REQUIRE(e != nullptr && dst != nullptr, "b2c_dropout_epoch_snapshot: null pointer");
-  epoch_bump_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(e, dst);
+  B2C_CUDA(launch_k(epoch_bump_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), e, dst));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -93,7 +99,7 @@ extern "C" int b2c_dropout_epoch_snapshot(uint64_t* dst, void* stream) {
 extern "C" int b2c_dropout_epoch_set(uint64_t value, void* stream) {
   uint64_t* e = dropout_epoch_ptr();
   B2C_REQUIRE(e != nullptr, "b2c_dropout_epoch_set: could not allocate the epoch word");
-  epoch_set_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(e, value);
+  B2C_CUDA(launch_k(epoch_set_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), e, value));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -118,7 +124,7 @@ extern "C" int b2c_dropout_export_mask(int kind, float drop_p, uint64_t drop_see
   B2C_REQUIRE(drop_p > 0.f, "b2c_dropout_export_mask: drop_p must be > 0");
   const int64_t n4 = rows * ((cols + 3) / 4);
   const int grid = static_cast<int>(n4 / 256 + 1 < 4 * 148 ? n4 / 256 + 1 : 4 * 148);
-  export_mask_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(kind, make_drop(drop_p, drop_seed), rows, cols, out);
+  B2C_CUDA(launch_k(export_mask_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), kind, make_drop(drop_p, drop_seed), rows, cols, out));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                                                                        const __grid_constant__ CUtensorMap tmO2,
                                                                        const __grid_constant__ CUtensorMap tmBh,
                                                                        const GemmParams p) {
+  pdl_trigger();                 // PDL: the next kernel may be scheduled; pdl_wait() follows the prologue below
   using Cfg = GemmCfg<BN, CTA2>;
   constexpr int BNH = Cfg::BNH;
   static_assert(!(CTA2 && CL > 1), "multicast clusters and CTA pairs are separate paths");
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   if constexpr (CDIV > 1) cluster_sync_all();            // peer barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                    // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -744,7 +746,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, tbh, p));
   } else if constexpr (!CTA2) {
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    kern<<<grid, GEMM_THREADS, EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM, st>>>(ta, tb, to, to2, tbh, p);
+    B2C_CUDA(launch_k(kern, dim3(grid), dim3(GEMM_THREADS), EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM, st, ta, tb, to, to2, tbh, p));
   } else {
     const int pairs = num_sms() / 2;
     const int npair = p.total_tiles < pairs ? p.total_tiles : pairs;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -145,6 +146,11 @@ int get_tensor_map_2d_sw(CUtensorMap* out, const void* base, int elem_bytes, uin
     cache.emplace(key, *out);
   }
   return 0;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("B2C_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 int num_sms() {

@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const floa
                                                                       float* __restrict__ mean_out,
                                                                       float* __restrict__ rstd_out, int64_t rows, int d,
                                                                       float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -91,6 +93,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const void
                                                                       float* __restrict__ dgamma,
                                                                       float* __restrict__ dbeta, int64_t rows, int d,
                                                                       int rows_per_warp, LnCast cast) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float red[];           // [2][d] per-block partial dgamma / dbeta (+ [d] cast column sums)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = d >> 2;
@@ -202,6 +206,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const void
 
 // ---------------------------------------------------------------------------------------------- helpers
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const float4 a = *reinterpret_cast<const float4*>(src + i);
@@ -216,6 +222,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 // table entries: {src fp32*, dst bf16*, n}; blockIdx.y = tensor, grid-stride over 8-element chunks
 struct CastEntry { const float* src; __nv_bfloat16* dst; int64_t n; };
 __global__ void multi_cast_kernel(const CastEntry* __restrict__ table) {
+  pdl_trigger();
+  pdl_wait();
   const CastEntry e = table[blockIdx.y];
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
   for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < e.n; i += stride) {
@@ -236,6 +244,8 @@ __global__ void multi_cast_kernel(const CastEntry* __restrict__ table) {
 __global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                         int64_t rows, int cols, float alpha, DropCfg drop,
                                                         float* __restrict__ colsum, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float cs_red[];                    // [cols] column partials of this CTA
   const int c4 = cols >> 2;                            // float4 groups per row
   const int tpr = c4 < 256 ? c4 : 256;                 // threads per row
@@ -282,6 +292,8 @@ __global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict
 // column sums of a bf16 matrix: block = 32 x 8 threads, each thread owns 2 adjacent columns over a row slab
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ a, int64_t ld, int64_t rows,
                                                          int64_t cols, float* __restrict__ out, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   // thread = one fixed group of 8 columns walking down this CTA's rows with 16-byte loads, four rows in flight; the
   // CTA's partials meet in shared memory and leave as one atomic per column (the first version read 4 bytes per thread
   // per step: 20 us for 37 MB)
@@ -323,6 +335,8 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 // generic fallback (any even cols / ld): a lane owns two adjacent columns
 __global__ void __launch_bounds__(256) colsum_bf16_pair_kernel(const __nv_bfloat16* __restrict__ a, int64_t ld, int64_t rows,
                                                               int64_t cols, float* __restrict__ out, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][64];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t col = static_cast<int64_t>(blockIdx.x) * 64 + tx * 2;
@@ -346,6 +360,8 @@ __global__ void __launch_bounds__(256) colsum_bf16_pair_kernel(const __nv_bfloat
 
 __global__ void repack_heads_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows,
                                     int nblk, int src_dh, int dst_dh) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t per_row = static_cast<int64_t>(nblk) * dst_dh;
   if (i >= rows * per_row) return;
@@ -366,7 +382,7 @@ extern "C" int b2c_layernorm_fwd(const float* x, const float* gamma, const float
   if (rows <= 0) return 0;
   const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define B2C_LN_FWD(BF, NV) layernorm_fwd_kernel<BF, NV><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps)
+#define B2C_LN_FWD(BF, NV) B2C_CUDA(launch_k(layernorm_fwd_kernel<BF, NV>, dim3(grid), dim3(LN_WARPS * 32), 0, st, x, gamma, beta, y, mean, rstd, rows, d, eps))
   const int nv = (d / 4 + 31) / 32;
   if (y_dtype == B2C_BF16) { if (nv <= 2) B2C_LN_FWD(true, 2); else if (nv <= 4) B2C_LN_FWD(true, 4); else B2C_LN_FWD(true, 8); }
   else                     { if (nv <= 2) B2C_LN_FWD(false, 2); else if (nv <= 4) B2C_LN_FWD(false, 4); else B2C_LN_FWD(false, 8); }
@@ -394,10 +410,10 @@ static int layernorm_bwd_launch(const void* dy, int dy_dtype, const float* x, co
   LnCast c0 = {};
 #define B2C_LN_BWD(BF, NV)                                                                                      \
   do {                                                                                                          \
-    if (cast) layernorm_bwd_kernel<BF, NV, true><<<grid, LN_WARPS * 32, smem, st>>>(                           \
-        dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma, dbeta, rows, d, rows_per_warp, *cast);            \
-    else layernorm_bwd_kernel<BF, NV, false><<<grid, LN_WARPS * 32, smem, st>>>(                               \
-        dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma, dbeta, rows, d, rows_per_warp, c0);               \
+    if (cast) B2C_CUDA(launch_k(layernorm_bwd_kernel<BF, NV, true>, dim3(grid), dim3(LN_WARPS * 32), smem, st,                            \
+        dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma, dbeta, rows, d, rows_per_warp, *cast));            \
+    else B2C_CUDA(launch_k(layernorm_bwd_kernel<BF, NV, false>, dim3(grid), dim3(LN_WARPS * 32), smem, st,                                \
+        dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma, dbeta, rows, d, rows_per_warp, c0));               \
   } while (0)
   const int nv = (d / 4 + 31) / 32;
   if (dy_dtype == B2C_BF16) { if (nv <= 2) B2C_LN_BWD(true, 2); else if (nv <= 4) B2C_LN_BWD(true, 4); else B2C_LN_BWD(true, 8); }
@@ -430,6 +446,8 @@ namespace b2c {
 // flattened token).  n elements; e holds at least n.
 __global__ void __launch_bounds__(256) add_f32_kernel(const float4* __restrict__ x, const float4* __restrict__ e,
                                                      float4* __restrict__ out, int64_t n4) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float4 a = x[i], b = e[i];
@@ -444,9 +462,9 @@ extern "C" int b2c_add_f32(const float* x, const float* e, float* out, int64_t n
               "b2c_add_f32: pointers must be 16-byte aligned");
   const int64_t n4 = n / 4;
   const int grid = static_cast<int>(n4 / 256 + 1 < 8 * 148 ? n4 / 256 + 1 : 8 * 148);
-  b2c::add_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(x),
+  B2C_CUDA(launch_k(b2c::add_f32_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float4*>(x),
                                                                          reinterpret_cast<const float4*>(e),
-                                                                         reinterpret_cast<float4*>(out), n4);
+                                                                         reinterpret_cast<float4*>(out), n4));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -456,8 +474,8 @@ extern "C" int b2c_cast_f32_bf16(const float* src, void* dst, int64_t n, void* s
   B2C_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
               "b2c_cast_f32_bf16: pointers must be 16-byte aligned");
   const int64_t threads = (n + 7) / 8;
-  cast_f32_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(dst), n);
+  B2C_CUDA(launch_k(cast_f32_bf16_kernel, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      src, static_cast<__nv_bfloat16*>(dst), n));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -467,8 +485,8 @@ extern "C" int b2c_multi_cast_f32_bf16(const void* table_dev, int n_tensors, int
   int64_t gx = (max_n / 8 + 255) / 256;
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;
-  multi_cast_kernel<<<dim3(static_cast<unsigned>(gx), n_tensors), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const CastEntry*>(table_dev));
+  B2C_CUDA(launch_k(multi_cast_kernel, dim3(dim3(static_cast<unsigned>(gx), n_tensors)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<const CastEntry*>(table_dev)));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -482,9 +500,9 @@ extern "C" int b2c_scale_cast(const float* src, void* dst, int64_t rows, int64_t
   int rows_per_block = static_cast<int>((rows + want_blocks - 1) / want_blocks);
   if (rows_per_block < 4) rows_per_block = 4;
   const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
-  scale_cast_kernel<<<grid, 256, colsum ? cols * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
+  B2C_CUDA(launch_k(scale_cast_kernel, dim3(grid), dim3(256), colsum ? cols * sizeof(float) : 0, static_cast<cudaStream_t>(stream), 
       src, static_cast<__nv_bfloat16*>(dst), rows, static_cast<int>(cols), alpha, make_drop(drop_p, drop_seed), colsum,
-      rows_per_block);
+      rows_per_block));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -499,8 +517,8 @@ extern "C" int b2c_colsum_bf16(const void* a, int64_t ld, int64_t rows, int64_t 
     int64_t rpb = (rows + nblk - 1) / nblk;
     rpb = ((rpb + rpi - 1) / rpi) * rpi;
     nblk = (rows + rpb - 1) / rpb;
-    colsum_bf16_kernel<<<static_cast<unsigned>(nblk), 256, cols * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(a), ld, rows, cols, out, static_cast<int>(rpb));
+    B2C_CUDA(launch_k(colsum_bf16_kernel, dim3(static_cast<unsigned>(nblk)), dim3(256), cols * sizeof(float), static_cast<cudaStream_t>(stream), 
+        static_cast<const __nv_bfloat16*>(a), ld, rows, cols, out, static_cast<int>(rpb)));
     B2C_CUDA(cudaGetLastError());
     return 0;
   }
@@ -509,8 +527,8 @@ extern "C" int b2c_colsum_bf16(const void* a, int64_t ld, int64_t rows, int64_t 
   int rows_per_block = static_cast<int>((rows + want_y - 1) / want_y);
   rows_per_block = ((rows_per_block + 7) / 8) * 8;
   const unsigned gy = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
-  colsum_bf16_pair_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(a), ld, rows, cols, out, rows_per_block);
+  B2C_CUDA(launch_k(colsum_bf16_pair_kernel, dim3(dim3(gx, gy)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<const __nv_bfloat16*>(a), ld, rows, cols, out, rows_per_block));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }
@@ -520,8 +538,8 @@ extern "C" int b2c_repack_heads(const void* src, void* dst, int64_t rows, int nb
   B2C_REQUIRE(src && dst && nblk > 0 && src_dh > 0 && dst_dh > 0, "b2c_repack_heads: bad argument");
   const int64_t n = rows * nblk * dst_dh;
   if (n <= 0) return 0;
-  repack_heads_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), rows, nblk, src_dh, dst_dh);
+  B2C_CUDA(launch_k(repack_heads_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), rows, nblk, src_dh, dst_dh));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

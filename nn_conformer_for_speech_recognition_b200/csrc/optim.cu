@@ -37,6 +37,8 @@ constexpr int AF_THREADS = 256;
 
 __global__ void __launch_bounds__(AF_THREADS) adafactor_stats_kernel(const AfTensor* __restrict__ tensors,
                                                                     const AfChunk* __restrict__ chunks, float eps1) {
+  pdl_trigger();
+  pdl_wait();
   const AfChunk ck = chunks[blockIdx.x];
   const AfTensor T = tensors[ck.t];
   if (!T.factored) return;
@@ -150,6 +152,8 @@ __global__ void __launch_bounds__(AF_THREADS) adafactor_stats_kernel(const AfTen
 
 // step counter and beta2_t live on the device so a captured CUDA graph advances them on every replay
 __global__ void adafactor_tick_kernel(int64_t* __restrict__ step, float* __restrict__ beta2t, float decay_rate) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t s = *step + 1;
   *step = s;
   *beta2t = 1.f - powf(static_cast<float>(s), decay_rate);          // HF: 1 - step^decay_rate
@@ -161,6 +165,8 @@ __global__ void adafactor_tick_kernel(int64_t* __restrict__ step, float* __restr
 // spread over the whole chip instead of crawling through one CTA.
 __global__ void __launch_bounds__(AF_THREADS) adafactor_factors_kernel(const AfTensor* __restrict__ tensors, int n_tensors,
                                                                       const float* __restrict__ beta2t_ptr) {
+  pdl_trigger();
+  pdl_wait();
   const float beta2t = *beta2t_ptr;
   const AfTensor T = tensors[blockIdx.y];
   if (!T.factored) return;
@@ -203,6 +209,8 @@ __global__ void __launch_bounds__(AF_THREADS) adafactor_update_kernel(const AfTe
                                                                      const AfChunk* __restrict__ chunks,
                                                                      const float* __restrict__ beta2t_ptr, float eps1,
                                                                      float lr, float beta1, float clip) {
+  pdl_trigger();
+  pdl_wait();
   const float beta2t = *beta2t_ptr;
   const AfChunk ck = chunks[blockIdx.x];
   const AfTensor T = tensors[ck.t];
@@ -319,11 +327,11 @@ extern "C" int b2c_adafactor_step(const void* tensors_dev, int n_tensors, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const AfTensor* T = static_cast<const AfTensor*>(tensors_dev);
   const AfChunk* Cc = static_cast<const AfChunk*>(chunks_dev);
-  adafactor_tick_kernel<<<1, 1, 0, st>>>(step_dev, beta2t_dev, decay_rate);
-  adafactor_stats_kernel<<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, eps1);
-  adafactor_factors_kernel<<<dim3(32, n_tensors), AF_THREADS, 0, st>>>(T, n_tensors, beta2t_dev);
-  adafactor_update_kernel<false><<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, beta2t_dev, eps1, lr, beta1, clip);
-  adafactor_update_kernel<true><<<n_chunks, AF_THREADS, 0, st>>>(T, Cc, beta2t_dev, eps1, lr, beta1, clip);
+  B2C_CUDA(launch_k(adafactor_tick_kernel, dim3(1), dim3(1), 0, st, step_dev, beta2t_dev, decay_rate));
+  B2C_CUDA(launch_k(adafactor_stats_kernel, dim3(n_chunks), dim3(AF_THREADS), 0, st, T, Cc, eps1));
+  B2C_CUDA(launch_k(adafactor_factors_kernel, dim3(dim3(32, n_tensors)), dim3(AF_THREADS), 0, st, T, n_tensors, beta2t_dev));
+  B2C_CUDA(launch_k(adafactor_update_kernel<false>, dim3(n_chunks), dim3(AF_THREADS), 0, st, T, Cc, beta2t_dev, eps1, lr, beta1, clip));
+  B2C_CUDA(launch_k(adafactor_update_kernel<true>, dim3(n_chunks), dim3(AF_THREADS), 0, st, T, Cc, beta2t_dev, eps1, lr, beta1, clip));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

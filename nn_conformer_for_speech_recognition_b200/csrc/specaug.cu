@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(256) specaug_kernel(const float* __restrict__ 
                                                      const int32_t* __restrict__ fmask, int n_fmask,
                                                      const int32_t* __restrict__ tmask, int n_tmask, int apply_masks,
                                                      float mask_value, int B, int F, int T, int f_per_block) {
+  pdl_trigger();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   const int f_lo = blockIdx.z * f_per_block, f_hi = min(F, f_lo + f_per_block);
@@ -80,9 +82,9 @@ extern "C" int b2c_specaug_apply(const float* x, float* out, const int32_t* tau,
   const int fz = F >= 32 ? 4 : 1;
   const int f_per_block = (F + fz - 1) / fz;
   dim3 grid((T + 255) / 256, B, (F + f_per_block - 1) / f_per_block);
-  specaug_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, tau, warp_w, warp_w0, n_warp, fmask,
+  B2C_CUDA(launch_k(specaug_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), x, out, tau, warp_w, warp_w0, n_warp, fmask,
                                                                       n_fmask, tmask, n_tmask, apply_masks, mask_value,
-                                                                      B, F, T, f_per_block);
+                                                                      B, F, T, f_per_block));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

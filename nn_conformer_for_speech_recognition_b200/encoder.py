@@ -150,7 +150,8 @@ class ConformerEncoder(nn.Module):
             x = specaug_plan.apply(x)
         elif SpecAugment:
             x = specaugment.SpecAugment(self, x, lens_host if lens_host is not None else input_lens)
-        tok = self.conv_sub_sampling.forward_tokens(x)                  # (B, T', F', C) bf16
+        with _lib.nvtx("encoder.conv_sub_sampling"):
+            tok = self.conv_sub_sampling.forward_tokens(x)              # (B, T', F', C) bf16
         B, To, Fo, C = tok.shape
         w_bf16 = self._bridge_weight()
         drop_p = self.bridge_dropout_p if self.training else 0.0

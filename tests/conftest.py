@@ -17,3 +17,14 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def pytest_collection_modifyitems(config, items):
+    """B2C_SANITIZE=1 (tools/sanitize.sh): compute-sanitizer slows kernels 10-100x, so the benchmark-size parametrisations
+    are skipped there; every kernel is still exercised at its small and ragged shapes."""
+    if os.environ.get("B2C_SANITIZE") != "1":
+        return
+    skip = pytest.mark.skip(reason="benchmark-size case skipped under compute-sanitizer")
+    for item in items:
+        if any(tok in item.nodeid for tok in ("23872", "40000", "19100", "benchmark_shape")):
+            item.add_marker(skip)
