@@ -91,6 +91,17 @@ int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t l
                   int64_t K, int split_k, int block_n, const b2c_epilogue* ep, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Fused macaron feed-forward half-step, INFERENCE:  out = x + alpha * (W2 SiLU(W1 LayerNorm(x) + b1) + b2)
+ * = torchaudio `_FeedForwardModule` (conformer.py:102-109, dropouts inactive) + the `0.5 * x + residual` of
+ * `ConformerLayer.forward` (conformer.py:185-187,207-209) in ONE kernel: the [M, f] hidden activation stays in shared
+ * memory / TMEM between the two tcgen05 products (SURVEY.md section 2a "fused LN->GEMM->SiLU->GEMM->1/2-residual").
+ *   x, out fp32 [M, d] (may alias); ln_w, ln_b, b2 fp32 [d]; b1 fp32 [f]; w1 bf16 [f, d]; w2 bf16 [d, f] (row-major,
+ *   torch Linear layout).  d % 16 == 0, d <= 256; f % 8 == 0.
+ * ------------------------------------------------------------------------------------------------------- */
+int b2c_ffn_fused_eval(const float* x, float* out, const float* ln_w, const float* ln_b, const void* w1, const float* b1,
+                       const void* w2, const float* b2, int64_t M, int d, int f, float alpha, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (biased variance, eps) -- torch.nn.LayerNorm at conformer.py:42,103,151,165.
  * x fp32 [rows,d] -> y (bf16 or fp32); mean/rstd fp32 [rows] optional (saved for backward).
  * bwd: dx (+)= LN'(dy); dgamma/dbeta fp32 [d] are ACCUMULATED (atomicAdd) -- zero them first.

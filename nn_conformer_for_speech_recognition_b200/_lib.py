@@ -78,6 +78,7 @@ SIGNATURES = {
     "b2c_scale_cast": [_P, _P, _L, _L, _F, _F, c_uint64, _P, _P],
     "b2c_colsum_bf16": [_P, _L, _L, _L, _P, _P],
     "b2c_repack_heads": [_P, _P, _L, _I, _I, _I, _P],
+    "b2c_ffn_fused_eval": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _F, _P],
     "b2c_bn1d_stats": [_P, _P, _L, _I, _P],
     "b2c_bn1d_apply": [_P, _P, _P, _P, _P, _P, _L, _I, _P],
     "b2c_bn1d_bwd_reduce": [_P, _P, _P, _P, _P, _L, _I, _P],

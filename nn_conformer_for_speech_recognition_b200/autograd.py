@@ -124,6 +124,7 @@ class _ConformerFn(torch.autograd.Function):
         for s in sizes:
             offs.append(offs[-1] + ((s + 3) // 4) * 4)         # keep every slice 16-byte aligned
         arena = torch.zeros(offs[-1], device=dev, dtype=torch.float32)
+        sums_all = torch.zeros((model.num_layers, 2 * d), device=dev, dtype=torch.float64)   # BatchNorm backward sums, one fill
         np_ = len(_LAYER_PARAMS)
 
         def G(li, name):
@@ -199,7 +200,7 @@ class _ConformerFn(torch.autograd.Function):
             bn = layer.conv_module.sequential[3]
             wgrad(dyb, s["c"], d, d, G(li, "conv_module.sequential.5.weight"))
             dc = ops.gemm(dyb, w["conv_module.sequential.5.weight"], M=M, N=d, K=d, b_mn=True)
-            sums = ops.convmod_bn_bwd_reduce(dc, s["y"], s["bmean"], s["brstd"], bn.weight, bn.bias)
+            sums = ops.convmod_bn_bwd_reduce(dc, s["y"], s["bmean"], s["brstd"], bn.weight, bn.bias, sums=sums_all[li])
             du = ops.convmod_dw_bwd(dc, s["y"], s["u"], s["bmean"], s["brstd"], bn.weight, bn.bias, sums, s["bn_train"],
                                     P("conv_module.sequential.2.weight").view(d, k),
                                     G(li, "conv_module.sequential.2.weight"), G(li, "conv_module.sequential.2.bias"),

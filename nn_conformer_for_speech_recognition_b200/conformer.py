@@ -29,6 +29,10 @@ from torch import nn
 from . import _lib, ops
 
 HEAD_PAD = 64          # the attention kernel's head dimension
+# inference: fused LN -> GEMM -> SiLU -> GEMM -> 1/2-residual kernel (csrc/ffn_fused.cu).  Parity-green but measured SLOWER than
+# the three-launch path at the benchmark shapes (105 vs 54 us per half-step at M = 23 872, d = 256, f = 1024: every 128-token
+# tile re-streams the 1 MB of weights through one SM's L2 port), so it is opt-in: B2C_FFN_FUSED=1.
+_FFN_FUSED = os.environ.get("B2C_FFN_FUSED", "0") == "1"
 _LAYER_CALLS = os.environ.get("B2C_LAYER_CALLS", "1") != "0"      # 0: eval issues every launch from Python (debug / profiling)
 
 
@@ -381,6 +385,12 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
         qkv_buf = torch.empty((M, nq * Hd), device=dev, dtype=bf)
         u_buf = torch.empty((M, 2 * d), device=dev, dtype=bf)
 
+    # per-layer BatchNorm scratch (fp64 sum / sum of squares) zeroed by ONE fill, counters bumped by ONE multi-tensor add:
+    # 2 launches per forward instead of 2 per layer (each ~2-3 us of an otherwise idle GPU)
+    stats_all = torch.zeros((model.num_layers, 2 * d), device=dev, dtype=torch.float64) if (bn_train or force_two_pass) else None
+    if bn_train:
+        torch._foreach_add_([l.conv_module.sequential[3].num_batches_tracked for l in model.conformer_layers], 1)
+
     for li, layer in enumerate(model.conformer_layers):
         w = weights[li]
         P = lambda name: _get(layer, name)                                      # noqa: E731
@@ -398,6 +408,9 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
                                  resid=x_in, out_dtype=torch.float32, alpha=0.5, drop_p=drop_p, drop_seed=sd + site + 1)
                 st[pre] = dict(x=x_in, a=a, mean=mean, rstd=rstd, u=u, h=h)
                 return x_out
+            if _FFN_FUSED and ops.ffn_fused_ok(d, f):      # one kernel: the [M, f] hidden activation never reaches HBM
+                return ops.ffn_fused_eval(x_in, ln_w, ln_b, w[pre + ".sequential.1.weight"], P(pre + ".sequential.1.bias"),
+                                          w[pre + ".sequential.4.weight"], P(pre + ".sequential.4.bias"), out=x_in)
             ops.layernorm_fwd(x_in, ln_w, ln_b, out=a_buf)
             ops.gemm(a_buf, w[pre + ".sequential.1.weight"], M=M, N=f, K=d, bias=P(pre + ".sequential.1.bias"),
                      act=ops.ACT_SILU, out=h_buf)
@@ -461,13 +474,12 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
             u = ops.gemm(a_buf, w["conv_module.sequential.0.weight"], M=M, N=2 * d, K=d,
                          bias=P("conv_module.sequential.0.bias"), out=u_buf)
         if bn_train:
-            y, stats = ops.convmod_dw_fwd(u, wdw, bdw, B, T)
+            y, stats = ops.convmod_dw_fwd(u, wdw, bdw, B, T, stats=stats_all[li])
             bmean, brstd = ops.convmod_bn_finalize(stats, M, bn.running_mean, bn.running_var, bn.eps,
                                                    bn.momentum if bn.momentum is not None else 0.1)
-            bn.num_batches_tracked += 1
             c = ops.convmod_bn_apply(y, bmean, brstd, bn.weight, bn.bias)
         elif force_two_pass:     # eval-mode BatchNorm under autograd: keep y, normalise with the running statistics
-            y, _ = ops.convmod_dw_fwd(u, wdw, bdw, B, T)
+            y, _ = ops.convmod_dw_fwd(u, wdw, bdw, B, T, stats=stats_all[li])
             bmean, brstd = bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)
             c = ops.convmod_bn_apply(y, bmean, brstd, bn.weight, bn.bias)
         else:

@@ -200,6 +200,10 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
   asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+  const uint4 v = ldg_stream_v4(p);
+  return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
 __device__ __forceinline__ uint2 ldg_stream_v2(const void* p) {
   uint2 v;
   asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));

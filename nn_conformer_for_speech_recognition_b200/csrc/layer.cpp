@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #include "b200conformer.h"
 #include "common.cuh"
@@ -48,8 +49,13 @@ extern "C" int b2c_conformer_layer_eval(float* x, const b2c_layer_weights* w, co
     ep.out_dtype = out_f32 ? B2C_F32 : B2C_BF16;
     return b2c_gemm_bf16(A, lda, 0, Wt, K, 0, M, N, K, 1, 0, &ep, stream);
   };
+  // opt-in (B2C_FFN_FUSED=1): measured slower than LN + 2 GEMMs at the benchmark shapes, see csrc/ffn_fused.cu / DESIGN.md
+  static const bool fused_on = [] { const char* e = getenv("B2C_FFN_FUSED"); return e && e[0] == '1'; }();
+  const bool fuse_ffn = fused_on && d % 16 == 0 && d <= 256 && f % 8 == 0;
   auto ffn = [&](const b2c_ffn_weights& q) -> int {
     int r;
+    if (fuse_ffn)      // LN -> GEMM -> SiLU -> GEMM -> 1/2-residual in one kernel: the hidden activation stays on chip
+      return b2c_ffn_fused_eval(x, x, q.ln_w, q.ln_b, q.w1, q.b1, q.w2, q.b2, M, d, f, 0.5f, eps, stream);
     if ((r = b2c_layernorm_fwd(x, q.ln_w, q.ln_b, a, B2C_BF16, nullptr, nullptr, M, d, eps, stream))) return r;
     if ((r = gemm(a, d, q.w1, f, d, q.b1, B2C_ACT_SILU, nullptr, h, 0, 1.f))) return r;
     return gemm(h, f, q.w2, d, f, q.b2, B2C_ACT_NONE, x, x, 1, 0.5f);

@@ -62,6 +62,23 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_mn: bool
     return out
 
 
+def ffn_fused_eval(x, ln_w, ln_b, w1_bf16, b1, w2_bf16, b2, alpha: float = 0.5, eps: float = 1e-5, out=None):
+    """out = x + alpha * (W2 SiLU(W1 LN(x) + b1) + b2) in one kernel (inference); x fp32 [M, d], may be updated in place."""
+    _lib.require_device()
+    _check(x, torch.float32, "x")
+    M, d = x.shape
+    f = w1_bf16.shape[0]
+    if out is None:
+        out = torch.empty_like(x)
+    call("b2c_ffn_fused_eval", ptr(x), ptr(out), ptr(ln_w), ptr(ln_b), ptr(w1_bf16), ptr(b1), ptr(w2_bf16), ptr(b2), M, d, f,
+         alpha, eps, stream_ptr(), flops=4.0 * M * d * f)
+    return out
+
+
+def ffn_fused_ok(d: int, f: int) -> bool:
+    return d % 16 == 0 and d <= 256 and f % 8 == 0
+
+
 def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, out_dtype=torch.bfloat16,
                   save_stats: bool = False, eps: float = 1e-5, out: Optional[torch.Tensor] = None):
     _lib.require_device()
@@ -106,10 +123,12 @@ def convmod_eval(u, wdw, bdw, bn_w, bn_b, bn_mean, bn_var, B: int, T: int, eps: 
     return out
 
 
-def convmod_dw_fwd(u, wdw, bdw, B: int, T: int):
+def convmod_dw_fwd(u, wdw, bdw, B: int, T: int, stats=None):
+    """stats: optional ZEROED fp64 [2d] slice (the caller zeroes one buffer for all layers with a single fill)."""
     d, k = wdw.shape[0], wdw.shape[-1]
     y = torch.empty((B * T, d), device=u.device, dtype=torch.bfloat16)
-    stats = torch.zeros(2 * d, device=u.device, dtype=torch.float64)
+    if stats is None:
+        stats = torch.zeros(2 * d, device=u.device, dtype=torch.float64)
     call("b2c_convmod_dw_fwd", ptr(u), ptr(wdw), ptr(bdw), ptr(y), ptr(stats), B, T, d, k, stream_ptr(),
          nbytes=3.0 * B * T * d * 2)
     return y, stats
@@ -280,9 +299,10 @@ def repack_heads(src, nblk: int, src_dh: int, dst_dh: int):
     return dst
 
 
-def convmod_bn_bwd_reduce(dc, y, mean, rstd, bn_w, bn_b):
+def convmod_bn_bwd_reduce(dc, y, mean, rstd, bn_w, bn_b, sums=None):
     rows, d = y.shape
-    sums = torch.zeros(2 * d, device=y.device, dtype=torch.float64)
+    if sums is None:
+        sums = torch.zeros(2 * d, device=y.device, dtype=torch.float64)
     call("b2c_convmod_bn_bwd_reduce", ptr(dc), ptr(y), ptr(mean), ptr(rstd), ptr(bn_w), ptr(bn_b), ptr(sums), rows, d,
          stream_ptr())
     return sums

@@ -570,3 +570,31 @@ def test_fused_column_sums(ops):
         out = ops.gemm(dy, w, M=M, N=N, K=K, b_mn=True, act=ops.ACT_SILU_BWD, aux=u, colsum=cs3, block_n=bn)
         _close(cs3, exact, rel=3e-3, abs_=5e-2, name=f"gemm colsum bn{bn}")
         _close(cs3, out.float().sum(0), rel=2e-2, abs_=5e-2, name=f"gemm colsum vs rounded outputs bn{bn}")
+
+
+@pytest.mark.parametrize("M,d,f", [(300, 256, 1024), (1000, 144, 576), (129, 128, 256), (64, 16, 32), (5000, 256, 1024),
+                                   (23872, 256, 1024), (640, 256, 136)])
+def test_ffn_fused_eval(ops, M, d, f):
+    """out = x + 0.5 * (W2 SiLU(W1 LN(x) + b1) + b2) in ONE kernel (torchaudio conformer.py:102-109 + :185-187, eval) against
+    fp64 torch on the bf16-rounded weights, and against the un-fused LN / GEMM / GEMM path it replaces."""
+    torch.manual_seed(M + d)
+    x = torch.randn(M, d, device="cuda") * 1.5 + 0.3
+    ln_w, ln_b = torch.rand(d, device="cuda") + 0.5, torch.randn(d, device="cuda") * 0.1
+    w1, b1 = _bf(torch.randn(f, d, device="cuda") / math.sqrt(d)), torch.randn(f, device="cuda") * 0.1
+    w2, b2 = _bf(torch.randn(d, f, device="cuda") / math.sqrt(f)), torch.randn(d, device="cuda") * 0.1
+    out = ops.ffn_fused_eval(x, ln_w, ln_b, w1, b1, w2, b2)
+    xd = x.double()
+    a = torch.nn.functional.layer_norm(xd, (d,), ln_w.double(), ln_b.double(), 1e-5)
+    ref = xd + 0.5 * (torch.nn.functional.silu(a @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double())
+    assert torch.isfinite(out).all()
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 1.5e-2 * (ref - xd).abs().max().item() + 1e-3, f"max err {err:.3e}"
+    # un-fused path (what training and d > 256 use)
+    a_bf = ops.layernorm_fwd(x, ln_w, ln_b)
+    h = ops.gemm(a_bf, w1, M=M, N=f, K=d, bias=b1, act=ops.ACT_SILU)
+    un = ops.gemm(h, w2, M=M, N=d, K=f, bias=b2, resid=x, out_dtype=torch.float32, alpha=0.5)
+    assert (out - un).abs().max().item() <= 1e-2 * (ref - xd).abs().max().item() + 1e-3
+    # in place
+    x2 = x.clone()
+    ops.ffn_fused_eval(x2, ln_w, ln_b, w1, b1, w2, b2, out=x2)
+    assert torch.equal(x2, out)
