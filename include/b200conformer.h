@@ -332,6 +332,21 @@ int b2c_bn1d_bwd_apply(const float* dy, const void* h, const void* z, const floa
                        const float* gamma, const double* sums, int train, void* dz, float* colsum, int64_t rows, int C,
                        void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Input pipeline.
+ * b2c_logmel: librosa.feature.melspectrogram -> log -> min-max normalisation of `SpeechCommands.get_mels`
+ *   (speechcommands.py:113-119) for n packed waveforms (wave fp32, wave_off int64 [n+1] sample offsets), written into the
+ *   zero-padded batch out fp32 [B, n_mels, t_max] (rows >= n zero; the padding of get_batch, speechcommands.py:186-190);
+ *   frames_out int32 [B].  basis fp32 [n_mels, n_fft/2+1] with per-filter non-zero ranges f_lo/f_hi int32 [n_mels];
+ *   mel_scratch fp32 [n, n_mels, frames_max], frames_max >= 1 + max_len // hop.  n_fft a power of two <= 4096.
+ * b2c_pad_batch: packed ragged features (utterance i = [F, lens[i]] at off[i]) -> out fp32 [B, F, t_max] zero-padded.
+ * ------------------------------------------------------------------------------------------------------- */
+int b2c_logmel(const float* wave, const int64_t* wave_off, int n, int B, const float* basis, const int32_t* f_lo,
+               const int32_t* f_hi, int n_fft, int hop, int n_mels, int frames_max, int t_max, float* mel_scratch, float* out,
+               int32_t* frames_out, void* stream);
+int b2c_pad_batch(const float* packed, const int64_t* off, const int32_t* lens, int n, int B, int F, int t_max, float* out,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

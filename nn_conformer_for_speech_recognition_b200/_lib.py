@@ -78,6 +78,8 @@ SIGNATURES = {
     "b2c_scale_cast": [_P, _P, _L, _L, _F, _F, c_uint64, _P, _P],
     "b2c_colsum_bf16": [_P, _L, _L, _L, _P, _P],
     "b2c_repack_heads": [_P, _P, _L, _I, _I, _I, _P],
+    "b2c_logmel": [_P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "b2c_pad_batch": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "b2c_ffn_fused_eval": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _F, _P],
     "b2c_bn1d_stats": [_P, _P, _L, _I, _P],
     "b2c_bn1d_apply": [_P, _P, _P, _P, _P, _P, _L, _I, _P],
@@ -96,7 +98,7 @@ HOST_SIGNATURES = {
 
 _lib = None
 LAUNCHES = 0          # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 2, "b2c_convsub_compose_bwd": 2, "b2c_attention_bwd": 4, "b2c_attention_rel_bwd": 4, "b2c_conformer_layer_eval": 20, "b2c_adafactor_step": 5, "b2c_ctc_loss": 3, "b2c_version": 0, "b2c_device_check": 0, "b2c_dropout_epoch_use": 0}
+_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 2, "b2c_convsub_compose_bwd": 2, "b2c_attention_bwd": 4, "b2c_attention_rel_bwd": 4, "b2c_conformer_layer_eval": 20, "b2c_adafactor_step": 5, "b2c_ctc_loss": 3, "b2c_logmel": 2, "b2c_version": 0, "b2c_device_check": 0, "b2c_dropout_epoch_use": 0}
 
 
 def load() -> ctypes.CDLL:
