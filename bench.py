@@ -323,7 +323,9 @@ class Rig:
             self.plan.draw(80, self.lens_host)    # SpecAugment draws (CPython `random`, reference order) -> pinned slot -> H2D
 
     def step(self, xin):
-        self.host_prepare()
+        if not getattr(self, "_prepared", False):
+            self.host_prepare()
+        self._prepared = False
         if self.graph is not None:
             if xin is not self.x_static:
                 self.x_static.copy_(xin, non_blocking=True)
@@ -371,7 +373,10 @@ class Rig:
                 return float(self.step(self.x_static))                # D2H read of the step's result (loss / checksum)
             xin = pre.get()                                           # this step's batch (copied while the previous step ran)
             pre.submit(self.x_host)                                   # H2D of the next step's batch, overlapping this step
-            return float(self.step(xin))
+            loss = self.step(xin)
+            self.host_prepare()                                       # the NEXT step's SpecAugment draws (host, CPython `random`) are made
+            self._prepared = True                                     # while the GPU runs this step -- still once per step, inside the timed region
+            return float(loss)                                        # D2H read of this step's loss
         e2e_step()
         e2e_ms = self.timed(e2e_step, steps)
         self.barrier()

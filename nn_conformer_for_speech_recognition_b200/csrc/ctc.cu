@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcParams p) {
   extern __shared__ float sm[];                       // [2 halves][2 rows][SP]
   const int b = blockIdx.x;
   const int SP = p.SP;
-  const int half = threadIdx.x >= SP ? 1 : 0;         // 0: alpha threads, 1: beta threads
-  const int s = threadIdx.x - half * SP;
+  const bool rec = static_cast<int>(threadIdx.x) < 2 * SP;   // recursion threads; the rest only help with the bulk phases
+  const int half = (rec && static_cast<int>(threadIdx.x) >= SP) ? 1 : 0;         // 0: alpha threads, 1: beta threads
+  const int s = rec ? static_cast<int>(threadIdx.x) - half * SP : SP;          // s = SP: never live
   const int len = min(p.in_lens[b], p.T);
   const int S = min(p.tgt_lens[b], p.Smax);
   const int S1 = 2 * S + 1;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcParams p) {
   if (stage) {
     const float4* src = reinterpret_cast<const float4*>(lpg);
     float4* dst4 = reinterpret_cast<float4*>(slp);
+#pragma unroll 4
     for (int i = threadIdx.x; i < len * SP / 4; i += blockDim.x) dst4[i] = src[i];
     __syncthreads();
   }
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcParams p) {
   float* dst = (half ? p.lb : p.la) + static_cast<int64_t>(b) * p.T * SP + s;
   const int bar_id = 1 + half;
   const int nthr = (SP + 31) & ~31;                   // threads of one half, rounded up to whole warps (SP % 32 == 0)
-  if (len > 0) {
+  if (len > 0 && rec) {
     // t0 = first step of this direction
     const int t0 = half ? len - 1 : 0;
     float v = CTC_NEG_INF;
@@ -188,14 +190,24 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const CtcParams p) {
   float* la = p.la + static_cast<int64_t>(b) * p.T * SP;
   const float* lb = p.lb + static_cast<int64_t>(b) * p.T * SP;
   const float* lpc = p.lpc + static_cast<int64_t>(b) * p.T * SP;
-  for (int idx = threadIdx.x; idx < len * SP; idx += blockDim.x) {
-    const int ss = idx % SP;
-    float o = 0.f;
-    if (ss < S1 && !inf) {
-      const float a = la[idx], bb = lb[idx];
-      if (a > CTC_NEG_INF && bb > CTC_NEG_INF) o = __expf(a + bb - lpc[idx] + nll);
+  // bulk phase, all threads, four independent load triples in flight per thread (the buffers are L2-resident)
+  const int ntot = len * SP;
+  for (int i0 = threadIdx.x; i0 < ntot; i0 += 4 * blockDim.x) {
+    float a[4], bb[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = min(i0 + q * static_cast<int>(blockDim.x), ntot - 1);
+      a[q] = la[idx]; bb[q] = lb[idx]; l[q] = stage ? slp[idx] : lpc[idx];
     }
-    la[idx] = o;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = i0 + q * static_cast<int>(blockDim.x);
+      if (idx < ntot) {
+        float o = 0.f;
+        if ((idx % SP) < S1 && !inf && a[q] > CTC_NEG_INF && bb[q] > CTC_NEG_INF) o = __expf(a[q] + bb[q] - l[q] + nll);
+        la[idx] = o;
+      }
+    }
   }
 }
 
@@ -291,7 +303,7 @@ extern "C" int b2c_ctc_loss(const float* logits, const int32_t* targets, const i
       B2C_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 4096));
       configured = 200 * 1024 + 4096;
     }
-    B2C_CUDA(launch_k(ctc_lattice_kernel, dim3(B), dim3(2 * SP), lat_smem, st, p));
+    B2C_CUDA(launch_k(ctc_lattice_kernel, dim3(B), dim3(2 * SP > 512 ? 2 * SP : 512), lat_smem, st, p));
   }
   if (phases & 2) B2C_CUDA(launch_k(ctc_grad_kernel, dim3(row_blocks), dim3(256), 0, st, p));
   B2C_CUDA(cudaGetLastError());

@@ -6,7 +6,7 @@ sys.path.insert(0, ".")
 import nn_conformer_for_speech_recognition_b200 as b2c
 from nn_conformer_for_speech_recognition_b200.optim import Adafactor
 
-from bench import HP
+from bench import make_hp as HP
 enc = b2c.ConformerEncoder(HP(80, 1500), 256, 4, 1024, 16, 31).cuda()
 head = torch.nn.Linear(256, 1024).cuda()
 params = [p for p in list(enc.parameters()) + list(head.parameters()) if p.requires_grad]

@@ -15,7 +15,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import CONFIGS, HP  # noqa: E402
+from bench import CONFIGS, make_hp  # noqa: E402
 from nn_conformer_for_speech_recognition_b200 import _lib, nst  # noqa: E402
 from nn_conformer_for_speech_recognition_b200.encoder import ConformerEncoder  # noqa: E402
 
@@ -37,7 +37,7 @@ def main():
     lengths = [rng.randint(500, 1500) for _ in range(n)]
     cfg = CONFIGS[args.model]
     torch.manual_seed(0)
-    enc = ConformerEncoder(HP(80, 1500), cfg["d"], cfg["h"], cfg["f"], cfg["L"], cfg["k"], 0.0).cuda().eval()
+    enc = ConformerEncoder(make_hp(80, 1500), cfg["d"], cfg["h"], cfg["f"], cfg["L"], cfg["k"], 0.0).cuda().eval()
     pool = torch.rand(80, 1500, device="cuda")                      # every utterance is a prefix of one resident buffer
     get = lambda i: pool[:, :lengths[i]]                             # noqa: E731
     keep = lambda y, m: int(m)                                       # noqa: E731  labels would be decoded here; keep the length only
