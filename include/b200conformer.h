@@ -165,8 +165,9 @@ int b2c_attention_fwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off,
                       void* stream);
 
 /* backward: dqkv bf16 [B*T, ld] laid out like qkv (every row < B*T and all three head slabs are written);
- * workspaces: delta fp32 [B,H,T], dq_f32 fp32 [ceil(T/128), B*T, H*64] (one partial-dQ slab per 128-key block, summed
- * and cast to bf16 by a second kernel).  Recomputes P from lse; the dropout mask is regenerated from (drop_p, drop_seed). */
+ * workspaces: delta fp32 [B,H,T], dq_f32 fp32 [B*T, H*64] (zeroed by this call; every 128-key block adds its partial dQ
+ * tile with a TMA reduce, a second kernel casts the sum to bf16).  Recomputes P from lse; the dropout mask is regenerated
+ * from (drop_p, drop_seed). */
 int b2c_attention_bwd(const void* qkv, int64_t ld, int64_t k_off, int64_t v_off, const int32_t* lengths,
                       const void* out, const void* dout, int64_t ld_out, const float* lse, float* delta, float* dq_f32,
                       void* dqkv, int B, int T, int H, float scale, float drop_p, uint64_t drop_seed, void* stream);

@@ -457,7 +457,7 @@ __device__ __forceinline__ void attn_bwd_tile_math(const AttnBwdParams& p, uint3
 //   UMMA  S = Q_i K_j^T, dP = dO_i V_j^T                  -> TMEM [0,128) and [128,256)
 //   regs  P = exp2(S*scale - lse), dS = P o (dP - delta)   -> smem (bf16, K-major SW128, DOUBLE-buffered), dropout regenerated
 //   UMMA  dV += P^T dO_i, dK += dS^T Q_i  (accumulate over i in TMEM), dQp = dS K_j (fresh)
-//   regs  dQp -> this key block's fp32 partial slab (plain 128 B stores); attn_dq_cast_kernel sums the slabs -> bf16
+//   regs  dQp -> smem -> TMA REDUCE-ADD into the one fp32 dQ buffer; attn_dq_cast_kernel converts it -> bf16
 // S and dP are recomputed here from the saved log-sum-exp, so no T x T tensor ever reaches HBM.
 //
 // Warp specialisation: the 512 math threads (four per tile row, 32 columns each: the tile math is latency bound) never
@@ -511,14 +511,7 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
   __nv_bfloat16* dv_dst = key_idx < p.T ? p.dqkv + static_cast<int64_t>(row_base + key_idx) * p.ld + p.v_col + h * AT_DH + cq * 16 : nullptr;
   if (key0 >= len) {                       // every key of this block is masked: P = 0 -> dK = dV = 0, dQ partial = 0
     if (issuer_warp) return;
-    for (int i = 0; i < (p.T + AT_BQ - 1) / AT_BQ; ++i) {
-      const int q_idx = i * AT_BQ + row;
-      if (q_idx < p.T) {
-        float* dst = dq_f32 + (static_cast<int64_t>(j) * p.B * p.T + row_base + q_idx) * (p.H * AT_DH) + h * AT_DH + cq * 16;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(dst + g * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
+    // (no dQ contribution: the dQ buffer is zero-initialised and every live key block ADDS its partial tile to it)
     if (dk_dst) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -636,8 +629,8 @@ __global__ void __launch_bounds__(544, 1) attn_bwd_kernel(const __grid_constant_
       named_barrier_sync(1, 512);            // all 512 math threads have staged their pieces
       if (tid == 0) {
         const uint8_t* src = smem + OFF_P + (i & 1) * 32768;
-        tma_store_3d(&tmDQ, src, h * AT_DH, i * AT_BQ, j * p.B + b);
-        tma_store_3d(&tmDQ, src + 16384, h * AT_DH + 32, i * AT_BQ, j * p.B + b);
+        tma_reduce_add_3d(&tmDQ, src, h * AT_DH, i * AT_BQ, b);            // dQ[b, i-th query block, head h] += dS K_j
+        tma_reduce_add_3d(&tmDQ, src + 16384, h * AT_DH + 32, i * AT_BQ, b);
         tma_store_commit();
       }
     };
@@ -829,9 +822,13 @@ static int attention_bwd_launch(const void* qkv, int64_t ld, int64_t k_off, int6
   p.delta_dbg = dq_f32;     // timing builds scribble cycle stamps over the head of the dQ workspace
   p.bd = bd; p.dbd = static_cast<__nv_bfloat16*>(dbd); p.Rp = Rp;
   dim3 grid((T + AT_BK - 1) / AT_BK, H, B);
-  CUtensorMap tdq;   // partial-dQ slabs as [slab * B + b][frame][H*64] fp32: the frame dimension clips at T per utterance
+  // dQ accumulates in ONE zeroed fp32 buffer [b][frame][H*64]: every key-block CTA adds its partial tile with a TMA
+  // reduce (round 1 wrote one slab per key block and summed them in a second kernel: 2/3 of that traffic is gone);
+  // the frame dimension clips at T per utterance
+  B2C_CUDA(cudaMemsetAsync(dq_f32, 0, static_cast<size_t>(B) * T * H * AT_DH * sizeof(float), st));
+  CUtensorMap tdq;
   if (int rc = get_tensor_map_3d(&tdq, dq_f32, 4, static_cast<uint64_t>(H) * AT_DH, static_cast<uint64_t>(T),
-                                 static_cast<uint64_t>(grid.x) * B, static_cast<uint64_t>(H) * AT_DH * 4,
+                                 static_cast<uint64_t>(B), static_cast<uint64_t>(H) * AT_DH * 4,
                                  static_cast<uint64_t>(T) * H * AT_DH * 4, 32, 128, true))
     return rc;
   CUtensorMap tdkv;  // dqkv as [b][frame][ld] bf16 (dK / dV tiles are stored through it, clipped at T)
@@ -842,7 +839,7 @@ static int attention_bwd_launch(const void* qkv, int64_t ld, int64_t k_off, int6
   else B2C_CUDA(launch_k(attn_bwd_kernel<false>, dim3(grid), dim3(544), ATTN_BWD_SMEM, st, tq, td, tdq, tdkv, p, dq_f32));
   const int64_t n8 = rows * H * AT_DH / 8;
   B2C_CUDA(launch_k(attn_dq_cast_kernel, dim3(static_cast<unsigned>((n8 + 255) / 256)), dim3(256), 0, st, dq_f32, static_cast<__nv_bfloat16*>(dqkv),
-                                                                               rows, H * AT_DH, ld, 0, (T + AT_BK - 1) / AT_BK));
+                                                                               rows, H * AT_DH, ld, 0, 1));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

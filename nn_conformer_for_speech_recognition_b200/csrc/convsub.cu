@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) convsub_wgrad_kernel(const __grid_constan
 // ----------------------------------------------------------------------------- weight composition (tiny)
 // One output element per group of CS_SPLIT lanes, which split the C1-long channel sum and meet in a shuffle reduction: with
 // one THREAD per element the whole composition was 16 k threads running 4608 dependent FMAs each (221 us).
-constexpr int CS_SPLIT = 8;
+constexpr int CS_SPLIT = 32;     // a whole warp per output element: 16 channels per lane (8 lanes: 62 us; 32 lanes measured below)
 __global__ void __launch_bounds__(256) compose_w_kernel(const float* __restrict__ W1, const float* __restrict__ W2, int C1,
                                                         int C2, int k1, int s1, int k2, int kc, int KP,
                                                         __nv_bfloat16* __restrict__ Wc, float* __restrict__ Wc_f32) {

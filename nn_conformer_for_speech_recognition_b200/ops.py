@@ -194,7 +194,7 @@ def attention_rel_bwd(qkv, pw, lengths_i32, att, datt, lse, B: int, T: int, H: i
     dbd = torch.zeros((M, H, Rp), device=dev, dtype=torch.bfloat16)
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, H, T), device=dev, dtype=torch.float32)
-    dq32 = torch.empty(((T + 127) // 128, M, Hd), device=dev, dtype=torch.float32)
+    dq32 = torch.empty((M, Hd), device=dev, dtype=torch.float32)          # zeroed by the library, accumulated by TMA reduce-adds
     call("b2c_attention_rel_bwd", ptr(qkv), qkv.stride(0), Hd, 2 * Hd, ptr(lengths_i32), ptr(att), ptr(datt),
          att.stride(0), ptr(lse), ptr(delta), ptr(dq32), ptr(dqkv), ptr(bd), ptr(dbd), Rp, B, T, H, scale, drop_p,
          drop_seed, stream_ptr(), flops=14.0 * B * H * T * T * 64)
@@ -323,7 +323,7 @@ def attention_bwd(qkv, lengths_i32, att, datt, lse, B: int, T: int, H: int, scal
                   drop_seed: int = 0):
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32)
-    dq32 = torch.empty(((T + 127) // 128, B * T, H * 64), device=qkv.device, dtype=torch.float32)
+    dq32 = torch.empty((B * T, H * 64), device=qkv.device, dtype=torch.float32)   # zeroed by the library, accumulated by TMA reduce-adds
     call("b2c_attention_bwd", ptr(qkv), qkv.stride(0), H * 64, 2 * H * 64, ptr(lengths_i32), ptr(att), ptr(datt),
          att.stride(0), ptr(lse), ptr(delta), ptr(dq32), ptr(dqkv), B, T, H, scale, drop_p, drop_seed, stream_ptr(),
          flops=14.0 * B * H * T * T * 64)
