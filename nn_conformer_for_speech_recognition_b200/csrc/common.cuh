@@ -88,6 +88,48 @@ __device__ __forceinline__ float silu_grad_f(float z) {
   const float t = tanh_approx(hz);
   return fmaf(0.5f, fmaf(hz, fmaf(-t, t, 1.f), t), 0.5f);
 }
+// packed fp32 pairs kept in 64-bit registers (FADD2 / FMUL2 / FFMA2: half the issue slots of the scalar forms); pk2 / upk2
+// are register-pair renames, not instructions, when the halves already sit in an aligned pair (tcgen05.ld / LDS.128 results)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// bf16x2 word from a packed fp32 pair (low half = low lane)
+__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// 0xFFFF / 0x0000 per 16-bit half from bit 7 (low half) and bit 15 (high half) of w: PRMT with sign replication
+__device__ __forceinline__ uint32_t halfmask_from_bits_7_15(uint32_t w) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0u), "r"(0x9988u));
+  return d;
+}
 // packed fp32 FMA (FFMA2): d = a * b + c on two lanes of a 64-bit register pair -- half the issue slots of two FFMAs
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   uint64_t ra, rb, rc, rd;
@@ -257,6 +299,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// pull one box of a tensor into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
 // 2-D tile load, coordinates {c_inner, c_outer}; completes `bar` with the box's bytes.
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c_inner, int c_outer) {
   asm volatile(
@@ -294,6 +341,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores of this thread have finished READING shared memory (the buffer may be rewritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the N most recently committed bulk-store groups of this thread have finished reading shared memory
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

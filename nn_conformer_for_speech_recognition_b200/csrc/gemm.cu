@@ -32,6 +32,8 @@
 // variants, MUFU.TANH-based SiLU, and a tile schedule whose last, mostly empty wave runs as half-width tiles.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "b200conformer.h"
 
@@ -39,8 +41,7 @@ namespace b2c {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int EPI_WARPS = 16;                 // 4 per TMEM lane quarter, each owning BN/4 columns of the tile
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int BS_MAXKB = 4;                   // weight-stationary path: k-blocks of the B tile kept resident (K <= 256)
 #ifndef B2C_DEFAULT_CLUSTER
 #define B2C_DEFAULT_CLUSTER 1                   // multicast cluster size picked when block_n = 0 (env B2C_GEMM_CLUSTER overrides)
 #endif
@@ -59,26 +60,38 @@ struct GemmParams {
   int kblocks_per_split, total_kb;
   int m_tiles, n_tiles, splits, total_tiles;
   int tiles_full;            // tiles [tiles_full, total_tiles) are HALF-width tail tiles (two per full tile); == total_tiles when unused
+  int bs_group, bs_rounds, bs_rem, bs_half;   // weight-stationary schedule (see tile_at)
   b2c_epilogue ep;
 };
 
-template <int BN, bool CTA2 = false>
+// BSTAT = weight-stationary variant: the CTA keeps ONE n-block of B (all K <= 256 of it) resident in shared memory for
+// its whole life and the ring streams A only.  With 128 KB of B parked, a 256-wide tile leaves room for 8 epilogue warps.
+// AUX3 (weight-stationary SiLU-backward dgrad on 128-wide tiles): three 2 KB boxes per epilogue warp instead of two.
+template <int BN, bool CTA2 = false, bool BSTAT = false, bool AUX3 = false>
 struct GemmCfg {
   static constexpr int BNH = CTA2 ? BN / 2 : BN;                         // B rows held by ONE CTA
-  static constexpr int STAGES = (BNH == 256) ? 3 : (BNH == 128 ? 4 : 6);
+  static constexpr int EPW = (BSTAT && BN == 256) ? 8 : 16;              // epilogue warps: 4 TMEM lane quarters x EPW/4 column slices
+  static constexpr int THREADS = 64 + EPW * 32;
+  static constexpr int STAGES = BSTAT ? (BN == 256 ? 3 : (AUX3 ? 4 : 5)) : ((BNH == 256) ? 3 : (BNH == 128 ? 4 : 6));
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BNH * BK * 2;
-  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SPAN = BN / (EPI_WARPS / 4);                      // columns owned by one epilogue warp
+  static constexpr uint32_t STAGE_BYTES = BSTAT ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr uint32_t BRES_OFF = STAGES * STAGE_BYTES;             // resident B: BS_MAXKB k-blocks of B_BYTES
+  static constexpr uint32_t BRES_BYTES = BSTAT ? BS_MAXKB * B_BYTES : 0;
+  static constexpr int SPAN = BN / (EPW / 4);                            // columns owned by one epilogue warp
   static constexpr int CW = SPAN < 32 ? SPAN : 32;                       // columns per epilogue chunk (one tcgen05.ld)
   static constexpr int CHUNKS = SPAN / CW;                               // chunks per epilogue warp per tile
-  static constexpr uint32_t STG_WARP_BYTES = 32 * CW * 4;                // fp32 transpose buffer per warp
-  static constexpr uint32_t STG_OFF = STAGES * STAGE_BYTES;
-  static constexpr uint32_t BAR_OFF = STG_OFF + EPI_WARPS * STG_WARP_BYTES;
-  static constexpr uint32_t AUXBAR_OFF = BAR_OFF + 256;                  // 2 mbarriers per epilogue warp (aux boxes of the SiLU' epilogue)
-  static constexpr uint32_t CS_OFF = BAR_OFF + 512;                      // per-CTA column-sum accumulators (training epilogues)
-  static constexpr uint32_t CS_MAXN = 4096;
-  static constexpr uint32_t SMEM = BAR_OFF + 512 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr int AUX_BUFS = AUX3 ? 3 : 2;                          // 2 KB boxes per warp in the SiLU-backward epilogue
+  static constexpr uint32_t STG_WARP_BYTES = AUX3 ? 3 * 2048 : 32 * CW * 4;   // fp32 transpose buffer / bf16 boxes per warp
+  static constexpr uint32_t STG_OFF = BRES_OFF + BRES_BYTES;
+  static constexpr uint32_t BAR_OFF = STG_OFF + EPW * STG_WARP_BYTES;
+  static constexpr uint32_t AUXBAR_OFF = BAR_OFF + (AUX3 ? 128 : 256);   // AUX_BUFS mbarriers per epilogue warp (aux boxes of the SiLU' epilogue)
+  static_assert((2 * STAGES + 6) * 8 <= (AUX3 ? 128 : 256), "pipeline barriers overlap the aux barriers");
+  static constexpr uint32_t BIAS_OFF = BAR_OFF + 512;                    // bias copy read by the row-domain epilogues (LDS broadcast)
+  static constexpr uint32_t BIAS_MAXN = BSTAT ? BN : 2048;               // stationary CTAs only ever see their own n-block
+  static constexpr uint32_t CS_OFF = BIAS_OFF + BIAS_MAXN * 4;           // per-CTA column-sum accumulators (training epilogues)
+  static constexpr uint32_t CS_MAXN = BSTAT ? BN : 2048;                 // (stationary: indexed from the CTA's first column)
+  static constexpr uint32_t SMEM = CS_OFF + 1024 /*align slack*/;
   static constexpr uint32_t SMEM_EXTRA = SMEM + CS_MAXN * 4;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
@@ -117,6 +130,37 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
   return t;
 }
 
+// it-th tile of this CTA.  Default schedule: static round-robin over decode_tile's order.  Weight-stationary schedule:
+// CTA c is bound to n-block c % n_tiles for its whole life (that B tile never leaves shared memory) and is member
+// j = c / n_tiles of that n-block's group of bs_group CTAs; the group walks the m-blocks round-robin for bs_rounds full
+// rounds, and the bs_rem m-blocks left over go out as full tiles or, when they fill at most half the group, as two
+// half-width tiles each (bs_half) -- CTAs side by side (same j) still share their A rows in L2.
+template <bool BSTAT, int CDIV>
+__device__ __forceinline__ bool tile_at(const GemmParams& p, int it, uint32_t rank, TileCoord& t) {
+  if constexpr (BSTAT) {
+    const int j = static_cast<int>(blockIdx.x) / p.n_tiles;
+    t.n_blk = static_cast<int>(blockIdx.x) - j * p.n_tiles;
+    t.split = 0;
+    t.hh = -1;
+    if (it < p.bs_rounds) { t.m_blk = j + it * p.bs_group; return true; }
+    if (it > p.bs_rounds) return false;
+    if (p.bs_half) {
+      if (j >= 2 * p.bs_rem) return false;
+      t.m_blk = p.bs_rounds * p.bs_group + (j >> 1);
+      t.hh = j & 1;
+      return true;
+    }
+    if (j >= p.bs_rem) return false;
+    t.m_blk = p.bs_rounds * p.bs_group + j;
+    return true;
+  } else {
+    const int tile = static_cast<int>(blockIdx.x) / CDIV + it * (static_cast<int>(gridDim.x) / CDIV);
+    if (tile >= p.total_tiles) return false;
+    t = decode_tile(p, tile, CDIV, rank);
+    return true;
+  }
+}
+
 // CTA2 = true: launched as clusters of two CTAs; tile = 256 x BN per pair (tcgen05.mma.cta_group::2, M = 256).  CTA r of
 // the pair owns rows [128 r, 128 r + 128) of the tile (A slab, accumulator, epilogue) and loads B rows
 // [r BN/2, (r+1) BN/2); the leader (r = 0) issues every MMA and its commits fan out to both CTAs' barriers.
@@ -127,22 +171,24 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
 // B bytes cross the L2 -> SM fabric once per cluster instead of once per CTA (these GEMMs are bound by that fabric,
 // not by HBM or the tensor pipe: K is only 256..1024, so a 128 x BN tile re-reads BN x K weights for ~1-2 k cycles of
 // MMA).  A stage is recycled only after the MMAs of all CL CTAs that read it have retired (multicast commit).
-template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA, int CL = 1>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA, int CL = 1, bool BSTAT = false>
+__global__ void __launch_bounds__((GemmCfg<BN, CTA2, BSTAT>::THREADS), 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmB,
                                                                        const __grid_constant__ CUtensorMap tmO,
                                                                        const __grid_constant__ CUtensorMap tmO2,
                                                                        const __grid_constant__ CUtensorMap tmBh,
                                                                        const GemmParams p) {
   pdl_trigger();                 // PDL: the next kernel may be scheduled; pdl_wait() follows the prologue below
-  using Cfg = GemmCfg<BN, CTA2>;
+  constexpr bool AUX3 = BSTAT && BN == 128 && EPI == EPI_SILU_BWD;
+  using Cfg = GemmCfg<BN, CTA2, BSTAT, AUX3>;
   constexpr int BNH = Cfg::BNH;
+  constexpr int EPI_WARPS = Cfg::EPW;
+  constexpr int GEMM_THREADS = Cfg::THREADS;
   static_assert(!(CTA2 && CL > 1), "multicast clusters and CTA pairs are separate paths");
+  static_assert(!BSTAT || (!CTA2 && CL == 1 && !A_MN), "the weight-stationary path is single-CTA with a K-major A");
   constexpr int CDIV = CTA2 ? 2 : CL;                    // CTAs that share one tile index
   constexpr uint16_t CL_MASK = static_cast<uint16_t>((1u << CL) - 1u);
   const uint32_t rank = CDIV > 1 ? cluster_ctarank() : 0u;
-  const int tile0 = static_cast<int>(blockIdx.x) / CDIV;
-  const int tile_step = static_cast<int>(gridDim.x) / CDIV;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -151,15 +197,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;     // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained (every epilogue warp arrives)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bfull_bar = tempty_bar + 3;              // weight-stationary: the resident B tile has landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // fused column sums (bias gradients): accumulated per CTA in shared memory and flushed with ONE global atomic per
   // column at the end -- one atomic per column per 32-row chunk (766 k of them on 1024 addresses for the FFN dgrad) cost
   // more than the rest of the epilogue
   float* cs_smem = reinterpret_cast<float*>(smem + Cfg::CS_OFF);
-  const bool cs_in_smem = EXTRA && p.ep.colsum != nullptr && p.N <= static_cast<int64_t>(Cfg::CS_MAXN);
+  const int64_t cs_base = BSTAT ? static_cast<int64_t>(static_cast<int>(blockIdx.x) % (p.n_tiles > 0 ? p.n_tiles : 1)) * BN : 0;   // first column kept
+  const int cs_n = BSTAT ? BN : static_cast<int>(p.N);
+  const bool cs_in_smem = EXTRA && p.ep.colsum != nullptr && (BSTAT || p.N <= static_cast<int64_t>(Cfg::CS_MAXN));
   if (cs_in_smem)
-    for (int i = threadIdx.x; i < static_cast<int>(p.N); i += GEMM_THREADS) cs_smem[i] = 0.f;
+    for (int i = threadIdx.x; i < cs_n; i += GEMM_THREADS) cs_smem[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -168,7 +217,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], CL);                      // multicast clusters: every CTA's MMAs release the stage
     }
-    for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(reinterpret_cast<uint64_t*>(smem + Cfg::AUXBAR_OFF) + s, 1);
+    for (int s = 0; s < Cfg::AUX_BUFS * EPI_WARPS; ++s) mbar_init(reinterpret_cast<uint64_t*>(smem + Cfg::AUXBAR_OFF) + s, 1);
+    mbar_init(bfull_bar, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], CTA2 ? 2 * EPI_WARPS : EPI_WARPS);     // pair: both CTAs' epilogues release the leader
@@ -190,9 +240,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      [[maybe_unused]] int pit = 0;
-      for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++pit) {
-        const TileCoord tc = decode_tile(p, tile, CDIV, rank);
+      TileCoord tc;
+      if constexpr (BSTAT) {
+        // the CTA's n-block of B, all k-blocks, once
+        if (tile_at<BSTAT, CDIV>(p, 0, rank, tc)) {
+          mbar_expect_tx(bfull_bar, static_cast<uint32_t>(p.total_kb) * Cfg::B_BYTES);
+          for (int kb = 0; kb < p.total_kb; ++kb) {
+            uint8_t* sBr = smem + Cfg::BRES_OFF + kb * Cfg::B_BYTES;
+            if constexpr (!B_MN) {
+              tma_load_2d(sBr, &tmB, bfull_bar, kb * BK, tc.n_blk * BN);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c) tma_load_2d(sBr + c * 8192, &tmB, bfull_bar, tc.n_blk * BN + c * 64, kb * BK);
+            }
+          }
+        }
+      }
+      for (int pit = 0; tile_at<BSTAT, CDIV>(p, pit, rank, tc); ++pit) {
         const int n_blk = tc.n_blk, m_blk = tc.m_blk, split = tc.split;
         const bool half_tile = tc.hh >= 0;
         const int kb0 = split * p.kblocks_per_split;
@@ -204,7 +268,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           B2C_GT(0, pit, 2 * (kb - kb0) + 1);
           uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
-          if constexpr (!CTA2) {
+          if constexpr (BSTAT) {
+            mbar_expect_tx(&full_bar[s], Cfg::A_BYTES);
+            tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m_blk * BM);
+          } else if constexpr (!CTA2) {
             mbar_expect_tx(&full_bar[s], half_tile ? Cfg::A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES);
             if constexpr (!A_MN) {
               tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m_blk * BM);
@@ -263,10 +330,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BM : BM, BN, A_MN, B_MN);
       int s = 0;
       uint32_t ph = 0;
-      uint32_t it = 0;
       constexpr uint32_t idesc_half = umma_idesc_bf16(CTA2 ? 2 * BM : BM, BN / 2, A_MN, B_MN);
-      for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++it) {
-        const TileCoord tc = decode_tile(p, tile, CDIV, rank);
+      TileCoord tc;
+      if constexpr (BSTAT) {
+        if (tile_at<BSTAT, CDIV>(p, 0, rank, tc)) mbar_wait(bfull_bar, 0u);
+      }
+      for (uint32_t it = 0; tile_at<BSTAT, CDIV>(p, static_cast<int>(it), rank, tc); ++it) {
         const int split = tc.split;
         const uint32_t idesc_t = tc.hh >= 0 ? idesc_half : idesc;
         const int kb0 = split * p.kblocks_per_split;
@@ -283,7 +352,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           B2C_GT(1, it, 3 + 2 * (kb - kb0));
           tc_fence_after();
           const uint32_t a_addr = base + s * Cfg::STAGE_BYTES;
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint32_t b_addr = BSTAT ? base + Cfg::BRES_OFF + (kb - kb0) * Cfg::B_BYTES + (tc.hh > 0 ? Cfg::B_BYTES / 2 : 0u)
+                                        : a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = A_MN ? umma_desc_sw128(a_addr + k * 2048, 8192, 1024)
@@ -323,30 +393,54 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     // CHUNK AHEAD of its use, into the two 2 KB halves of the warp's staging buffer; the thread reads its own row of the
     // box, overwrites it in place with the output row, and the box leaves again through a TMA store.
     constexpr bool ROWAUX = EPI == EPI_SILU_BWD && Cfg::CW == 32;
-    uint64_t* aux_bar = reinterpret_cast<uint64_t*>(smem + Cfg::AUXBAR_OFF) + 2 * ew;
+    uint64_t* aux_bar = reinterpret_cast<uint64_t*>(smem + Cfg::AUXBAR_OFF) + Cfg::AUX_BUFS * ew;
     uint32_t job = 0;                                  // chunks this warp has handled: buffer = job & 1
+    [[maybe_unused]] uint32_t jbuf = 0;                // AUX3: job % 3
     uint32_t aux_ph = 0;                               // bit b = parity the next wait on aux_bar[b] uses
-    auto aux_issue = [&](int tile_n, int ch_n, uint32_t jb) {   // lane 0: fetch the aux box of chunk ch_n of tile tile_n
-      if (tile_n >= p.total_tiles) return;
-      const TileCoord t = decode_tile(p, tile_n, CDIV, rank);
-      if (t.hh >= 0 && part >= 2) return;
+    constexpr int HALF_PARTS = (EPI_WARPS / 4) / 2;    // column slices that exist in a half-width tile
+    // row-domain epilogues read the bias from a shared-memory copy (one broadcast LDS.128 per four columns instead of a
+    // guarded global load whose L2 latency sat in front of every chunk's math); columns >= N read as 0 and are clipped
+    // (the host only picks these epilogues when the padded width n_tiles * BN fits the copy)
+    [[maybe_unused]] float* bias_s = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF);
+    if constexpr ((EPI == EPI_BF16 || EPI == EPI_SILU) && Cfg::CW == 32) {
+      const int ncols = BSTAT ? BN : p.n_tiles * BN;
+      const float* bsrc = static_cast<const float*>(ep.bias);
+      const int64_t c0 = BSTAT ? static_cast<int64_t>(static_cast<int>(blockIdx.x) % p.n_tiles) * BN : 0;
+      for (int i = static_cast<int>(threadIdx.x) - 64; i < ncols; i += EPI_WARPS * 32)
+        bias_s[i] = (bsrc && c0 + i < p.N) ? __ldg(bsrc + c0 + i) : 0.f;
+      named_barrier_sync(1, EPI_WARPS * 32);
+    }
+    // lane 0: fetch the aux box of chunk ch_n (may run past the tile: it carries into the following tiles) of this CTA's
+    // it_n-th tile into buffer jb & 1 -- or, L2ONLY, just pull it into L2 ahead of that fetch
+    auto aux_issue = [&](int it_n, int ch_n, uint32_t buf, bool l2only) {
+      it_n += ch_n / Cfg::CHUNKS;
+      ch_n %= Cfg::CHUNKS;
+      TileCoord t;
+      if (!tile_at<BSTAT, CDIV>(p, it_n, rank, t)) return;
+      if (t.hh >= 0 && part >= HALF_PARTS) return;
       const int64_t c = static_cast<int64_t>(t.n_blk) * BN + (t.hh > 0 ? BN / 2 : 0) + part * Cfg::SPAN + ch_n * Cfg::CW;
       const int64_t r = static_cast<int64_t>(t.m_blk) * BM + q * 32;
       if (c >= p.N || r >= p.M) return;                // the consumer skips the wait under the same condition
-      uint64_t* b = aux_bar + (jb & 1u);
+      if (l2only) {
+        tma_prefetch_l2_2d(&tmO2, static_cast<int>(c), static_cast<int>(r));
+        return;
+      }
+      uint64_t* b = aux_bar + buf;
       mbar_expect_tx(b, 2048);
-      tma_load_2d(reinterpret_cast<uint8_t*>(stg) + (jb & 1u) * 2048, &tmO2, b, static_cast<int>(c), static_cast<int>(r));
+      tma_load_2d(reinterpret_cast<uint8_t*>(stg) + buf * 2048, &tmO2, b, static_cast<int>(c), static_cast<int>(r));
     };
     if constexpr (ROWAUX) {
-      if (lane == 0) aux_issue(tile0, 0, 0);
+      if (lane == 0) {
+        aux_issue(0, 0, 0, false);
+        if constexpr (AUX3) aux_issue(0, 1, 1, false);
+      }
     }
-    uint32_t it = 0;
-    for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++it) {
-      const TileCoord tc = decode_tile(p, tile, CDIV, rank);
+    TileCoord tc;
+    for (uint32_t it = 0; tile_at<BSTAT, CDIV>(p, static_cast<int>(it), rank, tc); ++it) {
       const int m_blk = tc.m_blk, split = tc.split;
       const int64_t ncol0 = static_cast<int64_t>(tc.n_blk) * BN + (tc.hh > 0 ? BN / 2 : 0);   // first global column of the tile
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-      if (tc.hh >= 0 && part >= 2) {                   // half-width tail tile: this warp's columns do not exist
+      if (tc.hh >= 0 && part >= HALF_PARTS) {          // half-width tail tile: this warp's columns do not exist
         mbar_wait(&tfull_bar[as], aph);                // (stay in step with the tile sequence before releasing the buffer)
         tc_fence_after();
         tc_fence_before();
@@ -372,108 +466,167 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       // arithmetic / STG stream entirely -- with ~28 KB of L1 left the STGs alone were a quarter of the epilogue.
       constexpr bool ROWDOM = (EPI == EPI_BF16 || EPI == EPI_SILU) && Cfg::CW == 32;
       if constexpr (ROWDOM) {
-        uint8_t* box = reinterpret_cast<uint8_t*>(stg);
         const int64_t grow0 = static_cast<int64_t>(m_blk) * BM + q * 32;
         const uint64_t drow = static_cast<uint64_t>(grow0 + lane) * p.N;
-#pragma unroll 1
-        for (int ch = 0; ch < Cfg::CHUNKS; ++ch) {
-          const int col_t = part * Cfg::SPAN + ch * CW;
-          const int64_t col0 = ncol0 + col_t;
-          if (lane == 0) tma_store_wait_read();          // the stores issued from this buffer have read it
-          __syncwarp();
-          if (ch == 0) {
-            mbar_wait(&tfull_bar[as], aph);
-            tc_fence_after();
-          }
-          uint32_t v[32];
-          __syncwarp();
-          tmem_ld32(tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16) + col_t, v);
-          tmem_wait_ld();
-          if (ch == Cfg::CHUNKS - 1) {                   // all of this warp's TMEM reads for the tile are done
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if constexpr (CTA2) mbar_arrive_cluster(tempty_lead0 + as * 8); else mbar_arrive(&tempty_bar[as]);
-            }
-          }
-          uint32_t ph[16], pu[16];
-          // p = 0.5 (the reference's dropout, asrnn.py:29): ONE hash decides the thread's 32 consecutive columns, one bit
-          // each.  This mask has no second consumer (the backward reads it off the saved pre-activation), so its
-          // granularity is free; other probabilities use the 8-bit-per-element generator.
-          const bool half = do_drop && p.drop.thresh16 == 32768u;
-          uint32_t keep_bits = 0xFFFFFFFFu;
-          if (half) keep_bits = drop_hash32(drop.seed ^ 0x2545F4914F6CDD1Dull, (drow + static_cast<uint64_t>(col0)) >> 5);
+        const uint32_t tm_row = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16) + part * Cfg::SPAN;
+        const int colt0 = part * Cfg::SPAN;                                  // first column of this warp's slice inside the tile
+        const float* bsp = bias_s + (BSTAT ? (tc.hh > 0 ? BN / 2 : 0) : ncol0) + colt0;   // bias of the slice (shared memory copy)
+        // p = 0.5 (the reference's dropout, asrnn.py:29): ONE hash decides the thread's 32 consecutive columns, one bit
+        // each.  This mask has no second consumer (the backward reads it off the saved pre-activation), so its
+        // granularity and bit order are free; other probabilities use the 8-bit-per-element generator.
+        const int mode = !do_drop ? 0 : (p.drop.thresh16 == 32768u ? 1 : 2);
+        mbar_wait(&tfull_bar[as], aph);
+        tc_fence_after();
+        __syncwarp();
+        // The chunk loop is software-pipelined: chunk ch+1's tcgen05.ld is in flight while chunk ch is computed, and the
+        // bulk store of a chunk is only waited for (its shared-memory read) right before its box is rewritten -- with two
+        // boxes per warp that is a whole chunk later.  Elementwise math runs on packed fp32 pairs.
+        auto run = [&](auto MODE_) {
+          constexpr int MODE = decltype(MODE_)::value;           // 0 no dropout, 1 one-bit masks (p = 0.5), 2 general p
+          constexpr int SUBS = Cfg::SPAN / 16;                   // 16-column steps: two per 32-column store box
+          uint32_t v[2][16];
+          tmem_ld16(tm_row, v[0]);
+          [[maybe_unused]] uint32_t keep_bits = 0;
+          uint8_t* box = nullptr;
+          const uint64_t half2 = pk2(0.5f, 0.5f);
+          const uint32_t sw = (lane >> 1) & 3;                   // SWIZZLE_64B: 16-byte chunk index ^ ((row >> 1) & 3)
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bias && col0 + 4 * g < p.N) bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + 4 * g));   // warp-uniform address
-            float f[4] = {__uint_as_float(v[4 * g]) + bv.x, __uint_as_float(v[4 * g + 1]) + bv.y,
-                          __uint_as_float(v[4 * g + 2]) + bv.z, __uint_as_float(v[4 * g + 3]) + bv.w};
-            float ds0 = 1.f, ds1 = 1.f, ds2 = 1.f, ds3 = 1.f;
-            if (half) {
-              ds0 = (keep_bits >> (4 * g)) & 1u ? 2.f : 0.f; ds1 = (keep_bits >> (4 * g + 1)) & 1u ? 2.f : 0.f;
-              ds2 = (keep_bits >> (4 * g + 2)) & 1u ? 2.f : 0.f; ds3 = (keep_bits >> (4 * g + 3)) & 1u ? 2.f : 0.f;
-            } else if (do_drop) {
-              drop_scale4g(drop, drow + static_cast<uint64_t>(col0 + 4 * g), ds0, ds1, ds2, ds3);
+          for (int sc = 0; sc < SUBS; ++sc) {
+            const int ch = sc >> 1, hf = sc & 1;
+            uint32_t* vc = v[sc & 1];
+            const int64_t col0 = ncol0 + colt0 + ch * CW;        // first column of the 32-column box this step belongs to
+            tmem_wait_ld();
+            if (sc + 1 < SUBS) {
+              tmem_ld16(tm_row + (sc + 1) * 16, v[(sc + 1) & 1]);
+            } else {                                             // all of this warp's TMEM reads for the tile are done
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (CTA2) mbar_arrive_cluster(tempty_lead0 + as * 8); else mbar_arrive(&tempty_bar[as]);
+              }
             }
-            if (do_out2) {                               // dropped positions carry B2C_DROPPED_PREACT (see below)
-              pu[2 * g] = pack_bf16(ds0 != 0.f ? f[0] : B2C_DROPPED_PREACT, ds1 != 0.f ? f[1] : B2C_DROPPED_PREACT);
-              pu[2 * g + 1] = pack_bf16(ds2 != 0.f ? f[2] : B2C_DROPPED_PREACT, ds3 != 0.f ? f[3] : B2C_DROPPED_PREACT);
+            if (hf == 0) {
+              if (ew == 0 && lane == 0) B2C_GT(2, it, 2 + 5 * ch);
+              if constexpr (MODE == 1) keep_bits = drop_hash32(drop.seed ^ 0x2545F4914F6CDD1Dull, (drow + static_cast<uint64_t>(col0)) >> 5);
+              // two 2 KB boxes per warp: with a single output they alternate (the store issued a chunk ago may still be
+              // reading the other one); with the saved pre-activation both are rewritten every chunk
+              box = reinterpret_cast<uint8_t*>(stg) + (do_out2 ? 0u : (job & 1u) * 2048u);
+              if (do_out2) {                                     // (waiting here keeps the packed words out of local memory)
+                if (lane == 0) tma_store_wait_read_n<0>();
+                __syncwarp();
+              }
             }
-            if (do_silu) {
+            uint32_t ph[8], pu[8];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) f[j] *= sigmoid_fast(f[j]);
-            }
-            if (do_drop) { f[0] *= ds0; f[1] *= ds1; f[2] *= ds2; f[3] *= ds3; }
-            ph[2 * g] = pack_bf16(f[0], f[1]);
-            ph[2 * g + 1] = pack_bf16(f[2], f[3]);
-          }
-          const uint32_t sw = (lane >> 1) & 3;           // SWIZZLE_64B: 16-byte chunk index ^ ((row >> 1) & 3)
+            for (int gg = 0; gg < 4; ++gg) {
+              const int g = 4 * hf + gg;                         // group of four columns inside the 32-column box
+              const float4 bv = *reinterpret_cast<const float4*>(bsp + ch * CW + 4 * g);   // one address per warp: broadcast
+              uint64_t z[2] = {add2(pk2u(vc[4 * gg], vc[4 * gg + 1]), pk2(bv.x, bv.y)),
+                               add2(pk2u(vc[4 * gg + 2], vc[4 * gg + 3]), pk2(bv.z, bv.w))};
+              if constexpr (MODE == 2) {                         // general p: per-element scales, scalar math
+                float f[4], ds[4];
+                upk2(z[0], f[0], f[1]);
+                upk2(z[1], f[2], f[3]);
+                drop_scale4g(drop, drow + static_cast<uint64_t>(col0 + 4 * g), ds[0], ds[1], ds[2], ds[3]);
+                if (do_out2) {                                   // dropped positions carry B2C_DROPPED_PREACT (see below)
+                  pu[2 * gg] = pack_bf16(ds[0] != 0.f ? f[0] : B2C_DROPPED_PREACT, ds[1] != 0.f ? f[1] : B2C_DROPPED_PREACT);
+                  pu[2 * gg + 1] = pack_bf16(ds[2] != 0.f ? f[2] : B2C_DROPPED_PREACT, ds[3] != 0.f ? f[3] : B2C_DROPPED_PREACT);
+                }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            *reinterpret_cast<uint4*>(box + lane * 64 + ((c ^ sw) << 4)) = make_uint4(ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
-            if (do_out2)
-              *reinterpret_cast<uint4*>(box + 2048 + lane * 64 + ((c ^ sw) << 4)) = make_uint4(pu[4 * c], pu[4 * c + 1], pu[4 * c + 2], pu[4 * c + 3]);
+                for (int j = 0; j < 4; ++j) f[j] = (do_silu ? f[j] * sigmoid_fast(f[j]) : f[j]) * ds[j];
+                ph[2 * gg] = pack_bf16(f[0], f[1]);
+                ph[2 * gg + 1] = pack_bf16(f[2], f[3]);
+              } else {
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                  const int j = 2 * g + h2;                      // pair index inside the box: columns 2j, 2j + 1
+                  uint64_t r = z[h2];
+                  if (do_silu) {                                 // z * sigmoid(z) = hz + hz * tanh(hz), hz = z / 2  (x 2 = 1/keep at p = 0.5)
+                    const uint64_t hz = mul2(z[h2], half2);
+                    float h0, h1;
+                    upk2(hz, h0, h1);
+                    const uint64_t t = pk2(tanh_approx(h0), tanh_approx(h1));
+                    r = MODE == 1 ? fma2(z[h2], t, z[h2]) : fma2(hz, t, hz);
+                  } else if (MODE == 1) {
+                    r = add2(z[h2], z[h2]);
+                  }
+                  uint32_t o = cvt_bf16x2(r);
+                  if constexpr (MODE == 1) {
+                    // pair j reads its two keep bits at positions 8 apart: (7 - j, 15 - j) for j < 8, (8 + j, 16 + j) above
+                    const uint32_t m = halfmask_from_bits_7_15(j < 8 ? keep_bits << j : keep_bits >> (j + 1));
+                    o &= m;
+                    if (do_out2) pu[2 * gg + h2] = (cvt_bf16x2(z[h2]) & m) | (0xC61CC61Cu & ~m);   // bf16(B2C_DROPPED_PREACT) where dropped
+                  } else {
+                    if (do_out2) pu[2 * gg + h2] = cvt_bf16x2(z[h2]);
+                  }
+                  ph[2 * gg + h2] = o;
+                }
+              }
+            }
+            if (hf == 0) {
+              if (ew == 0 && lane == 0) B2C_GT(2, it, 3 + 5 * ch);
+              if (!do_out2) {
+                if (lane == 0) tma_store_wait_read_n<1>();
+                __syncwarp();
+              }
+              if (ew == 0 && lane == 0) B2C_GT(2, it, 4 + 5 * ch);
+            }
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = 2 * hf + cc;
+              *reinterpret_cast<uint4*>(box + lane * 64 + ((c ^ sw) << 4)) = make_uint4(ph[4 * cc], ph[4 * cc + 1], ph[4 * cc + 2], ph[4 * cc + 3]);
+              if (do_out2)
+                *reinterpret_cast<uint4*>(box + 2048 + lane * 64 + ((c ^ sw) << 4)) = make_uint4(pu[4 * cc], pu[4 * cc + 1], pu[4 * cc + 2], pu[4 * cc + 3]);
+            }
+            if (hf == 1) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0 && col0 < p.N && grow0 < p.M) {
+                tma_store_2d(&tmO, box, static_cast<int>(col0), static_cast<int>(grow0));
+                if (do_out2) tma_store_2d(&tmO2, box + 2048, static_cast<int>(col0), static_cast<int>(grow0));
+              }
+              if (lane == 0) tma_store_commit();                 // every chunk commits a (possibly empty) group: wait_group counts them
+              ++job;
+              if (ew == 0 && lane == 0) B2C_GT(2, it, 5 + 5 * ch);
+            }
           }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && col0 < p.N && grow0 < p.M) {
-            tma_store_2d(&tmO, box, static_cast<int>(col0), static_cast<int>(grow0));
-            if (do_out2) tma_store_2d(&tmO2, box + 2048, static_cast<int>(col0), static_cast<int>(grow0));
-            tma_store_commit();
-          }
-        }
+        };
+        using std::integral_constant;
+        if (mode == 0) run(integral_constant<int, 0>{});
+        else if (mode == 1) run(integral_constant<int, 1>{});
+        else run(integral_constant<int, 2>{});
       }
       if constexpr (ROWAUX) {
         const int64_t grow0 = static_cast<int64_t>(m_blk) * BM + q * 32;
         const bool do_colsum = EXTRA && ep.colsum != nullptr;
-        const float ha = 0.5f * ep.alpha;                // SiLU'(u) = (1 + t + (u/2)(1 - t^2)) / 2, t = tanh(u/2); alpha folded in
+        // SiLU'(u) = (1 + t + (u/2)(1 - t^2)) / 2, t = tanh(u/2); alpha and the 1/2 folded into ha.  Packed fp32 pairs.
+        const uint64_t ha2 = pk2(0.5f * ep.alpha, 0.5f * ep.alpha), half2 = pk2(0.5f, 0.5f), mhalf2 = pk2(-0.5f, -0.5f), m1 = pk2(-1.f, -1.f);
 #pragma unroll 1
         for (int ch = 0; ch < Cfg::CHUNKS; ++ch, ++job) {
           const int col_t = part * Cfg::SPAN + ch * CW;
           const int64_t col0 = ncol0 + col_t;
-          const uint32_t b = job & 1u;
+          const uint32_t b = AUX3 ? jbuf : (job & 1u);
           uint8_t* box = reinterpret_cast<uint8_t*>(stg) + b * 2048;
           const bool has = col0 < p.N && grow0 < p.M;
-          if (lane == 0) {
-            tma_store_wait_read();                       // the other buffer's last store has read it: refill it
-            if (ch + 1 < Cfg::CHUNKS) aux_issue(tile, ch + 1, job + 1); else aux_issue(tile + tile_step, 0, job + 1);
+          if (ew == 0 && lane == 0) B2C_GT(2, it, 2 + 5 * ch);
+          if constexpr (!AUX3) {
+            if (lane == 0) {
+              // two boxes: the other one's last store has read it: refill it with the next chunk's aux box (a whole chunk of
+              // lead time; issuing it later -- after this chunk's math -- measured slower: 33.8 -> 37.7 us, the aux wait
+              // moved into the open).  The wait itself is exposed: that store was issued moments ago (see AUX3 below).
+              tma_store_wait_read_n<0>();
+              aux_issue(static_cast<int>(it), ch + 1, (job + 1) & 1u, false);
+            }
           }
           if (ch == 0) {
+            if (ew == 0 && lane == 0) B2C_GT(2, it, 0);
             mbar_wait(&tfull_bar[as], aph);
+            if (ew == 0 && lane == 0) B2C_GT(2, it, 1);
             tc_fence_after();
           }
           uint32_t v[32];
           __syncwarp();
           tmem_ld32(tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16) + col_t, v);
-          tmem_wait_ld();
-          if (ch == Cfg::CHUNKS - 1) {                   // all of this warp's TMEM reads for the tile are done
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if constexpr (CTA2) mbar_arrive_cluster(tempty_lead0 + as * 8); else mbar_arrive(&tempty_bar[as]);
-            }
-          }
           const uint32_t sw = (lane >> 1) & 3;           // SWIZZLE_64B: 16-byte chunk index ^ ((row >> 1) & 3)
           uint4 a[4];
 #pragma unroll
@@ -484,32 +637,58 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
             for (int c = 0; c < 4; ++c) a[c] = *reinterpret_cast<const uint4*>(box + lane * 64 + ((c ^ sw) << 4));
           }
-          float f[32];
+          tmem_wait_ld();
+          if (ew == 0 && lane == 0) B2C_GT(2, it, 3 + 5 * ch);
+          if (ch == Cfg::CHUNKS - 1) {                   // all of this warp's TMEM reads for the tile are done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CTA2) mbar_arrive_cluster(tempty_lead0 + as * 8); else mbar_arrive(&tempty_bar[as]);
+            }
+          }
+          uint64_t f2[16];                               // fp32 outputs as pairs (kept for the fused bias gradient)
+          uint32_t o[16];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint32_t w[4] = {a[c].x, a[c].y, a[c].z, a[c].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 u2 = unpack_bf16(w[j]);
-              const float hu0 = 0.5f * u2.x, hu1 = 0.5f * u2.y;
-              const float t0 = tanh_approx(hu0), t1 = tanh_approx(hu1);
-              const float r0 = fmaf(hu0, fmaf(-t0, t0, 1.f), t0), r1 = fmaf(hu1, fmaf(-t1, t1, 1.f), t1);
-              f[8 * c + 2 * j] = __uint_as_float(v[8 * c + 2 * j]) * fmaf(ha, r0, ha);
-              f[8 * c + 2 * j + 1] = __uint_as_float(v[8 * c + 2 * j + 1]) * fmaf(ha, r1, ha);
+              const uint64_t u2 = pk2u(w[j] << 16, w[j] & 0xFFFF0000u);          // bf16 pair -> fp32 pair
+              const uint64_t hu = mul2(u2, half2), hn = mul2(u2, mhalf2);
+              float h0, h1;
+              upk2(hu, h0, h1);
+              const uint64_t t = pk2(tanh_approx(h0), tanh_approx(h1));
+              const uint64_t r = fma2(hn, fma2(t, t, m1), t);                    // t + (u/2)(1 - t^2)
+              const int e = 4 * c + j;
+              f2[e] = mul2(pk2u(v[2 * e], v[2 * e + 1]), fma2(ha2, r, ha2));
+              o[e] = cvt_bf16x2(f2[e]);
             }
-            *reinterpret_cast<uint4*>(box + lane * 64 + ((c ^ sw) << 4)) =
-                make_uint4(pack_bf16(f[8 * c], f[8 * c + 1]), pack_bf16(f[8 * c + 2], f[8 * c + 3]),
-                           pack_bf16(f[8 * c + 4], f[8 * c + 5]), pack_bf16(f[8 * c + 6], f[8 * c + 7]));
           }
+          if (ew == 0 && lane == 0) B2C_GT(2, it, 4 + 5 * ch);
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(box + lane * 64 + ((c ^ sw) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && has) {
-            tma_store_2d(&tmO, box, static_cast<int>(col0), static_cast<int>(grow0));
-            tma_store_commit();
+          if (lane == 0) {
+            if (has) tma_store_2d(&tmO, box, static_cast<int>(col0), static_cast<int>(grow0));
+            tma_store_commit();                            // (possibly empty: the wait below counts groups)
+            if constexpr (AUX3) {
+              // three boxes: the store issued a whole chunk ago has read its box -- no exposed wait -- and that box takes the
+              // aux operand of the chunk after next, which then has a whole chunk to arrive
+              tma_store_wait_read_n<1>();
+              aux_issue(static_cast<int>(it), ch + 2, jbuf == 0 ? 2u : jbuf - 1u, false);
+            }
           }
+          if constexpr (AUX3) jbuf = jbuf == 2 ? 0u : jbuf + 1u;
+          if (ew == 0 && lane == 0) B2C_GT(2, it, 5 + 5 * ch);
           if (do_colsum) {
             // bias gradient from the fp32 values: transpose-reduce over the warp's 32 rows -- 31 shuffles leave lane L
             // with the sum of column col0 + L (each step folds the half of the columns whose bit differs from the lane's)
+            float f[32];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) upk2(f2[e], f[2 * e], f[2 * e + 1]);
             float r16[16], r8[8], r4[4], r2[2];
             const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
 #pragma unroll
@@ -525,7 +704,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             for (int i = 0; i < 2; ++i)
               r2[i] = (b2 ? r4[i + 2] : r4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? r4[i] : r4[i + 2], 2);
             const float tot = (b1 ? r2[1] : r2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? r2[0] : r2[1], 1);
-            if (col0 + lane < p.N) atomicAdd((cs_in_smem ? cs_smem : ep.colsum) + col0 + lane, tot);
+            if (col0 + lane < p.N) {
+              if (cs_in_smem) atomicAdd(cs_smem + (col0 - cs_base) + lane, tot); else atomicAdd(ep.colsum + col0 + lane, tot);
+            }
           }
         }
       }
@@ -678,7 +859,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             cs2 += __shfl_xor_sync(0xffffffffu, cs2, o); cs3 += __shfl_xor_sync(0xffffffffu, cs3, o);
           }
           if (r_lane == 0 && col_ok) {
-            float* dst = cs_in_smem ? cs_smem + col : ep.colsum + col;
+            float* dst = cs_in_smem ? cs_smem + (col - cs_base) : ep.colsum + col;
             atomicAdd(dst, cs0); atomicAdd(dst + 1, cs1); atomicAdd(dst + 2, cs2); atomicAdd(dst + 3, cs3);
           }
         }
@@ -689,9 +870,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   tc_fence_before();
   __syncthreads();
   if (cs_in_smem)
-    for (int i = threadIdx.x; i < static_cast<int>(p.N); i += GEMM_THREADS) {
+    for (int i = threadIdx.x; i < cs_n; i += GEMM_THREADS) {
       const float v = cs_smem[i];
-      if (v != 0.f) atomicAdd(p.ep.colsum + i, v);
+      if (v != 0.f && cs_base + i < p.N) atomicAdd(p.ep.colsum + cs_base + i, v);
     }
   if constexpr (CDIV > 1) cluster_sync_all();            // peers may still be multicasting into this CTA / signalling its barriers
   if (warp == 1) {
@@ -700,11 +881,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA, int CL = 1>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2, bool EXTRA, int CL = 1, bool BSTAT = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                        const CUtensorMap& tbh, GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, CTA2>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CTA2, EXTRA, CL>;
+  using Cfg = GemmCfg<BN, CTA2, BSTAT, (BSTAT && BN == 128 && EPI == EPI_SILU_BWD)>;
+  constexpr int GEMM_THREADS = Cfg::THREADS;
+  static_assert((EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM) <= 227 * 1024, "shared-memory plan does not fit");
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CTA2, EXTRA, CL, BSTAT>;
   static bool configured = false;
   if (!configured) {
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM));
@@ -715,6 +898,18 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   p.m_tiles = static_cast<int>((p.M + CDIV * BM - 1) / (CDIV * BM));      // M units: blocks, pairs or clusters
   p.total_tiles = p.m_tiles * p.n_tiles * p.splits;
   p.tiles_full = p.total_tiles;
+  p.bs_group = p.bs_rounds = p.bs_rem = p.bs_half = 0;
+  if constexpr (BSTAT) {
+    int group = num_sms() / p.n_tiles;
+    if (group > p.m_tiles) group = p.m_tiles;
+    p.bs_group = group;
+    p.bs_rounds = p.m_tiles / group;
+    p.bs_rem = p.m_tiles % group;
+    p.bs_half = (p.bs_rem > 0 && 2 * p.bs_rem <= group) ? 1 : 0;
+    B2C_CUDA(launch_k(kern, dim3(group * p.n_tiles), dim3(GEMM_THREADS), EXTRA ? Cfg::SMEM_EXTRA : Cfg::SMEM, st, ta, tb, to, to2, tbh, p));
+    B2C_CUDA(cudaGetLastError());
+    return 0;
+  }
   if constexpr (!CTA2 && CL == 1 && !A_MN && BN >= 128) {
     // a last wave that is at most half full is issued as half-width tiles (see decode_tile)
     static const bool tail_ok = [] { const char* e = getenv("B2C_GEMM_TAIL"); return !(e && e[0] == '0'); }();
@@ -796,6 +991,7 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   int bn = block_n;
   bool cta2 = false;
   int cl = 1;
+  int bstat = 0;                                 // 1 = forced, 2 = picked automatically (falls back when no kernel matches)
   if (bn == 0) {
     // measured on B200 at the Conformer-M shapes (tools/kernel_bench.py, tools/wgrad_probe.py): weight gradients and
     // wide forward GEMMs run best on 128x256 tiles of single CTAs (weight gradients with a split-K that gives ONE wave:
@@ -810,6 +1006,11 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
     bn = -bn;
     cta2 = true;
     B2C_REQUIRE(bn == 128 || bn == 256, "b2c_gemm_bf16: CTA-pair tiles need block_n -128 or -256");
+  } else if (bn >= 9000) {                       // 9000 + BN: force the weight-stationary path (tools / tests)
+    bn -= 9000;
+    bstat = 1;
+    B2C_REQUIRE((bn == 128 || bn == 256) && !a_mn && K <= BS_MAXKB * BK && split_k <= 1,
+                "b2c_gemm_bf16: the weight-stationary path needs block_n = 9000 + {128,256}, a K-major A and K <= %d", BS_MAXKB * BK);
   } else if (bn >= 1000) {                       // 1000*CL + BN: multicast cluster of CL CTAs along M (CL = 2, 4)
     cl = bn / 1000;
     bn %= 1000;
@@ -820,6 +1021,24 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
     // automatic: share the B tile across vertically adjacent tiles when the problem is tall enough to fill the clusters
     static const int auto_cl = [] { const char* e = getenv("B2C_GEMM_CLUSTER"); return e ? atoi(e) : B2C_DEFAULT_CLUSTER; }();
     if ((auto_cl == 2 || auto_cl == 4) && M >= 128ll * auto_cl * 8) cl = (b_mn && bn == 128 && auto_cl == 4) ? 2 : auto_cl;
+  }
+  const int bn_plain = bn;                       // what the automatic choice falls back to when no stationary kernel matches
+  if (block_n == 0 && !cta2 && cl == 1 && !a_mn && K <= BS_MAXKB * BK && split_k <= 1 && M >= 4 * BM && ep->out_dtype == B2C_BF16 &&
+      !ep->resid && !ep->accumulate) {
+    // K <= 256: a tile's main loop is at most 4 k-blocks and re-fetching the B tile for every 128 rows of A is two thirds of
+    // what the tile pulls out of L2 (128 of 192 KB per 128x256 tile).  Where it measured faster (tools/bstat_probe.py, M =
+    // 23872, K = 256: QKV 12.5 -> 11.2 us, pointwise-1 10.2 -> 9.4, SiLU-backward dgrad 33.8 -> 31.6, N = 256 dgrad
+    // 8.0 -> 7.4; NOT the FFN1 SiLU epilogues: 24.0 streaming vs 25.7) the n-block's weights stay parked in shared memory.
+    // B2C_GEMM_BSTAT=0: off.
+    static const bool bs_auto = [] { const char* e = getenv("B2C_GEMM_BSTAT"); return !(e && e[0] == '0'); }();
+    const bool extra_req = ep->out2 || ep->colsum || ep->drop_p > 0.f;
+    int pick = 0;
+    if (ep->act == B2C_ACT_NONE && !extra_req && !ep->aux && ep->alpha == 1.f && N % 256 == 0) pick = 256;
+    else if (ep->act == B2C_ACT_SILU_BWD && N % 128 == 0) pick = 128;
+    if (bs_auto && pick) {
+      bstat = 2;
+      bn = pick;
+    }
   }
   B2C_REQUIRE(bn == 64 || bn == 128 || bn == 256, "b2c_gemm_bf16: block_n must be 64, 128 or 256");
   const int total_kb = static_cast<int>((K + BK - 1) / BK);
@@ -846,7 +1065,7 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   if (!b_mn && !cta2 && cl == 1 && bn >= 128 && (rc = get_tensor_map_2d(&tbh, B, 2, K, N, ldb * 2, BK, bn / 2, true))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // bf16 outputs of the plain / SiLU epilogues leave through TMA stores (row-domain epilogue): 32 x 32 boxes, 64B swizzle
-  const bool rowdom_ok = ep->out_dtype == B2C_BF16 && bn >= 128 && ep->ld_out % 8 == 0 &&
+  const bool rowdom_ok = ep->out_dtype == B2C_BF16 && bn >= 128 && ep->ld_out % 8 == 0 && (N + bn - 1) / bn * bn <= 2048 &&
                          (!ep->out2 || (ep->ld_out2 % 8 == 0 && (reinterpret_cast<uintptr_t>(ep->out2) & 15) == 0));
   // ... and the SiLU-backward dgrad also READS its aux operand (the saved pre-activation) as such boxes
   const bool rowaux_ok = rowdom_ok && ep->act == B2C_ACT_SILU_BWD && !ep->out2 && ep->ld_aux % 8 == 0 &&
@@ -911,6 +1130,32 @@ extern "C" int b2c_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
       if (epi == EPI_SILU_BWD) B2C_LAUNCH_CL(BN_, true, EPI_SILU_BWD, CL_);                        \
       return launch_gemm<BN_, false, true, EPI_GENERIC, false, true, CL_>(ta, tb, to, to2, tbh, p, st);          \
     }                                                                                              \
+  }
+#define B2C_LAUNCH_BS(BN_, BMN, E)                                                                 \
+  do {                                                                                             \
+    if (extra) return launch_gemm<BN_, false, BMN, E, false, true, 1, true>(ta, tb, to, to2, tbh, p, st);        \
+    return launch_gemm<BN_, false, BMN, E, false, false, 1, true>(ta, tb, to, to2, tbh, p, st);                  \
+  } while (0)
+#define B2C_DISPATCH_BS(BN_)                                                                       \
+  if (bstat && bn == BN_) {                                                                        \
+    if (!b_mn) {                                                                                   \
+      if (epi == EPI_BF16) B2C_LAUNCH_BS(BN_, false, EPI_BF16);                                    \
+      if (epi == EPI_SILU) B2C_LAUNCH_BS(BN_, false, EPI_SILU);                                    \
+    } else {                                                                                       \
+      if (epi == EPI_BF16) B2C_LAUNCH_BS(BN_, true, EPI_BF16);                                     \
+      if (epi == EPI_SILU_BWD) B2C_LAUNCH_BS(BN_, true, EPI_SILU_BWD);                             \
+    }                                                                                              \
+  }
+  B2C_DISPATCH_BS(128)
+  B2C_DISPATCH_BS(256)
+#undef B2C_DISPATCH_BS
+#undef B2C_LAUNCH_BS
+  B2C_REQUIRE(bstat != 1, "b2c_gemm_bf16: no weight-stationary kernel for this epilogue");
+  if (bstat == 2 && bn != bn_plain) {            // generic epilogue: back to the default tile and its B boxes
+    bn = bn_plain;
+    if (!b_mn && (rc = get_tensor_map_2d(&tb, B, 2, K, N, ldb * 2, BK, bn / cl, true))) return rc;
+    tbh = tb;
+    if (!b_mn && bn >= 128 && (rc = get_tensor_map_2d(&tbh, B, 2, K, N, ldb * 2, BK, bn / 2, true))) return rc;
   }
   B2C_DISPATCH_CL(128, 2, true)
   B2C_DISPATCH_CL(128, 4, false)

@@ -514,6 +514,43 @@ def test_gemm_multicast_cluster_forward(ops, M, N, K, bn):
     _close(x, want, rel=5e-3, name="cluster resid")
 
 
+# ----------------------------------------------------------------------------------------------- GEMM, weight-stationary
+@pytest.mark.parametrize("M,N,K,bn", [(512, 256, 64, 9256), (1000, 1024, 256, 9256), (777, 768, 144, 9256), (777, 384, 256, 9128),
+                                      (23872, 1024, 256, 9128), (23872, 768, 256, 9256), (2049, 520, 200, 9128), (130, 256, 256, 9256)])
+def test_gemm_weight_stationary(ops, M, N, K, bn):
+    """block_n = 9000 + BN (K <= 256): every CTA parks one n-block of the weights in shared memory and streams A only.
+    Ragged M / N, a remainder round issued as half-width tiles, every row-domain epilogue incl. the one-bit dropout
+    masks with the saved pre-activation, and the MN-major (dgrad) weight layout with the SiLU-backward epilogue."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().T + bias
+    _close(ops.gemm(a, w, M=M, N=N, K=K, bias=bias, block_n=bn), ref, name="stationary bias")
+    _close(ops.gemm(a, w, M=M, N=N, K=K, block_n=bn), ref - bias, name="stationary no bias")
+    out2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    h = ops.gemm(a, w, M=M, N=N, K=K, bias=bias, act=ops.ACT_SILU, out2=out2, block_n=bn)
+    _close(out2, ref, name="stationary pre-act")
+    _close(h, torch.nn.functional.silu(ref), name="stationary silu")
+    _close(ops.gemm(a, w, M=M, N=N, K=K, bias=bias, act=ops.ACT_SILU, block_n=bn), torch.nn.functional.silu(ref), name="stationary silu eval")
+    for p in (0.5, 0.25):
+        hd = ops.gemm(a, w, M=M, N=N, K=K, bias=bias, act=ops.ACT_SILU, out2=out2, drop_p=p, drop_seed=77, block_n=bn)
+        dropped = out2.float() < -5e3
+        assert abs(dropped.float().mean().item() - p) < 0.03
+        assert torch.equal(hd[dropped], torch.zeros_like(hd[dropped]))
+        _close(out2.float()[~dropped], ref[~dropped], name="stationary kept pre-act")
+        _close(hd.float()[~dropped], torch.nn.functional.silu(ref)[~dropped] / (1 - p), rel=2e-2, name="stationary kept act")
+    wt = _bf(torch.randn(K, N, device="cuda", generator=g) / math.sqrt(K))       # [K, N] storage: dgrad layout
+    _close(ops.gemm(a, wt, M=M, N=N, K=K, b_mn=True, block_n=bn), a.float() @ wt.float(), name="stationary dgrad")
+    u = _bf(torch.randn(M, N, device="cuda", generator=g))
+    cs = torch.zeros(N, device="cuda")
+    du = ops.gemm(a, wt, M=M, N=N, K=K, b_mn=True, act=ops.ACT_SILU_BWD, aux=u, alpha=2.0, colsum=cs, block_n=bn)
+    sg = torch.sigmoid(u.float())
+    want = 2.0 * (a.float() @ wt.float()) * (sg * (1 + u.float() * (1 - sg)))
+    _close(du, want, name="stationary silu bwd")
+    _close(cs, want.sum(0), rel=5e-3, abs_=0.5, name="stationary silu bwd colsum")
+
+
 @pytest.mark.parametrize("bn", [2128, 2256, 4256])
 def test_gemm_multicast_cluster_dgrad(ops, bn):
     g = torch.Generator(device="cuda").manual_seed(5)

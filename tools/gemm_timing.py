@@ -10,13 +10,14 @@ bn = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 shape = sys.argv[2] if len(sys.argv) > 2 else "ffn1"
 M, d, f = 23872, 256, 1024
 bf = torch.bfloat16
-N, K = {"ffn1": (f, d), "ffn2": (d, f), "qkv": (3 * d, d), "dsilu": (f, d), "dgrad": (d, f), "proj": (d, d)}[shape]
+N, K = {"ffn1": (f, d), "ffn1t": (f, d), "ffn2": (d, f), "qkv": (3 * d, d), "dsilu": (f, d), "dgrad": (d, f), "proj": (d, d)}[shape]
 a = torch.randn(M, K, device="cuda").to(bf); w = torch.randn(N, K, device="cuda").to(bf)
 bias = torch.randn(N, device="cuda"); out = torch.empty(M, N, device="cuda", dtype=bf)
 x = torch.randn(M, N, device="cuda")
 wt = torch.randn(K, N, device="cuda").to(bf); aux = torch.randn(M, N, device="cuda").to(bf)
 def run():
     if shape == "ffn1": ops.gemm(a, w, M=M, N=N, K=K, bias=bias, act=ops.ACT_SILU, out=out, block_n=bn)
+    elif shape == "ffn1t": ops.gemm(a, w, M=M, N=N, K=K, bias=bias, act=ops.ACT_SILU, out=out, out2=aux, drop_p=0.5, drop_seed=11, block_n=bn)
     elif shape in ("ffn2", "proj"): ops.gemm(a, w, M=M, N=N, K=K, bias=bias, resid=x, out=x, alpha=0.5, block_n=bn)
     elif shape == "dsilu": ops.gemm(a, wt, M=M, N=N, K=K, b_mn=True, act=ops.ACT_SILU_BWD, aux=aux, out=out, block_n=bn)
     elif shape == "dgrad": ops.gemm(a, wt, M=M, N=N, K=K, b_mn=True, out=out, block_n=bn)
@@ -35,8 +36,8 @@ print(f"shape {shape} M{M} N{N} K{K} bn{bn}: cycles relative to CTA 0's first st
 for it in range(4):
     pr = t[0, it, :2 * kbs] - t0
     mm = t[1, it, :2 + 2 * kbs] - t0
-    ep = t[2, it, :6] - t0
+    ep = t[2, it, :12] - t0
     pf = t[2, it, 8:12] - t0
     print(f"tile {it}: producer (wait_empty, got) per kb: {pr.tolist()}")
     print(f"         mma tempty wait {mm[0]}->{mm[1]}; full (wait, got) per kb: {mm[2:].tolist()}")
-    print(f"         epilogue warp0 tfull wait {ep[0]}->{ep[1]}; chunk (ld done, end): {ep[2:].tolist()}; prefetch issue (start, end) per chunk: {pf.tolist()}")
+    print(f"         epilogue warp0 tfull wait {ep[0]}->{ep[1]}; row-domain per chunk (ld done, first half packed, box free, stored, -): {ep[2:7].tolist()} {ep[7:12].tolist()}; coalesced-domain prefetch issue: {pf.tolist()}")
