@@ -334,6 +334,22 @@ int b2c_bn1d_bwd_apply(const float* dy, const void* h, const void* z, const floa
                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * LSTM cell (the bi-LSTM "decoder", self.lstm = nn.LSTM(...) at /root/reference/lib/standard/asrnn.py:38,
+ * called at asrnn.py:252).  One call per time step and direction, between two recurrent GEMMs (b2c_gemm_bf16); torch gate
+ * order i, f, g, o along the 4H axis.  N rows (the LSTM's batch axis), H hidden units (H % 4 == 0).
+ *   _fwd  gates fp32 [N, 4H] = x_t W_ih^T + b_ih + b_hh + h_{t-1} W_hh^T;  c_prev fp32 [N, H] or NULL (= 0).
+ *         c_out fp32 [N, H]; h_out fp32, row pitch ld_h (the [L, N, dirs*H] output, this direction's column block);
+ *         h_bf16 bf16 [N, H] (operand of the next step's GEMM); acts fp32 [N, 4H] or NULL: activated gates, saved for _bwd
+ *   _bwd  dout fp32 (row pitch ld_dout) or NULL: gradient of this step's output; dh_rec fp32 [N, H] or NULL: dG_{t+1} W_hh;
+ *         dc fp32 [N, H]: IN d loss / d c_t carried from step t+1 (zero at the last step), OUT d loss / d c_{t-1};
+ *         acts / c_prev (NULL = 0) / c_cur as saved by _fwd; dgates bf16 [N, 4H]: gradient of the pre-activations
+ * ------------------------------------------------------------------------------------------------------- */
+int b2c_lstm_cell_fwd(const float* gates, const float* c_prev, float* c_out, float* h_out, int64_t ld_h, void* h_bf16,
+                      float* acts, int64_t N, int H, void* stream);
+int b2c_lstm_cell_bwd(const float* dout, int64_t ld_dout, const float* dh_rec, float* dc, const float* acts,
+                      const float* c_prev, const float* c_cur, void* dgates, int64_t N, int H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Input pipeline.
  * b2c_logmel: librosa.feature.melspectrogram -> log -> min-max normalisation of `SpeechCommands.get_mels`
  *   (speechcommands.py:113-119) for n packed waveforms (wave fp32, wave_off int64 [n+1] sample offsets), written into the

@@ -86,6 +86,8 @@ SIGNATURES = {
     "b2c_bn1d_bwd_reduce": [_P, _P, _P, _P, _P, _L, _I, _P],
     "b2c_bn1d_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],
     "b2c_ctc_loss": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, ctypes.c_size_t, _P],
+    "b2c_lstm_cell_fwd": [_P, _P, _P, _P, _L, _P, _P, _L, _I, _P],
+    "b2c_lstm_cell_bwd": [_P, _L, _P, _P, _P, _P, _P, _P, _L, _I, _P],
 }
 HOST_SIGNATURES = {
     "b2c_dropout_keep_scale": ([c_float], c_float),

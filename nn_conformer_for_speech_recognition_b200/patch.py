@@ -33,10 +33,11 @@ def convsub_from_reference(ref) -> ConvSubSampling:
     return new.to(device=p.device, dtype=p.dtype).train(ref.training)
 
 
-def patch_asrnn(model, specaug_mode: str = "reference", encoder: bool = False):
+def patch_asrnn(model, specaug_mode: str = "reference", encoder: bool = False, lstm: bool = False):
     """encoder=True also replaces the callers either side of the hot path: `ASRNN.encoder`
     (bridge GEMM + fused dropout + sync-free length filter, asrnn.py:193-221) and `ASRNN.projection_block`
-    (Linear -> SiLU -> BatchNorm1d, asrnn.py:73-89) -- see asrnn_path.py.  The LSTM / final_fc tail stays the reference's."""
+    (Linear -> SiLU -> BatchNorm1d, asrnn.py:73-89) -- see asrnn_path.py.  lstm=True swaps `model.lstm` (asrnn.py:38,252)
+    for `b2c.LSTM` (lstm.py); `final_fc` / `log_softmax` stay the reference's."""
     if specaug_mode not in ("reference", "paper"):
         raise ValueError("specaug_mode must be 'reference' or 'paper'")
     model.conv_sub_sampling = convsub_from_reference(model.conv_sub_sampling)
@@ -48,4 +49,7 @@ def patch_asrnn(model, specaug_mode: str = "reference", encoder: bool = False):
         from . import asrnn_path
         model.encoder = types.MethodType(asrnn_path.encoder, model)
         model.projection_block = types.MethodType(asrnn_path.projection_block, model)
+    if lstm:
+        from .lstm import lstm_from_reference
+        model.lstm = lstm_from_reference(model.lstm)
     return model

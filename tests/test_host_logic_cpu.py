@@ -156,3 +156,21 @@ def test_relative_positional_embeddings_table_is_bit_exact_with_the_reference():
     t = RelativePositionalEmbeddings((4, 8))().detach()
     assert torch.equal(t[0], torch.tensor([0., 0., 0., 0., 1., 1., 1., 1.]))          # p = 0: sin half zero, cos half one
     assert abs(float(t[1, 0]) - float(torch.sin(torch.tensor(1.0)))) < 1e-7 and abs(float(t[1, 4]) - float(torch.cos(torch.tensor(1.0)))) < 1e-7
+
+
+def test_lstm_is_an_nn_lstm_with_the_same_parameters_and_no_cpu_path():
+    """b2c.LSTM keeps torch.nn.LSTM's constructor, parameter names / shapes and initialisation (asrnn.py:38), and has no CPU path."""
+    torch.manual_seed(11)
+    ref = torch.nn.LSTM(256, 512, bidirectional=True)
+    torch.manual_seed(11)
+    ours = b2c.LSTM(256, 512, bidirectional=True)
+    assert isinstance(ours, torch.nn.LSTM)
+    sd_r, sd_o = ref.state_dict(), ours.state_dict()
+    assert list(sd_r.keys()) == list(sd_o.keys())
+    for k in sd_r:
+        assert torch.equal(sd_r[k], sd_o[k]), k
+    conv = b2c.lstm_from_reference(ref)
+    assert all(torch.equal(conv.state_dict()[k], sd_r[k]) for k in sd_r)
+    if not torch.cuda.is_available():
+        with pytest.raises(b2c.B2CError):
+            ours(torch.zeros(3, 2, 256))
