@@ -83,8 +83,12 @@ struct LnCast {
   float alpha;
   DropCfg drop;
 };
+// d <= 256 (LN_MAXV = 2): capped at 80 registers so that THREE CTAs stay resident per SM (two at 128 registers for d <= 512),
+// which is what the launch geometry below assumes.  Uncapped, the fp32-dy + cast instantiation (the final LayerNorm of a layer) took 83 -> 88 allocated
+// registers -> two CTAs per SM -> its single wave of 444 CTAs ran as 1.5 waves: 28.3 us against 17.6 us for the bf16-dy
+// instantiation on the same rows (tools/kernel_bench.py ln).
 template <bool DY_BF16, int LN_MAXV, bool CAST>
-__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const void* __restrict__ dy,
+__global__ void __launch_bounds__(LN_WARPS * 32, LN_MAXV <= 2 ? 3 : (LN_MAXV <= 4 ? 2 : 1)) layernorm_bwd_kernel(const void* __restrict__ dy,
                                                                       const float* __restrict__ x,
                                                                       const float* __restrict__ gamma,
                                                                       const float* __restrict__ mean_in,
@@ -380,10 +384,10 @@ extern "C" int b2c_layernorm_fwd(const float* x, const float* gamma, const float
   B2C_REQUIRE(x && gamma && beta && y, "b2c_layernorm_fwd: null pointer");
   B2C_REQUIRE(d % 4 == 0 && d > 0 && d <= 128 * LN_MAX_CHUNKS, "b2c_layernorm_fwd: d=%d must be a multiple of 4, <= 1024", d);
   if (rows <= 0) return 0;
-  const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define B2C_LN_FWD(BF, NV) B2C_CUDA(launch_k(layernorm_fwd_kernel<BF, NV>, dim3(grid), dim3(LN_WARPS * 32), 0, st, x, gamma, beta, y, mean, rstd, rows, d, eps))
   const int nv = (d / 4 + 31) / 32;
+  const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
+#define B2C_LN_FWD(BF, NV) B2C_CUDA(launch_k(layernorm_fwd_kernel<BF, NV>, dim3(grid), dim3(LN_WARPS * 32), 0, st, x, gamma, beta, y, mean, rstd, rows, d, eps))
   if (y_dtype == B2C_BF16) { if (nv <= 2) B2C_LN_FWD(true, 2); else if (nv <= 4) B2C_LN_FWD(true, 4); else B2C_LN_FWD(true, 8); }
   else                     { if (nv <= 2) B2C_LN_FWD(false, 2); else if (nv <= 4) B2C_LN_FWD(false, 4); else B2C_LN_FWD(false, 8); }
 #undef B2C_LN_FWD
@@ -397,17 +401,19 @@ static int layernorm_bwd_launch(const void* dy, int dy_dtype, const float* x, co
   B2C_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "b2c_layernorm_bwd: null pointer");
   B2C_REQUIRE(d % 4 == 0 && d > 0 && d <= 128 * LN_MAX_CHUNKS, "b2c_layernorm_bwd: d=%d must be a multiple of 4, <= 1024", d);
   if (rows <= 0) return 0;
-  // ONE wave of CTAs (3 co-resident per SM at 256 threads x ~80 registers): each warp walks a contiguous run of rows, so
-  // the parameter-gradient atomics stay rare and no partial last wave trails behind (995 CTAs on 444 slots used to run
-  // as 2.24 waves)
-  const int64_t target_warps = static_cast<int64_t>(num_sms()) * 3 * LN_WARPS;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nv = (d / 4 + 31) / 32;
+  LnCast c0 = {};
+  // ONE wave of CTAs (3 / 2 / 1 co-resident per SM for d <= 256 / 512 / 1024: the kernel's launch bounds cap its registers at
+  // 80 / 128 / 255): each warp walks a contiguous run of rows, so the parameter-gradient atomics stay rare and no partial
+  // last wave trails behind (995 CTAs on 444 slots used to run as 2.24 waves)
+  const int per_sm = nv <= 2 ? 3 : (nv <= 4 ? 2 : 1);
+  const int64_t target_warps = static_cast<int64_t>(num_sms()) * per_sm * LN_WARPS;
   int rows_per_warp = static_cast<int>((rows + target_warps - 1) / target_warps);
   if (rows_per_warp < 1) rows_per_warp = 1;
   const int64_t warps = (rows + rows_per_warp - 1) / rows_per_warp;
   const unsigned grid = static_cast<unsigned>((warps + LN_WARPS - 1) / LN_WARPS);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = (cast ? 3 : 2) * d * sizeof(float);
-  LnCast c0 = {};
 #define B2C_LN_BWD(BF, NV)                                                                                      \
   do {                                                                                                          \
     if (cast) B2C_CUDA(launch_k(layernorm_bwd_kernel<BF, NV, true>, dim3(grid), dim3(LN_WARPS * 32), smem, st,                            \
@@ -415,7 +421,6 @@ static int layernorm_bwd_launch(const void* dy, int dy_dtype, const float* x, co
     else B2C_CUDA(launch_k(layernorm_bwd_kernel<BF, NV, false>, dim3(grid), dim3(LN_WARPS * 32), smem, st,                                \
         dy, x, gamma, mean, rstd, dx, dx_accumulate, dgamma, dbeta, rows, d, rows_per_warp, c0));               \
   } while (0)
-  const int nv = (d / 4 + 31) / 32;
   if (dy_dtype == B2C_BF16) { if (nv <= 2) B2C_LN_BWD(true, 2); else if (nv <= 4) B2C_LN_BWD(true, 4); else B2C_LN_BWD(true, 8); }
   else                      { if (nv <= 2) B2C_LN_BWD(false, 2); else if (nv <= 4) B2C_LN_BWD(false, 4); else B2C_LN_BWD(false, 8); }
 #undef B2C_LN_BWD

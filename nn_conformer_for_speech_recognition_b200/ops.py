@@ -57,8 +57,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_mn: bool
     ep.out_dtype = BF16 if out.dtype == torch.bfloat16 else F32
     ep.accumulate = int(accumulate)
     ep.colsum = ptr(colsum)
+    # algorithmic HBM bytes of the launch: both operands once, every epilogue operand once, the output(s) once
+    osz = 2 if out.dtype == torch.bfloat16 else 4
+    nbytes = 2.0 * (M * K + N * K) + M * N * (osz * (2 if accumulate else 1) + (2 if out2 is not None else 0)
+                                             + (2 if aux is not None else 0) + (4 if resid is not None else 0))
     call("b2c_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), M, N, K, split_k, block_n,
-         ctypes.byref(ep), stream_ptr(), flops=2.0 * M * N * K)
+         ctypes.byref(ep), stream_ptr(), flops=2.0 * M * N * K, nbytes=nbytes)
     return out
 
 

@@ -103,6 +103,13 @@ def main():
     y, mean, rstd = ops.layernorm_fwd(x, g, be, save_stats=True)
     dx, dg, db = torch.zeros_like(x), torch.zeros(d, device=dev), torch.zeros(d, device=dev)
     rec("layernorm bwd (dy bf16, accumulate)", timeit(lambda: ops.layernorm_bwd(out_d, x, g, mean, rstd, dx, True, dg, db)), 0, M * d * (4 + 2 + 8))
+    csum = torch.zeros(d, device=dev)
+    rec("layernorm fwd fp32 (final LN)", timeit(lambda: ops.layernorm_fwd(x, g, be, out_dtype=torch.float32, save_stats=True)), 0, M * d * 8)
+    rec("layernorm bwd + cast (dy bf16, accumulate, dropout 0.5)",
+        timeit(lambda: ops.layernorm_bwd(out_d, x, g, mean, rstd, dx, True, dg, db, cast=(0.5, 0.5, 7, csum))), 0, M * d * (4 + 2 + 8 + 2))
+    dxn = torch.empty_like(x)
+    rec("layernorm bwd + cast (dy fp32, out of place: final LN)",
+        timeit(lambda: ops.layernorm_bwd(dx, x, g, mean, rstd, dxn, False, dg, db, cast=(0.5, 0.5, 7, csum))), 0, M * d * (4 + 4 + 4 + 2))
     qkv = torch.randn(M, 3 * H * 64, device=dev).to(bf)
     lens = torch.full((B,), T, device=dev, dtype=torch.int32)
     sec("attn")
