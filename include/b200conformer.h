@@ -119,6 +119,23 @@ int b2c_layernorm_bwd_cast(const void* dy, int dy_dtype, const float* x, const f
                            int d, void* cast_out, float alpha, float drop_p, uint64_t drop_seed, float* colsum,
                            void* stream);
 
+/* Two LayerNorms back to back -- the final LayerNorm of Conformer layer i (torchaudio conformer.py:211) followed by the
+ * LayerNorm of layer i+1's first feed-forward module (conformer.py:103,185) -- in one pass over the rows:
+ *   _fwd_pair: y1 = LN1(x) (fp32, stored), a2 = LN2(y1) (bf16, stored); mean/rstd of both saved when non-null.
+ *              Bit-identical to b2c_layernorm_fwd(x -> y1, fp32) followed by b2c_layernorm_fwd(y1 -> a2, bf16).
+ *   _bwd_pair: dy1 = prev + LN2'(da2; y1);  dx = LN1'(dy1; x);  cast_out = bf16(alpha * dropout(dx)), colsum += its column
+ *              sums; dgamma / dbeta of BOTH LayerNorms are accumulated (atomicAdd).  Equals b2c_layernorm_bwd(da2, y1, ...,
+ *              dx = prev, accumulate = 1) followed by b2c_layernorm_bwd_cast(prev, fp32, x, ..., dx, accumulate = 0, ...)
+ *              without writing / re-reading the intermediate gradient.  `prev` is only read. */
+int b2c_layernorm_fwd_pair(const float* x, const float* gamma1, const float* beta1, float* y1, float* mean1, float* rstd1,
+                           const float* gamma2, const float* beta2, void* a2, float* mean2, float* rstd2, int64_t rows,
+                           int d, float eps, void* stream);
+int b2c_layernorm_bwd_pair(const void* da2, const float* y1, const float* gamma2, const float* mean2, const float* rstd2,
+                           float* dgamma2, float* dbeta2, const float* prev, const float* x, const float* gamma1,
+                           const float* mean1, const float* rstd1, float* dgamma1, float* dbeta1, float* dx, int64_t rows,
+                           int d, void* cast_out, float alpha, float drop_p, uint64_t drop_seed, float* colsum,
+                           void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Conv-module chain  GLU -> depthwise conv1d('same', cross-correlation) -> BatchNorm1d -> SiLU
  * (conformer.py:52-65; frames past `lengths` are NOT zeroed, conformer.py:85-88).

@@ -50,6 +50,8 @@ SIGNATURES = {
     "b2c_layernorm_fwd": [_P, _P, _P, _P, _I, _P, _P, _L, _I, _F, _P],
     "b2c_layernorm_bwd": [_P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],
     "b2c_layernorm_bwd_cast": [_P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P, _F, _F, c_uint64, _P, _P],
+    "b2c_layernorm_fwd_pair": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
+    "b2c_layernorm_bwd_pair": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _F, _F, c_uint64, _P, _P],
     "b2c_convmod_eval_fwd": [_P, _P, _P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _P],
     "b2c_convmod_dw_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b2c_convmod_bn_finalize": [_P, _L, _F, _F, _P, _P, _P, _P, _I, _P],

@@ -16,7 +16,7 @@ from typing import List
 import torch
 
 from . import _lib, ops
-from .conformer import HEAD_PAD, Conformer, _get, run_layers
+from .conformer import _LN_PAIR, HEAD_PAD, Conformer, _get, run_layers
 
 
 def conformer_apply(model: Conformer, inp: torch.Tensor, lengths_i32: torch.Tensor) -> torch.Tensor:
@@ -165,6 +165,7 @@ class _ConformerFn(torch.autograd.Function):
                          split_k=_split_k(M, tiles))
             keep.append((dyb, act))
 
+        pending = None
         for li in reversed(range(model.num_layers)):
             layer = model.conformer_layers[li]
             st = ctx.state[li]
@@ -178,12 +179,22 @@ class _ConformerFn(torch.autograd.Function):
             # pass over dx instead of LayerNorm-backward followed by a separate scale/cast kernel
             s5 = st["final"]
             dx_new = torch.empty_like(dx)
-            dyb = ops.layernorm_bwd(dx, s5["x"], P("final_layer_norm.weight"), s5["mean"], s5["rstd"], dx_new, False,
-                                    G(li, "final_layer_norm.weight"), G(li, "final_layer_norm.bias"),
-                                    cast=(0.5, drop_p, sd + 12 + 1, G(li, "ffn2.sequential.4.bias")))
+            if pending is not None:
+                # the layer above left its first LayerNorm's backward undone: both LayerNorms in one pass over the rows
+                # (b2c_layernorm_bwd_pair: the intermediate gradient is neither written nor re-read)
+                da2, y1, g2, m2, r2, dg2, db2 = pending
+                pending = None
+                dyb = ops.layernorm_bwd_pair(da2, y1, g2, m2, r2, dg2, db2, dx, s5["x"], P("final_layer_norm.weight"),
+                                             s5["mean"], s5["rstd"], G(li, "final_layer_norm.weight"),
+                                             G(li, "final_layer_norm.bias"), dx_new,
+                                             cast=(0.5, drop_p, sd + 12 + 1, G(li, "ffn2.sequential.4.bias")))
+            else:
+                dyb = ops.layernorm_bwd(dx, s5["x"], P("final_layer_norm.weight"), s5["mean"], s5["rstd"], dx_new, False,
+                                        G(li, "final_layer_norm.weight"), G(li, "final_layer_norm.bias"),
+                                        cast=(0.5, drop_p, sd + 12 + 1, G(li, "ffn2.sequential.4.bias")))
             dx = dx_new
 
-            def ffn_bwd(pre, site, dyb, next_cast):
+            def ffn_bwd(pre, site, dyb, next_cast, defer=False):
                 s = st[pre]
                 wgrad(dyb, s["h"], d, f, G(li, pre + ".sequential.4.weight"))
                 # s["u"] holds B2C_DROPPED_PREACT where the forward dropped the activation (SiLU' = 0 there), so the mask is
@@ -192,6 +203,9 @@ class _ConformerFn(torch.autograd.Function):
                               aux=s["u"], alpha=keep_scale, colsum=G(li, pre + ".sequential.1.bias"))
                 wgrad(du, s["a"], f, d, G(li, pre + ".sequential.1.weight"))
                 da = ops.gemm(du, w[pre + ".sequential.1.weight"], M=M, N=d, K=f, b_mn=True)
+                if defer:          # this LayerNorm's backward runs fused with the final LayerNorm of the layer below
+                    return (da, s["x"], P(pre + ".sequential.0.weight"), s["mean"], s["rstd"],
+                            G(li, pre + ".sequential.0.weight"), G(li, pre + ".sequential.0.bias"))
                 return ops.layernorm_bwd(da, s["x"], P(pre + ".sequential.0.weight"), s["mean"], s["rstd"], dx, True,
                                          G(li, pre + ".sequential.0.weight"), G(li, pre + ".sequential.0.bias"),
                                          cast=next_cast)
@@ -242,8 +256,11 @@ class _ConformerFn(torch.autograd.Function):
                                     G(li, "self_attn_layer_norm.weight"), G(li, "self_attn_layer_norm.bias"),
                                     cast=(0.5, drop_p, sd + 0 + 1, G(li, "ffn1.sequential.4.bias")))
 
-            # ---- 1. FFN1
-            ffn_bwd("ffn1", 0, dyb, None)
+            # ---- 1. FFN1 (its LayerNorm is deferred into the pair kernel of the layer below, unless this layer's gradients
+            # are about to be handed to the gradient exchange: a span must be final when it leaves)
+            defer = _LN_PAIR and li > 0 and d <= 512 and not (gsync is not None and li in group_lo)
+            r = ffn_bwd("ffn1", 0, dyb, None, defer)
+            pending = r if defer else None
             ctx.state[li] = None                  # free this layer's saved activations
             if gsync is not None and li in group_lo:
                 # every gradient of layers [li, group end) is final: hand the arena span to the gradient exchange now, so

@@ -34,6 +34,9 @@ HEAD_PAD = 64          # the attention kernel's head dimension
 # tile re-streams the 1 MB of weights through one SM's L2 port), so it is opt-in: B2C_FFN_FUSED=1.
 _FFN_FUSED = os.environ.get("B2C_FFN_FUSED", "0") == "1"
 _LAYER_CALLS = os.environ.get("B2C_LAYER_CALLS", "1") != "0"      # 0: eval issues every launch from Python (debug / profiling)
+# the final LayerNorm of layer i and the first LayerNorm of layer i+1 run as ONE kernel, forward and backward
+# (b2c_layernorm_fwd_pair / _bwd_pair); B2C_LN_PAIR=0 keeps them separate (A/B timing, bit-identity test)
+_LN_PAIR = os.environ.get("B2C_LN_PAIR", "1") != "0"
 
 
 class _FeedForwardModule(nn.Module):
@@ -391,6 +394,7 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
     if bn_train:
         torch._foreach_add_([l.conv_module.sequential[3].num_batches_tracked for l in model.conformer_layers], 1)
 
+    pending_ln = []        # (a, mean, rstd) of the next layer's first LayerNorm when the pair kernel has already produced it
     for li, layer in enumerate(model.conformer_layers):
         w = weights[li]
         P = lambda name: _get(layer, name)                                      # noqa: E731
@@ -399,8 +403,11 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
 
         def ffn(x_in, pre, site):
             ln_w, ln_b = P(pre + ".sequential.0.weight"), P(pre + ".sequential.0.bias")
+            # the first feed-forward module's LayerNorm may already have run, fused with the previous layer's final
+            # LayerNorm (b2c_layernorm_fwd_pair at the bottom of this loop)
+            done = pending_ln.pop() if (pre == "ffn1" and pending_ln) else None
             if save:
-                a, mean, rstd = ops.layernorm_fwd(x_in, ln_w, ln_b, save_stats=True)
+                a, mean, rstd = done if done is not None else ops.layernorm_fwd(x_in, ln_w, ln_b, save_stats=True)
                 u = torch.empty((M, f), device=dev, dtype=bf)
                 h = ops.gemm(a, w[pre + ".sequential.1.weight"], M=M, N=f, K=d, bias=P(pre + ".sequential.1.bias"),
                              act=ops.ACT_SILU, out2=u, drop_p=drop_p, drop_seed=sd + site)
@@ -500,12 +507,20 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
             x = ffn(x, "ffn2", 12)
 
         # ---- 5. x = LN(x)                                                            conformer.py:211
+        # ... fused with the LayerNorm that follows it immediately, the one of the NEXT layer's first feed-forward module
+        # (conformer.py:103,185): one pass over the rows instead of two (b2c_layernorm_fwd_pair)
         ln_w, ln_b = P("final_layer_norm.weight"), P("final_layer_norm.bias")
+        nxt = model.conformer_layers[li + 1] if (_LN_PAIR and save and li + 1 < model.num_layers and d <= 512) else None
         if save:
-            x_out, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, out_dtype=torch.float32, save_stats=True)
+            if nxt is not None:
+                x_out, mean, rstd, a_n, mean_n, rstd_n = ops.layernorm_fwd_pair(
+                    x, ln_w, ln_b, _get(nxt, "ffn1.sequential.0.weight"), _get(nxt, "ffn1.sequential.0.bias"), save_stats=True)
+                pending_ln.append((a_n, mean_n, rstd_n))
+            else:
+                x_out, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, out_dtype=torch.float32, save_stats=True)
             st["final"] = dict(x=x, mean=mean, rstd=rstd)
             train_state.append(st)
             x = x_out
-        else:
+        else:              # inference keeps the launch sequence of b2c_conformer_layer_eval (bit-identical paths)
             x = ops.layernorm_fwd(x, ln_w, ln_b, out_dtype=torch.float32)
     return x

@@ -208,6 +208,229 @@ __global__ void __launch_bounds__(LN_WARPS * 32, LN_MAXV <= 2 ? 3 : (LN_MAXV <= 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- LayerNorm pairs
+// Between two Conformer layers the stream passes through TWO LayerNorms back to back: the final LayerNorm of layer i
+// (conformer.py:211, fp32 output = the next layer's residual stream) and the LayerNorm of layer i+1's first feed-forward
+// module (conformer.py:103, bf16 output = a GEMM operand).  Run separately the second one re-reads what the first has just
+// written; the pair kernels keep the row in registers: y1 = LN1(x) is stored AND normalised again, a2 = LN2(y1).
+// Same instruction sequence per row as two layernorm_fwd_kernel launches, so the results are bit-identical.
+template <int LN_MAXV>
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_pair_kernel(
+    const float* __restrict__ x, const float* __restrict__ gamma1, const float* __restrict__ beta1, float* __restrict__ y1,
+    float* __restrict__ mean1_out, float* __restrict__ rstd1_out, const float* __restrict__ gamma2,
+    const float* __restrict__ beta2, __nv_bfloat16* __restrict__ a2, float* __restrict__ mean2_out,
+    float* __restrict__ rstd2_out, int64_t rows, int d, float eps) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = d >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+  float4 v[LN_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      v[i] = xr[c];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(s) / d;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, e = v[i].w - mean;
+      ss += a * a + b * b + cc * cc + e * e;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / d + eps);
+  if (lane == 0) {
+    if (mean1_out) mean1_out[row] = mean;
+    if (rstd1_out) rstd1_out[row] = rstd;
+  }
+  s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma1) + c), b = __ldg(reinterpret_cast<const float4*>(beta1) + c);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      reinterpret_cast<float4*>(y1 + row * d)[c] = o;
+      v[i] = o;                                        // the second LayerNorm's input
+      s += o.x + o.y + o.z + o.w;
+    }
+  }
+  const float mean2 = warp_sum(s) / d;
+  ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      const float a = v[i].x - mean2, b = v[i].y - mean2, cc = v[i].z - mean2, e = v[i].w - mean2;
+      ss += a * a + b * b + cc * cc + e * e;
+    }
+  }
+  const float rstd2 = rsqrtf(warp_sum(ss) / d + eps);
+  if (lane == 0) {
+    if (mean2_out) mean2_out[row] = mean2;
+    if (rstd2_out) rstd2_out[row] = rstd2;
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma2) + c), b = __ldg(reinterpret_cast<const float4*>(beta2) + c);
+      float4 o;
+      o.x = (v[i].x - mean2) * rstd2 * g.x + b.x;
+      o.y = (v[i].y - mean2) * rstd2 * g.y + b.y;
+      o.z = (v[i].z - mean2) * rstd2 * g.z + b.z;
+      o.w = (v[i].w - mean2) * rstd2 * g.w + b.w;
+      reinterpret_cast<uint2*>(a2 + row * d)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    }
+  }
+}
+
+// Backward of the pair, one pass: the gradient arriving at a2 (bf16, from the feed-forward module's dgrad GEMM) goes
+// through LN2 and is added to the running residual-stream gradient `prev` (what layernorm_bwd_kernel<true,..,false> does
+// with accumulate = 1); the sum goes through LN1 and leaves as dx (fp32) and as cast_out = bf16(alpha * dropout(dx)) with
+// its column sums (what layernorm_bwd_kernel<false,..,true> does): the intermediate gradient is neither written nor re-read.
+struct LnPairBwd {
+  const __nv_bfloat16* da2;                            // gradient w.r.t. a2
+  const float* y1;   const float* gamma2; const float* mean2; const float* rstd2; float* dgamma2; float* dbeta2;
+  const float* prev;                                   // running gradient w.r.t. y1 (read only)
+  const float* x;    const float* gamma1; const float* mean1; const float* rstd1; float* dgamma1; float* dbeta1;
+  float* dx;                                           // out: gradient w.r.t. x
+};
+template <int LN_MAXV>
+__global__ void __launch_bounds__(LN_WARPS * 32, LN_MAXV <= 2 ? 2 : 1) layernorm_bwd_pair_kernel(const LnPairBwd a, int64_t rows, int d,
+                                                                                                 int rows_per_warp, LnCast cast) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float red[];           // [5][d]: dgamma2, dbeta2, dgamma1, dbeta1, cast column sums
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = d >> 2;
+  for (int i = threadIdx.x; i < 5 * d; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float4 dg2[LN_MAXV], db2[LN_MAXV], dg1[LN_MAXV], db1[LN_MAXV], cs[LN_MAXV];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) dg2[i] = db2[i] = dg1[i] = db1[i] = cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  DropCfg drop = cast.drop;
+  if (drop.thresh16) drop = drop_resolve(drop);
+  const float4* g2p = reinterpret_cast<const float4*>(a.gamma2);
+  const float4* g1p = reinterpret_cast<const float4*>(a.gamma1);
+  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp) * rows_per_warp;
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const int64_t row = row0 + rr;
+    if (row >= rows) break;
+    const float mean2 = a.mean2[row], rstd2 = a.rstd2[row], mean1 = a.mean1[row], rstd1 = a.rstd1[row];
+    float4 xh[LN_MAXV], g[LN_MAXV], t[LN_MAXV], xf[LN_MAXV];
+    // every operand of the row is fetched up front: one memory round trip for both LayerNorms
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        t[i] = reinterpret_cast<const float4*>(a.prev + row * d)[c];
+        xf[i] = reinterpret_cast<const float4*>(a.x + row * d)[c];
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        const float4 yv = reinterpret_cast<const float4*>(a.y1 + row * d)[c];
+        const uint2 u = reinterpret_cast<const uint2*>(a.da2 + row * d)[c];
+        const float2 p = unpack_bf16(u.x), q = unpack_bf16(u.y);
+        const float4 dyv = make_float4(p.x, p.y, q.x, q.y);
+        const float4 gm = __ldg(g2p + c);
+        xh[i] = make_float4((yv.x - mean2) * rstd2, (yv.y - mean2) * rstd2, (yv.z - mean2) * rstd2, (yv.w - mean2) * rstd2);
+        g[i] = make_float4(dyv.x * gm.x, dyv.y * gm.y, dyv.z * gm.z, dyv.w * gm.w);
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+        dg2[i].x += dyv.x * xh[i].x; dg2[i].y += dyv.y * xh[i].y; dg2[i].z += dyv.z * xh[i].z; dg2[i].w += dyv.w * xh[i].w;
+        db2[i].x += dyv.x; db2[i].y += dyv.y; db2[i].z += dyv.z; db2[i].w += dyv.w;
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+    float u1 = 0.f, u2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        // gradient w.r.t. y1 = LN2 backward + the running gradient (exactly the accumulate = 1 path)
+        float4 o;
+        o.x = rstd2 * (g[i].x - s1 - xh[i].x * s2);
+        o.y = rstd2 * (g[i].y - s1 - xh[i].y * s2);
+        o.z = rstd2 * (g[i].z - s1 - xh[i].z * s2);
+        o.w = rstd2 * (g[i].w - s1 - xh[i].w * s2);
+        o.x += t[i].x; o.y += t[i].y; o.z += t[i].z; o.w += t[i].w;
+        // ... which is the dy of LN1
+        const float4 gm = __ldg(g1p + c);
+        xh[i] = make_float4((xf[i].x - mean1) * rstd1, (xf[i].y - mean1) * rstd1, (xf[i].z - mean1) * rstd1, (xf[i].w - mean1) * rstd1);
+        g[i] = make_float4(o.x * gm.x, o.y * gm.y, o.z * gm.z, o.w * gm.w);
+        u1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        u2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+        dg1[i].x += o.x * xh[i].x; dg1[i].y += o.y * xh[i].y; dg1[i].z += o.z * xh[i].z; dg1[i].w += o.w * xh[i].w;
+        db1[i].x += o.x; db1[i].y += o.y; db1[i].z += o.z; db1[i].w += o.w;
+      }
+    }
+    u1 = warp_sum(u1) / d;
+    u2 = warp_sum(u2) / d;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        float4 o;
+        o.x = rstd1 * (g[i].x - u1 - xh[i].x * u2);
+        o.y = rstd1 * (g[i].y - u1 - xh[i].y * u2);
+        o.z = rstd1 * (g[i].z - u1 - xh[i].z * u2);
+        o.w = rstd1 * (g[i].w - u1 - xh[i].w * u2);
+        reinterpret_cast<float4*>(a.dx + row * d)[c] = o;
+        float f[4] = {o.x * cast.alpha, o.y * cast.alpha, o.z * cast.alpha, o.w * cast.alpha};
+        const uint64_t idx = static_cast<uint64_t>(row) * d + 4 * c;
+        if (drop.thresh16) {
+          float k0, k1, k2, k3;
+          drop_scale4g(drop, idx, k0, k1, k2, k3);
+          f[0] *= k0; f[1] *= k1; f[2] *= k2; f[3] *= k3;
+        }
+        const uint2 packed = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+        *reinterpret_cast<uint2*>(cast.out + idx) = packed;
+        const float2 p0 = unpack_bf16(packed.x), p1 = unpack_bf16(packed.y);   // sums of the ROUNDED values
+        cs[i].x += p0.x; cs[i].y += p0.y; cs[i].z += p1.x; cs[i].w += p1.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      const float4 acc[5] = {dg2[i], db2[i], dg1[i], db1[i], cs[i]};
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        atomicAdd(&red[k * d + 4 * c + 0], acc[k].x); atomicAdd(&red[k * d + 4 * c + 1], acc[k].y);
+        atomicAdd(&red[k * d + 4 * c + 2], acc[k].z); atomicAdd(&red[k * d + 4 * c + 3], acc[k].w);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(a.dgamma2 + i, red[i]);
+    atomicAdd(a.dbeta2 + i, red[d + i]);
+    atomicAdd(a.dgamma1 + i, red[2 * d + i]);
+    atomicAdd(a.dbeta1 + i, red[3 * d + i]);
+    if (cast.colsum) atomicAdd(cast.colsum + i, red[4 * d + i]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- helpers
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
   pdl_trigger();
@@ -545,6 +768,57 @@ extern "C" int b2c_repack_heads(const void* src, void* dst, int64_t rows, int nb
   if (n <= 0) return 0;
   B2C_CUDA(launch_k(repack_heads_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), rows, nblk, src_dh, dst_dh));
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2c_layernorm_fwd_pair(const float* x, const float* gamma1, const float* beta1, float* y1, float* mean1,
+                                      float* rstd1, const float* gamma2, const float* beta2, void* a2, float* mean2,
+                                      float* rstd2, int64_t rows, int d, float eps, void* stream) {
+  B2C_REQUIRE(x && gamma1 && beta1 && y1 && gamma2 && beta2 && a2, "b2c_layernorm_fwd_pair: null pointer");
+  B2C_REQUIRE(d % 4 == 0 && d > 0 && d <= 128 * LN_MAX_CHUNKS, "b2c_layernorm_fwd_pair: d=%d must be a multiple of 4, <= 1024", d);
+  if (rows <= 0) return 0;
+  const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define B2C_LN_PAIR(NV) B2C_CUDA(launch_k(layernorm_fwd_pair_kernel<NV>, dim3(grid), dim3(LN_WARPS * 32), 0, st, x, gamma1, beta1, y1, \
+                                          mean1, rstd1, gamma2, beta2, static_cast<__nv_bfloat16*>(a2), mean2, rstd2, rows, d, eps))
+  const int nv = (d / 4 + 31) / 32;
+  if (nv <= 2) B2C_LN_PAIR(2); else if (nv <= 4) B2C_LN_PAIR(4); else B2C_LN_PAIR(8);
+#undef B2C_LN_PAIR
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2c_layernorm_bwd_pair(const void* da2, const float* y1, const float* gamma2, const float* mean2,
+                                      const float* rstd2, float* dgamma2, float* dbeta2, const float* prev, const float* x,
+                                      const float* gamma1, const float* mean1, const float* rstd1, float* dgamma1,
+                                      float* dbeta1, float* dx, int64_t rows, int d, void* cast_out, float alpha,
+                                      float drop_p, uint64_t drop_seed, float* colsum, void* stream) {
+  B2C_REQUIRE(da2 && y1 && gamma2 && mean2 && rstd2 && dgamma2 && dbeta2 && prev && x && gamma1 && mean1 && rstd1 && dgamma1 &&
+                  dbeta1 && dx && cast_out, "b2c_layernorm_bwd_pair: null pointer");
+  B2C_REQUIRE(d % 4 == 0 && d > 0 && d <= 128 * LN_MAX_CHUNKS, "b2c_layernorm_bwd_pair: d=%d must be a multiple of 4, <= 1024", d);
+  if (rows <= 0) return 0;
+  LnPairBwd a;
+  a.da2 = static_cast<const __nv_bfloat16*>(da2);
+  a.y1 = y1; a.gamma2 = gamma2; a.mean2 = mean2; a.rstd2 = rstd2; a.dgamma2 = dgamma2; a.dbeta2 = dbeta2;
+  a.prev = prev;
+  a.x = x; a.gamma1 = gamma1; a.mean1 = mean1; a.rstd1 = rstd1; a.dgamma1 = dgamma1; a.dbeta1 = dbeta1;
+  a.dx = dx;
+  LnCast c;
+  c.out = static_cast<__nv_bfloat16*>(cast_out); c.colsum = colsum; c.alpha = alpha;
+  c.drop = make_drop(drop_p, drop_seed);
+  const int nv = (d / 4 + 31) / 32;
+  const int per_sm = nv <= 2 ? 2 : 1;                 // launch bounds of the kernel: 128 registers for d <= 256
+  const int64_t target_warps = static_cast<int64_t>(num_sms()) * per_sm * LN_WARPS;
+  int rows_per_warp = static_cast<int>((rows + target_warps - 1) / target_warps);
+  if (rows_per_warp < 1) rows_per_warp = 1;
+  const int64_t warps = (rows + rows_per_warp - 1) / rows_per_warp;
+  const unsigned grid = static_cast<unsigned>((warps + LN_WARPS - 1) / LN_WARPS);
+  const size_t smem = 5 * static_cast<size_t>(d) * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define B2C_LN_PAIRB(NV) B2C_CUDA(launch_k(layernorm_bwd_pair_kernel<NV>, dim3(grid), dim3(LN_WARPS * 32), smem, st, a, rows, d, rows_per_warp, c))
+  if (nv <= 2) B2C_LN_PAIRB(2); else if (nv <= 4) B2C_LN_PAIRB(4); else B2C_LN_PAIRB(8);
+#undef B2C_LN_PAIRB
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

@@ -117,6 +117,37 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx, accumulate: bool, dgamma, dbeta,
     return out
 
 
+def layernorm_fwd_pair(x, gamma1, beta1, gamma2, beta2, *, save_stats: bool = False, eps: float = 1e-5, out1=None, out2=None):
+    """y1 = LN1(x) (fp32), a2 = LN2(y1) (bf16) in one pass -- see b2c_layernorm_fwd_pair.
+    Returns (y1, a2) or (y1, mean1, rstd1, a2, mean2, rstd2)."""
+    _lib.require_device()
+    _check(x, torch.float32, "x")
+    d = x.shape[-1]
+    rows = x.numel() // d
+    y1 = out1 if out1 is not None else torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    a2 = out2 if out2 is not None else torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    m1 = r1 = m2 = r2 = None
+    if save_stats:
+        m1, r1, m2, r2 = (torch.empty(rows, device=x.device, dtype=torch.float32) for _ in range(4))
+    call("b2c_layernorm_fwd_pair", ptr(x), ptr(gamma1), ptr(beta1), ptr(y1), ptr(m1), ptr(r1), ptr(gamma2), ptr(beta2), ptr(a2),
+         ptr(m2), ptr(r2), rows, d, eps, stream_ptr())
+    return (y1, m1, r1, a2, m2, r2) if save_stats else (y1, a2)
+
+
+def layernorm_bwd_pair(da2, y1, gamma2, mean2, rstd2, dgamma2, dbeta2, prev, x, gamma1, mean1, rstd1, dgamma1, dbeta1, dx, cast):
+    """Backward of `layernorm_fwd_pair`: dx = LN1'(prev + LN2'(da2)), returns bf16(alpha * dropout(dx)) -- see
+    b2c_layernorm_bwd_pair.  cast = (alpha, drop_p, drop_seed, colsum)."""
+    _check(da2, torch.bfloat16, "da2")
+    d = x.shape[-1]
+    rows = x.numel() // d
+    alpha, drop_p, drop_seed, colsum = cast
+    out = torch.empty((rows, d), device=dx.device, dtype=torch.bfloat16)
+    call("b2c_layernorm_bwd_pair", ptr(da2), ptr(y1), ptr(gamma2), ptr(mean2), ptr(rstd2), ptr(dgamma2), ptr(dbeta2), ptr(prev),
+         ptr(x), ptr(gamma1), ptr(mean1), ptr(rstd1), ptr(dgamma1), ptr(dbeta1), ptr(dx), rows, d, ptr(out), alpha, drop_p,
+         drop_seed, ptr(colsum), stream_ptr())
+    return out
+
+
 def convmod_eval(u, wdw, bdw, bn_w, bn_b, bn_mean, bn_var, B: int, T: int, eps: float = 1e-5):
     _lib.require_device()
     _check(u, torch.bfloat16, "u")

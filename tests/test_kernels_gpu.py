@@ -168,6 +168,51 @@ def test_layernorm_fwd_bwd(ops, rows, d):
         _close(db, beta.grad, rel=rel, abs_=1e-3, name="ln dbeta")
 
 
+@pytest.mark.parametrize("rows,d", [(1000, 256), (77, 144), (300, 512), (23872, 256), (5, 16)])
+def test_layernorm_pair_kernels_equal_two_single_launches(ops, rows, d):
+    """b2c_layernorm_fwd_pair / _bwd_pair (final LayerNorm of layer i + first LayerNorm of layer i+1 in one pass) against the
+    two single-LayerNorm launches they replace: outputs, statistics, dx and the fused cast bit for bit; parameter
+    gradients / column sums are atomics in another order (fp32 tolerance)."""
+    g = torch.Generator(device="cuda").manual_seed(rows * 7 + d)
+    rnd = lambda *shape: torch.randn(*shape, device="cuda", generator=g)          # noqa: E731
+    x = rnd(rows, d) * 1.7 + 0.4
+    g1, b1, g2, b2 = 1 + 0.2 * rnd(d), 0.3 * rnd(d), 1 + 0.2 * rnd(d), 0.3 * rnd(d)
+    # ---- forward
+    y_ref, m1_ref, r1_ref = ops.layernorm_fwd(x, g1, b1, out_dtype=torch.float32, save_stats=True)
+    a_ref, m2_ref, r2_ref = ops.layernorm_fwd(y_ref, g2, b2, save_stats=True)
+    y, m1, r1, a, m2, r2 = ops.layernorm_fwd_pair(x, g1, b1, g2, b2, save_stats=True)
+    for got, ref, name in ((y, y_ref, "y1"), (m1, m1_ref, "mean1"), (r1, r1_ref, "rstd1")):
+        assert torch.equal(got, ref), name                # the first LayerNorm is the same instruction sequence
+    for got, ref, name in ((m2, m2_ref, "mean2"), (r2, r2_ref, "rstd2")):
+        _close(got, ref, rel=1e-6, abs_=1e-7, name=name)
+    mism = (a.view(torch.int16) != a_ref.view(torch.int16)).float().mean().item()
+    assert mism < 1e-3, f"a2: {mism:.2e} of the bf16 words differ"
+    _close(a, a_ref, rel=1e-2, abs_=1e-2, name="a2")
+    y_b, a_b = ops.layernorm_fwd_pair(x, g1, b1, g2, b2)                            # no statistics requested
+    assert torch.equal(y_b, y) and torch.equal(a_b.view(torch.int16), a.view(torch.int16))
+    # ---- backward
+    da = _bf(rnd(rows, d))
+    prev = rnd(rows, d)
+    for drop_p in (0.0, 0.5):
+        z = lambda: torch.zeros(d, device="cuda")                                   # noqa: E731
+        dg2_r, db2_r, dg1_r, db1_r, cs_r = z(), z(), z(), z(), z()
+        mid = prev.clone()
+        ops.layernorm_bwd(da, y_ref, g2, m2_ref, r2_ref, mid, True, dg2_r, db2_r)
+        dx_r = torch.empty_like(x)
+        cast_r = ops.layernorm_bwd(mid, x, g1, m1_ref, r1_ref, dx_r, False, dg1_r, db1_r, cast=(0.5, drop_p, 91, cs_r))
+        dg2, db2, dg1, db1, cs = z(), z(), z(), z(), z()
+        dx = torch.empty_like(x)
+        keep = prev.clone()
+        cast = ops.layernorm_bwd_pair(da, y_ref, g2, m2_ref, r2_ref, dg2, db2, keep, x, g1, m1_ref, r1_ref, dg1, db1, dx,
+                                      cast=(0.5, drop_p, 91, cs))
+        assert torch.equal(keep, prev), "prev must only be read"
+        _close(dx, dx_r, rel=1e-6, abs_=1e-6, name="pair dx")
+        assert (cast.float() - cast_r.float()).abs().max().item() <= 1e-2 * cast_r.float().abs().max().item()
+        assert ((cast.view(torch.int16) != cast_r.view(torch.int16)).float().mean().item()) < 1e-3   # same mask, same rounding
+        for got, ref, name in ((dg2, dg2_r, "dgamma2"), (db2, db2_r, "dbeta2"), (dg1, dg1_r, "dgamma1"), (db1, db1_r, "dbeta1"), (cs, cs_r, "colsum")):
+            _close(got, ref, rel=1e-4, abs_=1e-3, name=f"pair {name}")
+
+
 # ----------------------------------------------------------------------------------------------- conv module chain
 def test_layernorm_bwd_fused_cast_equals_separate_scale_cast(ops):
     """b2c_layernorm_bwd_cast = b2c_layernorm_bwd followed by b2c_scale_cast on the new dx, bit for bit (same dropout
