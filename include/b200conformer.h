@@ -155,6 +155,11 @@ int b2c_convmod_bn_finalize(const double* stats, int64_t count, float eps, float
                             float* running_mean, float* running_var, int d, void* stream);
 int b2c_convmod_bn_apply(const void* y, const float* mean, const float* rstd, const float* bn_w, const float* bn_b,
                          void* out, int64_t rows, int d, void* stream);
+/* _bn_finalize + _bn_apply in one launch (training forward): bit-identical results, mean / rstd / running statistics written
+ * by the kernel's first CTA */
+int b2c_convmod_bn_finalize_apply(const void* y, const double* stats, int64_t count, float eps, float momentum,
+                                  const float* bn_w, const float* bn_b, void* out, float* mean, float* rstd,
+                                  float* running_mean, float* running_var, int64_t rows, int d, void* stream);
 /* backward of the chain.  dc = grad wrt the chain output (bf16 [rows,d]); y = saved depthwise output; mean/rstd = the
  * statistics the forward normalised with (batch stats in train mode, running stats -> rstd = 1/sqrt(var+eps) in eval).
  *  _bn_bwd_reduce: fp64 sums [2*d] (zeroed by the caller): S1 = sum dz, S2 = sum dz*yhat, dz = dc*SiLU'(z)

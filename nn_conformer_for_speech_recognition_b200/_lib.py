@@ -56,6 +56,7 @@ SIGNATURES = {
     "b2c_convmod_dw_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b2c_convmod_bn_finalize": [_P, _L, _F, _F, _P, _P, _P, _P, _I, _P],
     "b2c_convmod_bn_apply": [_P, _P, _P, _P, _P, _P, _L, _I, _P],
+    "b2c_convmod_bn_finalize_apply": [_P, _P, _L, _F, _F, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
     "b2c_convmod_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
     "b2c_convmod_dw_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b2c_attention_bwd": [_P, _L, _L, _L, _P, _P, _P, _L, _P, _P, _P, _P, _I, _I, _I, _F, _F, c_uint64, _P],
@@ -102,7 +103,7 @@ HOST_SIGNATURES = {
 
 _lib = None
 LAUNCHES = 0          # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 2, "b2c_convsub_compose_bwd": 2, "b2c_attention_bwd": 4, "b2c_attention_rel_bwd": 4, "b2c_conformer_layer_eval": 20, "b2c_adafactor_step": 5, "b2c_ctc_loss": 3, "b2c_logmel": 2, "b2c_version": 0, "b2c_device_check": 0, "b2c_dropout_epoch_use": 0}
+_LAUNCHES_PER_CALL = {"b2c_convsub_compose": 1, "b2c_convsub_compose_bwd": 2, "b2c_attention_bwd": 4, "b2c_attention_rel_bwd": 4, "b2c_conformer_layer_eval": 20, "b2c_adafactor_step": 5, "b2c_ctc_loss": 3, "b2c_logmel": 2, "b2c_version": 0, "b2c_device_check": 0, "b2c_dropout_epoch_use": 0}
 
 
 def load() -> ctypes.CDLL:

@@ -482,9 +482,8 @@ def run_layers(model: Conformer, x: torch.Tensor, lengths_i32: torch.Tensor, B: 
                          bias=P("conv_module.sequential.0.bias"), out=u_buf)
         if bn_train:
             y, stats = ops.convmod_dw_fwd(u, wdw, bdw, B, T, stats=stats_all[li])
-            bmean, brstd = ops.convmod_bn_finalize(stats, M, bn.running_mean, bn.running_var, bn.eps,
-                                                   bn.momentum if bn.momentum is not None else 0.1)
-            c = ops.convmod_bn_apply(y, bmean, brstd, bn.weight, bn.bias)
+            c, bmean, brstd = ops.convmod_bn_finalize_apply(y, stats, M, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                                            bn.eps, bn.momentum if bn.momentum is not None else 0.1)
         elif force_two_pass:     # eval-mode BatchNorm under autograd: keep y, normalise with the running statistics
             y, _ = ops.convmod_dw_fwd(u, wdw, bdw, B, T, stats=stats_all[li])
             bmean, brstd = bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)

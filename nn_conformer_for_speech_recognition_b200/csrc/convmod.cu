@@ -266,6 +266,68 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
   }
 }
 
+// bn_finalize + bn_apply in ONE launch (training forward: dw -> finalize -> apply was three launches; the finalize kernel is two
+// CTAs of pure latency between two memory passes).  Every thread derives mean / rstd of its own 8 channels from the fp64
+// sums -- the same expressions, rounded to fp32 at the same points, as bn_finalize_kernel, so the result is bit-identical to
+// the two-launch path -- and CTA 0 also publishes mean / rstd (the backward pass needs them) and updates the running statistics.
+__global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const __nv_bfloat16* __restrict__ y, const double* __restrict__ stats,
+                                                               double count, float eps, float momentum,
+                                                               const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                                                               __nv_bfloat16* __restrict__ out, float* __restrict__ mean_out,
+                                                               float* __restrict__ rstd_out, float* __restrict__ running_mean,
+                                                               float* __restrict__ running_var, int64_t rows, int d,
+                                                               int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
+  const int cg = d >> 3, rpi = 256 / cg;
+  const int tr = threadIdx.x / cg, tg = threadIdx.x - tr * cg;
+  if (tr >= rpi) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = tg * 8 + j;
+    const double mu = stats[c] / count;
+    double var = stats[d + c] / count - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float mean_f = static_cast<float>(mu);
+    const float rstd_f = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    sc[j] = rstd_f * __ldg(bn_w + c);
+    sh[j] = __ldg(bn_b + c) - mean_f * sc[j];
+    if (blockIdx.x == 0 && tr == 0) {
+      mean_out[c] = mean_f;
+      rstd_out[c] = rstd_f;
+      if (running_mean) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mu);
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+      }
+    }
+  }
+  const int64_t r_end = min(rows, (static_cast<int64_t>(blockIdx.x) + 1) * rows_per_block);
+  constexpr int UN = 4;
+  for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + tr; r0 < r_end; r0 += static_cast<int64_t>(UN) * rpi) {
+    uint4 v[UN];
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const int64_t r = r0 + static_cast<int64_t>(q) * rpi;
+      if (r < r_end) v[q] = *reinterpret_cast<const uint4*>(y + r * d + tg * 8);
+    }
+#pragma unroll
+    for (int q = 0; q < UN; ++q) {
+      const int64_t r = r0 + static_cast<int64_t>(q) * rpi;
+      if (r >= r_end) break;
+      const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(w[j]);
+        o[j] = pack_bf16(silu_f(fmaf(f.x, sc[2 * j], sh[2 * j])), silu_f(fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1])));
+      }
+      *reinterpret_cast<uint4*>(out + r * d + tg * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 
 // ================================================================================================
 // backward of the chain
@@ -630,6 +692,25 @@ extern "C" int b2c_convmod_bn_apply(const void* y, const float* mean, const floa
   B2C_CUDA(launch_k(bn_apply_kernel, dim3(static_cast<unsigned>(nblk)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(y), mean, rstd, bn_w, bn_b, static_cast<__nv_bfloat16*>(out), rows, d,
       static_cast<int>(rpb)));
+  B2C_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2c_convmod_bn_finalize_apply(const void* y, const double* stats, int64_t count, float eps, float momentum,
+                                            const float* bn_w, const float* bn_b, void* out, float* mean, float* rstd,
+                                            float* running_mean, float* running_var, int64_t rows, int d, void* stream) {
+  B2C_REQUIRE(y && stats && bn_w && bn_b && out && mean && rstd && count > 0, "b2c_convmod_bn_finalize_apply: bad argument");
+  B2C_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "b2c_convmod_bn_finalize_apply: running stats mismatch");
+  B2C_REQUIRE(d % 8 == 0 && d <= 2048, "b2c_convmod_bn_finalize_apply: d must be a multiple of 8, <= 2048");
+  if (rows <= 0) return 0;
+  const int rpi = 256 / (d / 8);
+  int64_t nblk = static_cast<int64_t>(num_sms()) * 4;
+  int64_t rpb = (rows + nblk - 1) / nblk;
+  rpb = ((rpb + rpi - 1) / rpi) * rpi;
+  nblk = (rows + rpb - 1) / rpb;
+  B2C_CUDA(launch_k(bn_finalize_apply_kernel, dim3(static_cast<unsigned>(nblk)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+      static_cast<const __nv_bfloat16*>(y), stats, static_cast<double>(count), eps, momentum, bn_w, bn_b,
+      static_cast<__nv_bfloat16*>(out), mean, rstd, running_mean, running_var, rows, d, static_cast<int>(rpb)));
   B2C_CUDA(cudaGetLastError());
   return 0;
 }

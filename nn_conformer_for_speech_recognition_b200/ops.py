@@ -178,6 +178,17 @@ def convmod_bn_finalize(stats, count: int, running_mean, running_var, eps: float
     return mean, rstd
 
 
+def convmod_bn_finalize_apply(y, stats, count: int, bn_w, bn_b, running_mean, running_var, eps: float = 1e-5, momentum: float = 0.1):
+    """`convmod_bn_finalize` + `convmod_bn_apply` in one launch; returns (out, mean, rstd)."""
+    d = y.shape[1]
+    mean = torch.empty(d, device=y.device, dtype=torch.float32)
+    rstd = torch.empty(d, device=y.device, dtype=torch.float32)
+    out = torch.empty_like(y)
+    call("b2c_convmod_bn_finalize_apply", ptr(y), ptr(stats), count, eps, momentum, ptr(bn_w), ptr(bn_b), ptr(out), ptr(mean),
+         ptr(rstd), ptr(running_mean), ptr(running_var), y.shape[0], d, stream_ptr(), nbytes=2.0 * y.shape[0] * d * 2)
+    return out, mean, rstd
+
+
 def convmod_bn_apply(y, mean, rstd, bn_w, bn_b):
     out = torch.empty_like(y)
     call("b2c_convmod_bn_apply", ptr(y), ptr(mean), ptr(rstd), ptr(bn_w), ptr(bn_b), ptr(out), y.shape[0], y.shape[1],

@@ -277,6 +277,12 @@ def test_convmod_eval_and_train(ops, B, T, d, k):
     c = ops.convmod_bn_apply(y, mean, rstd, bn_w, bn_b)
     z = (y.float() - mu_ref) / torch.sqrt(var_ref + 1e-5) * bn_w + bn_b
     _close(c, torch.nn.functional.silu(z), name="bn apply")
+    # finalize + apply as ONE launch (what the training forward uses): bit-identical outputs, statistics and running stats
+    rm2, rv2 = rmean.clone(), rvar.clone()
+    c2, mean2, rstd2 = ops.convmod_bn_finalize_apply(y, stats, B * T, bn_w, bn_b, rm2, rv2)
+    assert torch.equal(mean2, mean) and torch.equal(rstd2, rstd), "fused finalize: statistics"
+    assert torch.equal(rm2, rm) and torch.equal(rv2, rv), "fused finalize: running statistics"
+    assert torch.equal(c2.view(torch.int16), c.view(torch.int16)), "fused finalize + apply: output"
 
 
 # ----------------------------------------------------------------------------------------------- attention
