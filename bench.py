@@ -367,18 +367,48 @@ class Rig:
         if pre is not None:
             pre.submit(self.x_host)
 
+        from nn_conformer_for_speech_recognition_b200.prefetch import ResultFetcher
+        fetcher = ResultFetcher(self.dev) if prefetch else None
+        state = dict(fut=None, losses=[])
+
         def e2e_step():
             if pre is None:
                 self.x_static.copy_(self.x_host, non_blocking=True)   # H2D of this step's batch from pinned memory
-                return float(self.step(self.x_static))                # D2H read of the step's result (loss / checksum)
+                state["losses"].append(float(self.step(self.x_static)))   # D2H read of the step's result (loss / checksum)
+                return
             xin = pre.get()                                           # this step's batch (copied while the previous step ran)
             pre.submit(self.x_host)                                   # H2D of the next step's batch, overlapping this step
             loss = self.step(xin)
+            nxt = fetcher.fetch(loss)                                 # D2H of THIS step's loss, enqueued in stream order
             self.host_prepare()                                       # the NEXT step's SpecAugment draws (host, CPython `random`) are made
             self._prepared = True                                     # while the GPU runs this step -- still once per step, inside the timed region
-            return float(loss)                                        # D2H read of this step's loss
+            if state["fut"] is not None:
+                state["losses"].append(state["fut"].value())          # host reads the PREVIOUS step's loss while this step runs
+            state["fut"] = nxt
+
+        def e2e_drain():
+            if state["fut"] is not None:
+                state["losses"].append(state["fut"].value())
+                state["fut"] = None
         e2e_step()
-        e2e_ms = self.timed(e2e_step, steps)
+        e2e_drain()
+        # ONE event pair around all K steps (host launch gaps between steps are inside it); the L2-flush fills between steps
+        # are timed by their own event pairs and subtracted.  The last step's loss is read before the clock stops.
+        torch.cuda.synchronize()
+        n0 = len(state["losses"])
+        fl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_a.record()
+        for f0, f1 in fl:
+            f0.record()
+            self.flush.zero_()
+            f1.record()
+            e2e_step()
+        e2e_drain()
+        ev_b.record()
+        torch.cuda.synchronize()
+        assert len(state["losses"]) - n0 == steps, "every step's result must have been read back inside the timed region"
+        e2e_ms = [(ev_a.elapsed_time(ev_b) - sum(f0.elapsed_time(f1) for f0, f1 in fl)) / steps] * steps
         self.barrier()
         tot = torch.tensor([sum(ms), sum(e2e_ms)], device=self.dev, dtype=torch.float64)
         if self.world > 1:
@@ -653,7 +683,11 @@ def main():
                 e2e=dict(value=e2e_val, unit="audio-s/s", h2d_bytes_per_step=rig.x_host.numel() * 4 * world,
                          d2h_bytes_per_step=4 * world, ms_per_step=m["e2e_ms"],
                          input=("next batch copied on a copy stream during the step (HostPrefetcher, 2 device buffers)"
-                                if m["prefetch"] else "copied in front of each step")),
+                                if m["prefetch"] else "copied in front of each step"),
+                         result=("loss of step n copied to pinned memory in stream order and read by the host while step n+1 "
+                                 "runs (ResultFetcher); all K losses are read before the clock stops"
+                                 if m["prefetch"] else "loss.item() behind every step"),
+                         timing="one CUDA-event pair around all K steps (host launch gaps included) minus the timed L2-flush fills"),
                 gpu_launches=m["launches"])
     fl = model_flops_fwd(cfg, B, T, Tp) * (3 if args.mode == "train" else 1)
     line["model_tflops_executed"] = fl * world / (m["ms"] / 1e3) / 1e12

@@ -13,6 +13,20 @@ The reference feeds its model straight from the DataLoader (`/root/reference/lib
 
 Two device buffers alternate.  A buffer is refilled only after the work that was enqueued on the consumer stream up to
 the NEXT `get()` has finished with it (event recorded there), so `x` stays valid until the second `get()` after it.
+
+`ResultFetcher` is the same idea in the other direction: the reference reads `loss.item()` right behind every step
+(`runner.py:147-149`), which parks the host until the GPU has drained and leaves the GPU idle while the host launches the next
+step.  `fetch(t)` enqueues the device -> pinned-host copy of a step's result in stream order and returns a handle; its
+`value()` is read one step later, while the next step computes:
+
+    fut = None
+    for ...:
+        loss = step(x)
+        nxt = fetcher.fetch(loss)      # D2H of THIS step's loss, asynchronous
+        if fut is not None:
+            log(fut.value())           # the previous step's loss (its copy finished long ago)
+        fut = nxt
+    log(fut.value())
 """
 from __future__ import annotations
 
@@ -65,3 +79,37 @@ class HostPrefetcher:
         self.in_flight -= 1
         self.last = i
         return self.bufs[i]
+
+
+class _Fetched:
+    def __init__(self, host: torch.Tensor, event: torch.cuda.Event):
+        self._host, self._event = host, event
+
+    def value(self) -> float:
+        """Blocks until the copy has landed (normally it has), then reads the pinned word."""
+        self._event.synchronize()
+        return float(self._host[0])
+
+    def tensor(self) -> torch.Tensor:
+        self._event.synchronize()
+        return self._host.clone()
+
+
+class ResultFetcher:
+    """Asynchronous device -> host read-back of small per-step results (loss, metric) through `depth` pinned slots."""
+
+    def __init__(self, device, numel: int = 1, dtype=torch.float32, depth: int = 4):
+        if torch.device(device).type != "cuda":
+            raise ValueError("ResultFetcher needs a CUDA device (there is no CPU fallback)")
+        self.hosts = [torch.zeros(numel, dtype=dtype).pin_memory() for _ in range(depth)]
+        self.slot = 0
+        self.bytes_per_fetch = numel * self.hosts[0].element_size()
+
+    def fetch(self, t: torch.Tensor) -> _Fetched:
+        """Enqueue the copy of `t` (numel elements) on the current stream; the slot is reused `depth` fetches later."""
+        h = self.hosts[self.slot]
+        self.slot = (self.slot + 1) % len(self.hosts)
+        h.copy_(t.detach().reshape(-1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return _Fetched(h, ev)
