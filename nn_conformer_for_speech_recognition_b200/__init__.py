@@ -16,7 +16,7 @@ from .ctc import CTCLoss, ctc_loss_from_logits  # noqa: F401
 from .encoder import ConformerEncoder, Linear  # noqa: F401
 from .frontend import LogMelFrontend, PaddedBatcher  # noqa: F401
 from .lstm import LSTM, lstm_from_reference  # noqa: F401
-from .prefetch import HostPrefetcher  # noqa: F401
+from .prefetch import HostPrefetcher, ResultFetcher  # noqa: F401
 from .relpos import RelativePositionalEmbeddings  # noqa: F401
 from .patch import conformer_from_torchaudio, convsub_from_reference, patch_asrnn  # noqa: F401
 
