@@ -3,11 +3,12 @@
 # sha256 of libb200conformer.so; bench.py only uses it when it matches the library it is running).
 #     gpurun --timeout 1200 -- tools/traffic_capture.sh        -> gpurun_out/r02_traffic_raw.csv, profiles/r02_traffic_train.json
 set -u
-CMD="python bench.py --no-graph --steps 1 --warmup 3 --no-cpu-baseline --no-instrument --no-secondary --no-parity"
+CMD="python bench.py --no-graph --steps 1 --warmup 2 --no-cpu-baseline --no-instrument --no-secondary --no-parity"
 mkdir -p gpurun_out
 $CMD > gpurun_out/traffic_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/traffic_plain.log; exit 1; }
-# skip the first step (lazy initialisation), take the next ~2 steps of this library's kernels
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:b2c:: -s 800 -c 1600 \
+# skip the first two steps (lazy initialisation, warm-up), take ONE step's worth of this library's launches (704 per step;
+# any 704 consecutive launches are one full step cyclically)
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:b2c:: -s ${TRAFFIC_SKIP:-1430} -c ${TRAFFIC_COUNT:-704} \
     --csv --log-file gpurun_out/r02_traffic_raw.csv $CMD > gpurun_out/traffic_ncu.log 2>&1
 echo "ncu rc=$?"
 python tools/traffic_summary.py gpurun_out/r02_traffic_raw.csv gpurun_out/r02_traffic_kernels.json | head -20
@@ -15,7 +16,7 @@ python - <<'PY'
 import hashlib, json
 k = json.load(open("gpurun_out/r02_traffic_kernels.json"))
 h = hashlib.sha256(open("nn_conformer_for_speech_recognition_b200/libb200conformer.so", "rb").read()).hexdigest()[:16]
-json.dump(dict(lib_sha256_16=h, command="ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:b2c -s 800 -c 1600 python bench.py --no-graph --steps 1 --warmup 3 ...",
+json.dump(dict(lib_sha256_16=h, command="ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:b2c:: -s 1430 -c 704 python bench.py --no-graph --steps 1 --warmup 2 ... (one eager training step)",
                kernels=k), open("gpurun_out/r02_traffic_train.json", "w"), indent=1)
 print("lib", h)
 PY
