@@ -40,6 +40,15 @@ for rep in range(2):
     c = ops.convmod_bn_apply(yy, mean_c, rstd_c, one, zero)
     sums = ops.convmod_bn_bwd_reduce(c, yy, mean_c, rstd_c, one, zero)
     ops.convmod_dw_bwd(c, yy, uu, mean_c, rstd_c, one, zero, sums, True, wdw, torch.zeros(d, k, device=dev), torch.zeros(d, device=dev), dg, db, B, T)
+    c2, mean_c2, rstd_c2 = ops.convmod_bn_finalize_apply(yy, stats, M, one, zero, None, None)                         # finalize + apply, one launch
+    y1, m1, r1, a2, m2, r2 = ops.layernorm_fwd_pair(x, g, be, g, be, save_stats=True)                                   # LayerNorm pair fwd
+    dxp = torch.empty_like(x)
+    ops.layernorm_bwd_pair(a2, y1, g, m2, r2, dg, db, dx, x, g, m1, r1, dg, db, dxp, cast=(0.5, 0.5, 9, torch.zeros(d, device=dev)))   # pair bwd
+    W1c, b1c = torch.randn(512, 1, 7, 7, device=dev) / 7, torch.zeros(512, device=dev)
+    W2c, b2c_ = torch.randn(128, 512, 3, 3, device=dev) / 68, torch.zeros(128, device=dev)
+    Wc, bc = ops.convsub_compose(W1c, b1c, W2c, b2c_, 2, 128)                                                          # staged composition
+    ops.convsub_compose_bwd(torch.randn(128, 128, device=dev), torch.randn(128, device=dev), W1c, b1c, W2c, 2,
+                            torch.zeros_like(W1c), torch.zeros_like(b1c), torch.zeros_like(W2c), torch.zeros_like(b2c_))
     logits = torch.randn(B, T, 1024, device=dev, requires_grad=True)
     ctc_loss_from_logits(logits, torch.randint(1, 1024, (B, 20), device=dev), [T] * B, [20] * B).backward()
 torch.cuda.synchronize()
