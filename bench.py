@@ -458,23 +458,35 @@ class Rig:
 
 
 def lib_hash():
-    from nn_conformer_for_speech_recognition_b200 import _lib
+    """Identity of the kernel code: sha256 over the library's SOURCES (csrc/*, the C header), not over the .so -- nvcc embeds
+    per-build identifiers, so two builds of the same sources differ in a few dozen bytes and a binary hash would never match
+    on a box that rebuilt the library."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "nn_conformer_for_speech_recognition_b200", "csrc", "*.cu")) +
+                   glob.glob(os.path.join(ROOT, "nn_conformer_for_speech_recognition_b200", "csrc", "*.cuh")) +
+                   glob.glob(os.path.join(ROOT, "nn_conformer_for_speech_recognition_b200", "csrc", "*.cpp")) +
+                   glob.glob(os.path.join(ROOT, "nn_conformer_for_speech_recognition_b200", "csrc", "Makefile")) +
+                   glob.glob(os.path.join(ROOT, "include", "*.h")))
+    h = hashlib.sha256()
     try:
-        return hashlib.sha256(open(_lib.LIB_PATH, "rb").read()).hexdigest()[:16]
+        for f in files:
+            h.update(os.path.basename(f).encode())
+            h.update(open(f, "rb").read())
     except OSError:
         return None
+    return h.hexdigest()[:16] if files else None
 
 
 def load_traffic(mode, model):
-    """DRAM bytes per launch from the committed ncu capture -- used ONLY when it was taken from this very binary (the
-    capture records the sha256 of libb200conformer.so; see tools/traffic_capture.sh)."""
+    """DRAM bytes per launch from the committed ncu capture -- used ONLY when it was taken from this very kernel code (the
+    capture records the sha256 of the library's sources, `lib_hash()`; see tools/traffic_capture.sh)."""
     p = os.path.join(ROOT, "profiles", "r02_traffic_train.json")
     if not (mode == "train" and model == "M" and os.path.exists(p)):
         return {}, "no ncu traffic capture for this mode/model"
     d = json.load(open(p))
-    if d.get("lib_sha256_16") != lib_hash():
-        return {}, f"profiles/r02_traffic_train.json was captured from another build ({d.get('lib_sha256_16')}); not used"
-    return d.get("kernels", {}), "mean DRAM bytes per launch, ncu capture of one eager step of this binary (profiles/r02_traffic_train.json)"
+    if d.get("src_sha256_16") != lib_hash():
+        return {}, f"profiles/r02_traffic_train.json was captured from other kernel sources ({d.get('src_sha256_16')}); not used"
+    return d.get("kernels", {}), "mean DRAM bytes per launch, ncu capture of one eager step of these kernel sources (profiles/r02_traffic_train.json)"
 
 
 def parity_check(rig):

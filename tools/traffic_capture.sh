@@ -1,6 +1,6 @@
 #!/bin/bash
-# DRAM traffic per kernel of ONE eager training step of bench.py, captured with ncu from THIS binary (the capture records the
-# sha256 of libb200conformer.so; bench.py only uses it when it matches the library it is running).
+# DRAM traffic per kernel of ONE eager training step of bench.py, captured with ncu from THESE kernel sources (the capture
+# records bench.lib_hash(), a sha256 over csrc/ and the C header; bench.py only uses it when it matches the sources it runs).
 #     gpurun --timeout 1200 -- tools/traffic_capture.sh        -> gpurun_out/r02_traffic_raw.csv, profiles/r02_traffic_train.json
 set -u
 CMD="python bench.py --no-graph --steps 1 --warmup 2 --no-cpu-baseline --no-instrument --no-secondary --no-parity"
@@ -13,10 +13,12 @@ ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum 
 echo "ncu rc=$?"
 python tools/traffic_summary.py gpurun_out/r02_traffic_raw.csv gpurun_out/r02_traffic_kernels.json | head -20
 python - <<'PY'
-import hashlib, json
+import json, sys
+sys.path.insert(0, ".")
+import bench
 k = json.load(open("gpurun_out/r02_traffic_kernels.json"))
-h = hashlib.sha256(open("nn_conformer_for_speech_recognition_b200/libb200conformer.so", "rb").read()).hexdigest()[:16]
-json.dump(dict(lib_sha256_16=h, command="ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:b2c:: -s 1430 -c 704 python bench.py --no-graph --steps 1 --warmup 2 ... (one eager training step)",
+h = bench.lib_hash()
+json.dump(dict(src_sha256_16=h, command="ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:b2c:: -s 1430 -c 704 python bench.py --no-graph --steps 1 --warmup 2 ... (one eager training step)",
                kernels=k), open("gpurun_out/r02_traffic_train.json", "w"), indent=1)
-print("lib", h)
+print("kernel sources", h)
 PY
