@@ -174,3 +174,30 @@ def test_lstm_is_an_nn_lstm_with_the_same_parameters_and_no_cpu_path():
     if not torch.cuda.is_available():
         with pytest.raises(b2c.B2CError):
             ours(torch.zeros(3, 2, 256))
+
+
+def test_prefetch_helpers_refuse_cpu_devices():
+    """HostPrefetcher / ResultFetcher are CUDA plumbing (copy stream, pinned slots, events): no CPU path, loud errors."""
+    with pytest.raises(ValueError):
+        b2c.HostPrefetcher((2, 3), "cpu")
+    with pytest.raises(ValueError):
+        b2c.ResultFetcher("cpu")
+
+
+def test_traffic_capture_is_keyed_to_the_kernel_sources():
+    """bench.lib_hash() identifies the kernel code by its SOURCES (nvcc builds are not bit-reproducible); the committed ncu
+    traffic capture carries the hash of the sources it was taken from, and bench.py ignores it when they differ."""
+    import importlib
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    h = bench.lib_hash()
+    assert isinstance(h, str) and len(h) == 16 and h == bench.lib_hash()
+    cap = json.load(open(os.path.join(root, "profiles", "r02_traffic_train.json")))
+    assert "src_sha256_16" in cap and "kernels" in cap
+    kernels, note = bench.load_traffic("train", "M")
+    assert (len(kernels) > 0) == (cap["src_sha256_16"] == h), note
+    assert bench.load_traffic("infer", "M")[0] == {}
