@@ -60,6 +60,17 @@ def _split_k(tokens: int, out_tiles: int, sms: int = 148) -> int:
     return max(1, min(want, kb // 4 if kb >= 4 else 1))
 
 
+def defer_first_layernorm(li: int, d: int, exchange_active: bool, group_lo) -> bool:
+    """Backward-pass scheduling rule of the LayerNorm pairs: layer `li` may leave the backward of its first LayerNorm
+    (ffn1.sequential.0) to the pair kernel that opens layer li-1's backward pass -- unless there is no layer below, the
+    width has no pair instantiation worth running (d > 512: 255 registers, spills), or `li` is the first layer of a
+    gradient-exchange group: that group's span of the gradient arena is handed to the all-reduce at the END of layer li's
+    backward pass and must be final by then (dp.GradSync.attach; `group_lo` maps a group's first layer to one past its last)."""
+    if not _LN_PAIR or li <= 0 or d > 512:
+        return False
+    return not (exchange_active and li in group_lo)
+
+
 class _ConformerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inp, lengths_i32, model, *params):
@@ -258,7 +269,7 @@ class _ConformerFn(torch.autograd.Function):
 
             # ---- 1. FFN1 (its LayerNorm is deferred into the pair kernel of the layer below, unless this layer's gradients
             # are about to be handed to the gradient exchange: a span must be final when it leaves)
-            defer = _LN_PAIR and li > 0 and d <= 512 and not (gsync is not None and li in group_lo)
+            defer = defer_first_layernorm(li, d, gsync is not None, group_lo)
             r = ffn_bwd("ffn1", 0, dyb, None, defer)
             pending = r if defer else None
             ctx.state[li] = None                  # free this layer's saved activations

@@ -201,3 +201,20 @@ def test_traffic_capture_is_keyed_to_the_kernel_sources():
     kernels, note = bench.load_traffic("train", "M")
     assert (len(kernels) > 0) == (cap["src_sha256_16"] == h), note
     assert bench.load_traffic("infer", "M")[0] == {}
+
+
+def test_layernorm_pair_deferral_never_crosses_a_gradient_exchange_boundary():
+    """autograd.defer_first_layernorm: the first LayerNorm of layer li may be left to the pair kernel of layer li-1 only if the
+    gradient span that contains it has not been handed to the all-reduce yet (groups of dp.GradSync.attach)."""
+    from nn_conformer_for_speech_recognition_b200 import autograd as ag
+    L, ng = 16, 4
+    bounds = [round(i * L / ng) for i in range(ng + 1)]
+    group_lo = {bounds[i]: bounds[i + 1] for i in range(ng)}
+    if not ag._LN_PAIR:
+        pytest.skip("B2C_LN_PAIR=0")
+    for li in range(L):
+        single = ag.defer_first_layernorm(li, 256, False, {})
+        multi = ag.defer_first_layernorm(li, 256, True, group_lo)
+        assert single == (li > 0)                       # layer 0 has no layer below
+        assert multi == (li > 0 and li not in group_lo)  # first layer of a group: its span leaves at the end of this layer
+        assert not ag.defer_first_layernorm(li, 1024, False, {})
